@@ -1,0 +1,188 @@
+"""Seeded synthetic workloads for the geometry path (frames, heatmaps, boxes, point sets).
+
+There are no datasets or checkpoints offline, so every test and benchmark runs on synthetic data
+of the reference's shapes: a broadcast-like camera homography per frame,
+Gaussian landmark peaks rendered into (57, 135, 240) float32 heatmaps at the positions
+``KeypointModel`` would emit them (keypoint_hrnet.py:590-591: x/(W-1), y/(H-1) normalisation), and
+detector-shaped boxes whose foot points fall on the pitch.  CPU (numpy) generation serves the
+tests and the CPU baseline; ``*_device`` variants generate directly in HBM for the benchmark.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .pitch import NUM_LANDMARKS, OFF_PLANE, PITCH_LENGTH_M, PITCH_WIDTH_M, WORLD_XYZ
+
+HM_H, HM_W = 135, 240  # HRNet-W48 branch-0 resolution for a 540x960 input (keypoint_hrnet.py:481)
+
+# image(1280x720) -> pitch homography of a typical main-camera view
+_BASE_IMG_TO_PITCH_720P = np.array([[0.09, -0.02, -5.0], [0.004, 0.16, -20.0], [1e-5, 6e-4, 1.0]])
+
+
+def sample_cameras(n: int, width: int, height: int, rng: np.random.Generator) -> np.ndarray:
+    """(n, 3, 3) float64 pitch->image homographies: pans/zooms/perturbations of the base view."""
+    base = np.linalg.inv(_BASE_IMG_TO_PITCH_720P)  # pitch -> 720p image
+    S = np.diag([width / 1280.0, height / 720.0, 1.0])
+    out = np.empty((n, 3, 3))
+    for i in range(n):
+        pan = np.eye(3)
+        pan[0, 2] = rng.uniform(-420.0, 420.0)  # px at 720p
+        pan[1, 2] = rng.uniform(-40.0, 60.0)
+        z = rng.uniform(0.8, 1.5)
+        zoom = np.array([[z, 0, 640.0 * (1 - z)], [0, z, 360.0 * (1 - z)], [0, 0, 1.0]])
+        pert = np.eye(3) + rng.normal(0.0, 1.0, (3, 3)) * np.array([[2e-2, 2e-2, 0], [2e-2, 2e-2, 0], [2e-6, 2e-6, 0]])
+        H = S @ zoom @ pan @ base @ pert
+        out[i] = H / H[2, 2]
+    return out
+
+
+def project_points(H: np.ndarray, pts: np.ndarray) -> np.ndarray:
+    p = np.c_[pts, np.ones(len(pts))] @ H.T
+    return p[:, :2] / p[:, 2:3]
+
+
+def landmark_pixels(cam: np.ndarray, width: int, height: int, margin: float = 4.0):
+    """Image positions of the 57 landmarks under ``cam`` and a visibility mask (inside the frame).
+
+    Off-plane landmarks (cross-bar ends) are drawn above their goal-line foot; they are never
+    used for the fit (pitch.OFF_PLANE) but do appear in the heatmaps like any other channel.
+    """
+    px = project_points(cam, WORLD_XYZ[:, :2])
+    for ch in OFF_PLANE:
+        px[ch, 1] -= 0.06 * height
+    vis = (px[:, 0] >= margin) & (px[:, 0] <= width - 1 - margin) & (px[:, 1] >= margin) & (px[:, 1] <= height - 1 - margin)
+    p = np.c_[WORLD_XYZ[:, :2], np.ones(NUM_LANDMARKS)] @ cam.T
+    vis &= p[:, 2] > 0
+    return px, vis
+
+
+def render_heatmaps(px: np.ndarray, vis: np.ndarray, width: int, height: int, rng: np.random.Generator,
+                    peak: float = 0.9, sigma: float = 1.5, background: float = 0.05, jitter: float = 0.3) -> np.ndarray:
+    """(57, 135, 240) float32: U(0, background) noise plus one Gaussian bump per visible landmark."""
+    hm = rng.uniform(0.0, background, (NUM_LANDMARKS, HM_H, HM_W)).astype(np.float32)
+    ys, xs = np.mgrid[0:HM_H, 0:HM_W]
+    for ch in np.nonzero(vis)[0]:
+        cx = px[ch, 0] / width * (HM_W - 1) + rng.normal(0.0, jitter)
+        cy = px[ch, 1] / height * (HM_H - 1) + rng.normal(0.0, jitter)
+        g = peak * np.exp(-((xs - cx) ** 2 + (ys - cy) ** 2) / (2.0 * sigma * sigma))
+        hm[ch] += g.astype(np.float32)
+    np.clip(hm, 0.0, 1.0, out=hm)
+    return hm
+
+
+def sample_objects(cam: np.ndarray, width: int, height: int, rng: np.random.Generator,
+                   n_players: int = 20, n_goalkeepers: int = 2, ball: bool = True) -> dict:
+    """A ``detect_objects``-shaped dict (coordinate_model.py:557-628): clipped int boxes, confidences,
+    ``Bottom_center = [int((x1+x2)/2), y2]``.  Most foot points fall on the visible pitch; a few
+    are placed off it so that the out-of-bounds branch (:385-386) is exercised."""
+    out = {"Player": {}, "Goalkeeper": {}}
+    inv = np.linalg.inv(cam)
+    s = height / 720.0
+    next_id = 1
+
+    def one_box(w_px, h_px):
+        for _ in range(50):
+            foot = np.array([rng.uniform(0.05, 0.95) * width, rng.uniform(0.30, 0.97) * height])
+            wp = project_points(inv, foot[None])[0]
+            if rng.uniform() < 0.08 or (0 <= wp[0] <= PITCH_LENGTH_M and 0 <= wp[1] <= PITCH_WIDTH_M):
+                break
+        x1 = int(np.clip(foot[0] - w_px / 2, 0, width - 1)); x2 = int(np.clip(foot[0] + w_px / 2, 0, width - 1))
+        y2 = int(np.clip(foot[1], 0, height - 1)); y1 = int(np.clip(foot[1] - h_px, 0, height - 1))
+        return [x1, y1, x2, y2]
+
+    for cls, count in (("Player", n_players), ("Goalkeeper", n_goalkeepers)):
+        for _ in range(count):
+            box = one_box(rng.uniform(30, 50) * s, rng.uniform(70, 110) * s)
+            out[cls][next_id] = {"BBox": box, "Confidence": float(rng.uniform(0.4, 0.95)),
+                                 "Bottom_center": [int((box[0] + box[2]) / 2), box[3]]}
+            next_id += 1
+    if ball:
+        b = one_box(10 * s, 10 * s)
+        box = np.array(b)  # the reference keeps the ball box as an int ndarray (:622,627)
+        out["Ball"] = {0: {"BBox": box, "Confidence": float(rng.uniform(0.4, 0.9)),
+                           "Bottom_center": [int((box[0] + box[2]) / 2), box[3]]}}
+    return out
+
+
+def make_clip(n_frames: int, width: int, height: int, seed: int = 0, with_frames: bool = False,
+              hide_prob: float = 0.1, ghost_prob: float = 0.0):
+    """A synthetic clip: dict(cameras, heatmaps (F,57,135,240) f32, objects list, frames or None).
+
+    hide_prob drops a visible landmark's bump (missed detection); ghost_prob adds a bump for a
+    landmark at a wrong place (outlier correspondence).
+    """
+    rng = np.random.default_rng(seed)
+    cams = sample_cameras(n_frames, width, height, rng)
+    heat = np.empty((n_frames, NUM_LANDMARKS, HM_H, HM_W), np.float32)
+    objs = []
+    for i in range(n_frames):
+        px, vis = landmark_pixels(cams[i], width, height)
+        vis = vis & (rng.uniform(size=NUM_LANDMARKS) >= hide_prob)
+        if ghost_prob > 0:
+            ghosts = rng.uniform(size=NUM_LANDMARKS) < ghost_prob
+            px = px.copy()
+            px[ghosts] = rng.uniform([8, 8], [width - 9, height - 9], (int(ghosts.sum()), 2))
+            vis = vis | ghosts
+        heat[i] = render_heatmaps(px, vis, width, height, rng)
+        objs.append(sample_objects(cams[i], width, height, rng))
+    frames = None
+    if with_frames:
+        frames = rng.integers(0, 256, (n_frames, height, width, 3), dtype=np.uint8)
+    return {"cameras": cams, "heatmaps": heat, "objects": objs, "frames": frames, "width": width, "height": height}
+
+
+def objects_to_arrays(objs: list, max_points: int):
+    """Pack detect_objects() dicts into the flat arrays the C ABI takes.
+
+    Returns foot (F, P, 2) float32 (Bottom_center per object, reference iteration order: class
+    dict order, then id order) and count (F,) int32.
+    """
+    F = len(objs)
+    foot = np.zeros((F, max_points, 2), np.float32)
+    count = np.zeros(F, np.int32)
+    for i, o in enumerate(objs):
+        k = 0
+        for cls in o:
+            for _id, d in o[cls].items():
+                if k >= max_points:
+                    raise ValueError(f"frame {i}: more than {max_points} objects")
+                foot[i, k] = d["Bottom_center"]
+                k += 1
+        count[i] = k
+    return foot, count
+
+
+def stress_point_sets(n_frames: int, width: int, height: int, seed: int = 0, outlier_frac: float = 0.4,
+                      noise_px: float = 0.5):
+    """RANSAC stress inputs (BASELINE.json configs[3]): all 53 on-plane landmarks present, a fraction
+    replaced by gross outliers (>= 15 m off in pitch space), inliers with sub-pixel noise, rounded to
+    integer pixels.  Returns (kp_xy (F,57,2) int32, valid mask (F,) uint64, outlier flags (F,57) bool,
+    cameras)."""
+    rng = np.random.default_rng(seed)
+    on = np.array([i for i in range(NUM_LANDMARKS) if i not in OFF_PLANE])
+    n_out = int(round(outlier_frac * len(on)))
+    kp = np.zeros((n_frames, NUM_LANDMARKS, 2), np.int32)
+    flags = np.zeros((n_frames, NUM_LANDMARKS), bool)
+    cams = np.empty((n_frames, 3, 3))
+    base = np.linalg.inv(_BASE_IMG_TO_PITCH_720P)
+    S = np.diag([width / 1280.0, height / 720.0, 1.0])
+    for f in range(n_frames):
+        # a wide view that keeps every landmark in front of the camera
+        pert = np.eye(3) + rng.normal(0.0, 1.0, (3, 3)) * np.array([[1e-2, 1e-2, 0], [1e-2, 1e-2, 0], [1e-6, 1e-6, 0]])
+        cam = S @ base @ pert
+        cam /= cam[2, 2]
+        cams[f] = cam
+        px = project_points(cam, WORLD_XYZ[:, :2]) + rng.normal(0.0, noise_px, (NUM_LANDMARKS, 2))
+        inv = np.linalg.inv(cam)
+        out_idx = rng.choice(on, n_out, replace=False)
+        for ch in out_idx:
+            for _ in range(100):
+                cand = rng.uniform([0, 0], [width, height])
+                wp = project_points(inv, cand[None])[0]
+                if np.hypot(*(wp - WORLD_XYZ[ch, :2])) >= 15.0:
+                    break
+            px[ch] = cand
+        flags[f, out_idx] = True
+        kp[f] = np.rint(px).astype(np.int32)
+    valid = np.full(n_frames, sum(1 << int(i) for i in on), np.uint64)
+    return kp, valid, flags, cams
