@@ -1,0 +1,204 @@
+"""Drop-in host adapter: the reference's processor-level call signatures over the CUDA path.
+
+Mirrors ``eagle.models.coordinate_model.CoordinateModel`` for the geometry path:
+
+    model = CoordinateModel(keypoint_model=..., detect_objects=...)
+    coords = model.get_coordinates(frames, fps, num_homography=1, num_keypoint_detection=1)
+
+returns the dict ``Processor.__init__`` takes (eagle/processor.py:65-68) and docs/data.md:20-42
+documents: ``{frame_idx: {"Coordinates", "Time", "Keypoints", "Boundaries"}}``.
+
+What runs where
+  * the two networks are NOT part of this package: ``keypoint_model`` is any callable mapping a
+    (N,3,540,960) float32 CUDA tensor to (N,57,135,240) heatmaps (the reference's HRNet-W48 +
+    sigmoid, keypoint_hrnet.py:565-573); ``detect_objects`` is any callable frame -> boxes dict
+    (coordinate_model.py:557-628, YOLO + BoT-SORT);
+  * preprocessing, heatmap decode, keypoint synthesis, homography fit, cadence selection and
+    projection are CUDA kernels (eagle_b200/csrc) called through the C ABI;
+  * this module only moves data and assembles Python dicts.
+
+Cadence: the homography cadence (``num_homography``, retry after a failed fit, reuse of the
+previous H) is reproduced exactly.  Keypoint cadence other than "every frame" needs Lucas-Kanade
+optical-flow propagation between network frames (coordinate_model.py:419-478), which is outside
+this path; ``num_keypoint_detection`` must therefore give a keypoint interval of 1.
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .engine import GeometryEngine
+from .pitch import LANDMARK_NAMES, OFF_PLANE, PITCH_LENGTH_M, PITCH_WIDTH_M
+from .synthetic import objects_to_arrays
+
+BATCH = 4  # reference's HRNet batch (coordinate_model.py:20); only the chunking of the network calls
+
+
+def frame_time(i: int, fps: int) -> str:
+    """coordinate_model.py:415."""
+    return f"{i // fps // 60:02d}:{i // fps % 60:02d}"
+
+
+def assemble_frames(objects_per_frame, fps: int, first_index: int, kp_xy, kp_order, kp_count, used_mask, inlier_mask,
+                    status, attempted, h_index, coords_i, in_bounds, bounds) -> dict:
+    """Host-side dict assembly (coordinate_model.py:359-362, 369-392, 405-415) from the arrays the
+    kernels produced (all numpy, already on the host)."""
+    res = {}
+    off = set(OFF_PLANE)
+    for k, objects in enumerate(objects_per_frame):
+        i = first_index + k
+        # --- "Keypoints": inliers as float lists when this frame's fit was used, else all keypoints
+        n = int(kp_count[k, 0])
+        chans = [int(c) for c in kp_order[k, :n]]
+        if attempted[k] and status[k] == N.FIT_OK:
+            inl = int(inlier_mask[k])
+            keypoints = {LANDMARK_NAMES[c]: [float(kp_xy[k, c, 0]), float(kp_xy[k, c, 1])]
+                         for c in chans if c not in off and (inl >> c) & 1}
+        else:
+            keypoints = {LANDMARK_NAMES[c]: (int(kp_xy[k, c, 0]), int(kp_xy[k, c, 1])) for c in chans}
+        # --- "Coordinates"
+        have_h = h_index[k] >= 0
+        indiv = {}
+        p = 0
+        for class_name, class_dict in objects.items():
+            for obj_id, obj in class_dict.items():
+                bbox = np.array(obj["BBox"], dtype=np.uint16).tolist()
+                if have_h and in_bounds[k, p]:
+                    curr = {int(obj_id): {"BBox": bbox, "Confidence": obj["Confidence"],
+                                          "Transformed_Coordinates": [int(coords_i[k, p, 0]), int(coords_i[k, p, 1])]}}
+                else:
+                    curr = {int(obj_id): {"BBox": bbox, "Confidence": obj["Confidence"], "Transformed_Coordinates": None,
+                                          "Image_Bottom_center": obj["Bottom_center"]}}
+                p += 1
+                if class_name not in indiv:
+                    indiv[class_name] = curr
+                else:
+                    indiv[class_name].update(curr)
+        # --- "Boundaries"
+        b = bounds[k]
+        if have_h and not np.isnan(b[0]):
+            boundaries = [(float(b[0]), 0), (float(b[1]), PITCH_WIDTH_M), (float(b[2]), PITCH_WIDTH_M), (float(b[3]), 0)]
+        else:
+            boundaries = [None, None, None, None]
+        res[i] = {"Coordinates": indiv, "Time": frame_time(i, fps), "Keypoints": keypoints, "Boundaries": boundaries}
+    return res
+
+
+class GeometryPath:
+    """decode -> synthesis -> fit -> cadence -> projection for frames whose heatmaps and boxes exist."""
+
+    def __init__(self, device="cuda:0", keypoint_conf: float = 0.3, synthesis: bool = True, fit_mode: int = N.FIT_CV2_COMPAT,
+                 max_iters: int = 2000, thr: float = 5.0):
+        self.engine = GeometryEngine(device)
+        self.keypoint_conf = keypoint_conf
+        self.synthesis = synthesis
+        self.fit_mode = fit_mode
+        self.max_iters = max_iters
+        self.thr = thr
+
+    def run_device(self, heatmaps: torch.Tensor, foot: torch.Tensor, count: torch.Tensor, width: int, height: int,
+                   homography_interval: int = 1):
+        """All kernels for one chunk, nothing copied to the host.  Returns (kp, fit, h_index, attempted, proj)."""
+        e = self.engine
+        kp = e.decode(heatmaps, width, height, self.keypoint_conf)
+        if self.synthesis:
+            e.synthesize(kp)
+        fit = e.fit(kp, mode=self.fit_mode, K=self.max_iters, thr=self.thr)
+        h_index, attempted = e.select(fit.status, homography_interval)
+        proj = e.project(fit.H, foot, count, width, height, h_index=h_index)
+        return kp, fit, h_index, attempted, proj
+
+    def run(self, heatmaps: torch.Tensor, objects_per_frame: Sequence[dict], width: int, height: int, fps: int,
+            homography_interval: int = 1, first_index: int = 0) -> dict:
+        """heatmaps (F,57,h,w) float32 CUDA tensor + detect_objects() dicts -> reference result dict."""
+        max_pts = max(1, max(sum(len(v) for v in o.values()) for o in objects_per_frame))
+        foot_h, count_h = objects_to_arrays(list(objects_per_frame), max_pts)
+        dev = self.engine.device
+        foot = torch.from_numpy(foot_h).to(dev, non_blocking=True)
+        count = torch.from_numpy(count_h).to(dev, non_blocking=True)
+        kp, fit, h_index, attempted, proj = self.run_device(heatmaps, foot, count, width, height, homography_interval)
+        c = lambda t: t.cpu().numpy()
+        return assemble_frames(objects_per_frame, fps, first_index, c(kp.xy), c(kp.order), c(kp.count), c(fit.used_mask),
+                               c(fit.inlier_mask), c(fit.status), c(attempted), c(h_index), c(proj.coords_i),
+                               c(proj.in_bounds), c(proj.bounds))
+
+
+class CoordinateModel:
+    """Reference-shaped front end (constructor kwargs and method names of
+    eagle/models/coordinate_model.py:49,188,480,557)."""
+
+    def __init__(self, keypoint_conf: float = 0.3, detector_conf: float = 0.35, *, keypoint_model: Callable | None = None,
+                 detect_objects: Callable | None = None, device="cuda:0", chunk: int = 64):
+        self.device = torch.device(device)
+        self.keypoint_conf = keypoint_conf
+        self.detector_conf = detector_conf
+        self.keypoint_model = keypoint_model
+        self._detect_objects = detect_objects
+        self.chunk = chunk
+        self.path = GeometryPath(device, keypoint_conf)
+
+    def detect_objects(self, frame: np.ndarray) -> dict:
+        if self._detect_objects is None:
+            raise RuntimeError("no detector attached: pass detect_objects=<callable frame -> boxes dict>")
+        return self._detect_objects(frame)
+
+    @torch.no_grad()
+    def _heatmaps(self, frames: Sequence[np.ndarray]) -> torch.Tensor:
+        if self.keypoint_model is None:
+            raise RuntimeError("no keypoint network attached: pass keypoint_model=<callable tensor -> heatmaps>")
+        host = torch.from_numpy(np.ascontiguousarray(np.stack(frames)))
+        dev_frames = host.pin_memory().to(self.device, non_blocking=True)
+        x = self.path.engine.preprocess(dev_frames)
+        outs = [self.keypoint_model(x[i:i + BATCH]) for i in range(0, x.shape[0], BATCH)]
+        return torch.cat(outs).to(torch.float32).contiguous()
+
+    @torch.no_grad()
+    def detect_keypoints(self, frame: np.ndarray) -> dict:
+        """coordinate_model.py:480-518: {label: (xi, yi)} for one BGR frame."""
+        h, w = frame.shape[:2]
+        kp = self.path.engine.decode(self._heatmaps([frame]), w, h, self.keypoint_conf)
+        n = int(kp.count[0, 0])
+        order = kp.order[0, :n].cpu().numpy()
+        xy = kp.xy[0].cpu().numpy()
+        return {LANDMARK_NAMES[int(c)]: (int(xy[c, 0]), int(xy[c, 1])) for c in order}
+
+    def get_coordinates(self, frames, fps: int, num_homography: int = 1, num_keypoint_detection: int = 1,
+                        verbose: bool = True, calibration: bool = False) -> dict:
+        """coordinate_model.py:188-417."""
+        homography_interval = max(1, int(fps / max(1, num_homography)))
+        keypoint_interval = max(1, int(fps / max(1, num_keypoint_detection)))
+        if keypoint_interval != 1:
+            raise NotImplementedError("keypoint cadence other than every frame needs optical-flow propagation "
+                                      "(coordinate_model.py:419-478), which is outside the accelerated path")
+        if calibration:
+            raise NotImplementedError("brightness calibration (coordinate_model.py:520-555) is outside the accelerated path")
+        res = {}
+        if len(frames) == 0:
+            return res
+        height, width = frames[0].shape[:2]
+        # cadence state crosses chunk boundaries through carry_in; chunks keep memory bounded
+        all_obj = [self.detect_objects(f) for f in frames]
+        # the select kernel needs the whole clip's statuses, so fit per chunk first, then select+project once
+        e = self.path.engine
+        kps, fits = [], []
+        for s in range(0, len(frames), self.chunk):
+            hm = self._heatmaps(frames[s:s + self.chunk])
+            kp = e.decode(hm, width, height, self.keypoint_conf)
+            e.synthesize(kp)
+            kps.append(kp)
+            fits.append(e.fit(kp))
+        cat = lambda xs: torch.cat(xs) if len(xs) > 1 else xs[0]
+        status = cat([f.status for f in fits]); Hs = cat([f.H for f in fits])
+        h_index, attempted = e.select(status, homography_interval)
+        max_pts = max(1, max(sum(len(v) for v in o.values()) for o in all_obj))
+        foot_h, count_h = objects_to_arrays(all_obj, max_pts)
+        proj = e.project(Hs, torch.from_numpy(foot_h).to(self.device), torch.from_numpy(count_h).to(self.device), width, height,
+                         h_index=h_index)
+        c = lambda t: t.cpu().numpy()
+        return assemble_frames(all_obj, fps, 0, c(cat([k.xy for k in kps])), c(cat([k.order for k in kps])),
+                               c(cat([k.count for k in kps])), c(cat([f.used_mask for f in fits])),
+                               c(cat([f.inlier_mask for f in fits])), c(status), c(attempted), c(h_index), c(proj.coords_i),
+                               c(proj.in_bounds), c(proj.bounds))

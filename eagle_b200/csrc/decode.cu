@@ -1,0 +1,195 @@
+// K2: heatmap decode (replaces KeypointModel.get_keypoints, eagle/models/keypoint_hrnet.py:583-594,
+// and the keypoint post-processing at eagle/models/coordinate_model.py:229-248).
+//
+// HBM-bound: every float of the (F,57,135,240) heatmap tensor is read exactly once (7,387,200 B per
+// frame) and 8 bytes per channel are written.  Layout of the work:
+//   * argmax_kernel -- persistent, one CTA per SM.  CTA c owns a CONTIGUOUS range of maps
+//     (total_maps*c/G ...), so each SM streams one long sequential region of HBM.  The maps are
+//     pulled through a 6-stage shared-memory ring by the TMA engine (cp.async.bulk, 32,400-byte
+//     chunks = a quarter of a 135x240 map, completion signalled on an mbarrier per stage), i.e. up
+//     to 5 x 32 KB in flight per SM with no registers tied up by loads.  The 8 warps scan a chunk
+//     with LDS.128, keeping (max, first flat index) per thread; per map a warp-shuffle arg-max and
+//     a cross-warp step produce the result.  Ties resolve to the lowest flat index = np.argmax.
+//   * postprocess_kernel -- one thread per frame over the 57 (index, score) pairs: confidence
+//     filter, scale to image pixels, duplicate-pixel arbitration, reference dict order.
+#include "common.cuh"
+#include "geometry_core.cuh"
+
+namespace egl {
+
+constexpr int kDecThreads = 256;
+constexpr int kDecWarps = kDecThreads / 32;
+constexpr int kStages = 6;
+constexpr int kChunkF4Max = 2025;  // float4 per stage: 32,400 B
+
+struct DecodeArgs {
+    const float4* hm;
+    long long total_maps;
+    int map_f4;          // float4 per map (hm_h*hm_w/4)
+    int chunk_f4;        // float4 per chunk (<= kChunkF4Max)
+    int chunks_per_map;
+    int32_t* kp_flat;
+    float* kp_score;
+};
+
+// np.argmax ordering on (value, index): larger value wins, NaN beats everything, first index on ties
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
+    const bool vn = v != v, bn = bv != bv;
+    if (vn || bn) return vn && (!bn || i < bi);
+    return v > bv || (v == bv && i < bi);
+}
+
+__global__ void __launch_bounds__(kDecThreads, 1) argmax_kernel(DecodeArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* ring = reinterpret_cast<float4*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * a.chunk_f4 * sizeof(float4));
+    __shared__ float s_val[kDecWarps];
+    __shared__ int s_idx[kDecWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long m0 = a.total_maps * blockIdx.x / gridDim.x;
+    const long long m1 = a.total_maps * (blockIdx.x + 1) / gridDim.x;
+    const long long nchunks = (m1 - m0) * a.chunks_per_map;
+    if (nchunks == 0) return;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](long long c) {  // called by thread 0 only
+        const long long map = m0 + c / a.chunks_per_map;
+        const int k = (int)(c % a.chunks_per_map);
+        const int off = k * a.chunk_f4;
+        const int n = min(a.chunk_f4, a.map_f4 - off);
+        const int stage = (int)(c % kStages);
+        mbar_expect_tx(&full[stage], (uint32_t)n * 16u);
+        bulk_g2s(ring + (size_t)stage * a.chunk_f4, a.hm + map * a.map_f4 + off, (uint32_t)n * 16u, &full[stage]);
+    };
+    if (tid == 0) {
+        const long long pre = nchunks < kStages ? nchunks : kStages;
+        for (long long c = 0; c < pre; ++c) issue(c);
+    }
+
+    // (max, flat index) of the current map as seen by this thread.  The index starts at the first
+    // element the thread will visit so that an all -inf map still decodes to index 0 like np.argmax.
+    const int first_bi = tid < a.chunk_f4 ? tid * 4 : 0x7fffffff;
+    float bv = -INFINITY;
+    int bi = first_bi;
+    bool bnan = false;
+    for (long long c = 0; c < nchunks; ++c) {
+        const int stage = (int)(c % kStages);
+        const int k = (int)(c % a.chunks_per_map);
+        const int off = k * a.chunk_f4;
+        const int n = min(a.chunk_f4, a.map_f4 - off);
+        if (k == 0) { bv = -INFINITY; bi = first_bi; bnan = false; }
+        mbar_wait(&full[stage], (uint32_t)((c / kStages) & 1));
+        const float4* src = ring + (size_t)stage * a.chunk_f4;
+        // ascending flat index per thread, strict '>' keeps the first maximum
+#pragma unroll 4
+        for (int i = tid; i < n; i += kDecThreads) {
+            const float4 v = src[i];
+            const int base = (off + i) * 4;
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool take = !bnan && (e[j] > bv || e[j] != e[j]);
+                if (take) { bv = e[j]; bi = base + j; bnan = e[j] != e[j]; }
+            }
+        }
+        const bool last = (k == a.chunks_per_map - 1);
+        if (last) {
+            float v = bv;
+            int ix = bi;
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                const float ov = __shfl_xor_sync(kFull, v, m);
+                const int oi = __shfl_xor_sync(kFull, ix, m);
+                if (better(ov, oi, v, ix)) { v = ov; ix = oi; }
+            }
+            if (lane == 0) { s_val[warp] = v; s_idx[warp] = ix; }
+        }
+        __syncthreads();  // all reads of this stage are done (and s_val/s_idx are visible)
+        if (tid == 0 && c + kStages < nchunks) issue(c + kStages);
+        if (last && warp == 0) {
+            float v = lane < kDecWarps ? s_val[lane] : -INFINITY;
+            int ix = lane < kDecWarps ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+            for (int m = kDecWarps / 2; m > 0; m >>= 1) {
+                const float ov = __shfl_xor_sync(kFull, v, m);
+                const int oi = __shfl_xor_sync(kFull, ix, m);
+                if (better(ov, oi, v, ix)) { v = ov; ix = oi; }
+            }
+            if (lane == 0) {
+                const long long map = m0 + c / a.chunks_per_map;
+                a.kp_flat[map] = ix;
+                a.kp_score[map] = v;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64) postprocess_kernel(const int32_t* __restrict__ kp_flat, const float* __restrict__ kp_score,
+                                                         int F, int hm_h, int hm_w, int img_w, int img_h, double conf,
+                                                         int32_t* kp_xy, uint8_t* kp_order, int32_t* kp_count) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    int32_t flat[kLandmarks], xy[2 * kLandmarks];
+    float score[kLandmarks];
+    uint8_t order[EGL_ORDER_STRIDE];
+    for (int c = 0; c < kLandmarks; ++c) {
+        flat[c] = kp_flat[(size_t)f * kLandmarks + c];
+        score[c] = kp_score[(size_t)f * kLandmarks + c];
+    }
+    const int n = postprocess_keypoints(flat, score, hm_h, hm_w, img_w, img_h, conf, xy, order);
+    for (int c = 0; c < 2 * kLandmarks; ++c) kp_xy[(size_t)f * 2 * kLandmarks + c] = xy[c];
+    for (int j = 0; j < EGL_ORDER_STRIDE; ++j) kp_order[(size_t)f * EGL_ORDER_STRIDE + j] = j < n ? order[j] : 0xFF;
+    kp_count[2 * f] = n;
+    kp_count[2 * f + 1] = n;
+}
+
+}  // namespace egl
+
+using namespace egl;
+
+extern "C" int egl_decode_heatmaps(const float* hm, int F, int hm_h, int hm_w, int img_w, int img_h, double keypoint_conf,
+                                   int32_t* kp_flat, float* kp_score, int32_t* kp_xy, uint8_t* kp_order, int32_t* kp_count,
+                                   void* stream) {
+    EGL_REQUIRE(hm && kp_flat && kp_score && kp_xy && kp_order && kp_count, EGL_ERR_NULL, "egl_decode_heatmaps: null pointer");
+    EGL_REQUIRE(F >= 0 && hm_h > 0 && hm_w > 0 && img_w > 0 && img_h > 0, EGL_ERR_SHAPE, "egl_decode_heatmaps: bad shape");
+    EGL_REQUIRE(((long long)hm_h * hm_w) % 4 == 0, EGL_ERR_SHAPE,
+                "egl_decode_heatmaps: hm_h*hm_w must be a multiple of 4 (got %dx%d)", hm_h, hm_w);
+    EGL_REQUIRE((long long)hm_h * hm_w < (1ll << 29), EGL_ERR_SHAPE, "egl_decode_heatmaps: map too large");
+    EGL_REQUIRE((reinterpret_cast<uintptr_t>(hm) & 15) == 0, EGL_ERR_ALIGN, "egl_decode_heatmaps: hm must be 16-byte aligned");
+    if (F == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    DecodeArgs a;
+    a.hm = reinterpret_cast<const float4*>(hm);
+    a.total_maps = (long long)F * kLandmarks;
+    a.map_f4 = hm_h * hm_w / 4;
+    a.chunks_per_map = (a.map_f4 + kChunkF4Max - 1) / kChunkF4Max;
+    a.chunk_f4 = (a.map_f4 + a.chunks_per_map - 1) / a.chunks_per_map;  // balanced chunks, <= kChunkF4Max
+    a.kp_flat = kp_flat;
+    a.kp_score = kp_score;
+    const size_t smem = (size_t)kStages * a.chunk_f4 * sizeof(float4) + kStages * sizeof(uint64_t);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        int rc = cuda_status(cudaFuncSetAttribute(argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)((size_t)kStages * kChunkF4Max * sizeof(float4) + kStages * sizeof(uint64_t))),
+                             "egl_decode_heatmaps: cudaFuncSetAttribute");
+        if (rc) return rc;
+        configured_dev = dev;
+    }
+    int sms = egl_sm_count();
+    if (sms <= 0) return -1;
+    long long grid = a.total_maps < sms ? a.total_maps : sms;
+    argmax_kernel<<<(unsigned)grid, kDecThreads, smem, s>>>(a);
+    int rc = cuda_status(cudaGetLastError(), "egl_decode_heatmaps: argmax kernel launch");
+    if (rc) return rc;
+    postprocess_kernel<<<(F + 63) / 64, 64, 0, s>>>(kp_flat, kp_score, F, hm_h, hm_w, img_w, img_h, keypoint_conf, kp_xy,
+                                                    kp_order, kp_count);
+    return cuda_status(cudaGetLastError(), "egl_decode_heatmaps: postprocess kernel launch");
+}

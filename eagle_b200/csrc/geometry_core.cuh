@@ -1,0 +1,814 @@
+// Scalar building blocks of the homography fit and the projection, shared by every kernel.
+//
+// Everything here is a pure function of its arguments, written so that the operation order is
+// fixed (explicit round-to-nearest intrinsics where a fused multiply-add would change a result
+// that has to match OpenCV bit for bit).  The functions are __host__ __device__: the kernels in
+// fit.cu / project.cu call them on the GPU, and tests/native/host_check.cpp compiles the very
+// same code with g++ (-ffp-contract=off) so the arithmetic can be checked against the oracle on
+// a machine without a GPU.  That host build is a test artefact only; the product never calls it.
+//
+// OpenCV references are to calib3d (fundam.cpp, ptsetreg.cpp, levmarq.cpp) of opencv-python
+// 4.11/4.13, the library behind the reference's cv2.findHomography call
+// (eagle/models/coordinate_model.py:355).
+#pragma once
+
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define EGL_HD __host__ __device__ __forceinline__
+#define EGL_HD_NOINLINE static __host__ __device__ __noinline__
+#define EGL_UNROLL _Pragma("unroll")
+#else
+#define EGL_UNROLL
+#define EGL_HD inline
+#define EGL_HD_NOINLINE static inline
+#endif
+
+namespace egl {
+
+// ---- non-contracted float arithmetic (OpenCV's x86 build has no FMA in computeError) ----------
+#if defined(__CUDA_ARCH__)
+EGL_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+EGL_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+EGL_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
+EGL_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+EGL_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+EGL_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+EGL_HD double dsub(double a, double b) { return __dsub_rn(a, b); }
+#else
+EGL_HD float fmul(float a, float b) { return a * b; }  // host build uses -ffp-contract=off
+EGL_HD float fadd(float a, float b) { return a + b; }
+EGL_HD float fsub(float a, float b) { return a - b; }
+EGL_HD float fdiv(float a, float b) { return a / b; }
+EGL_HD double dmul(double a, double b) { return a * b; }
+EGL_HD double dadd(double a, double b) { return a + b; }
+EGL_HD double dsub(double a, double b) { return a - b; }
+#endif
+
+// ---- cv::RNG (multiply-with-carry); RANSACPointSetRegistrator::run seeds it with 2^64-1 -------
+struct CvRng {
+    uint64_t state;
+    EGL_HD uint32_t next() {
+        state = (uint64_t)(uint32_t)state * 4164903690ull + (state >> 32);
+        return (uint32_t)state;
+    }
+    EGL_HD int uniform(int a, int b) { return a == b ? a : a + (int)(next() % (uint32_t)(b - a)); }
+};
+
+// getSubset(): 4 distinct indices by rejection.
+EGL_HD void draw_subset(CvRng& rng, int count, int idx[4]) {
+    for (int i = 0; i < 4; ++i) {
+        int v;
+        bool dup;
+        do {
+            v = rng.uniform(0, count);
+            dup = false;
+            for (int k = 0; k < i; ++k) dup |= (idx[k] == v);
+        } while (dup);
+        idx[i] = v;
+    }
+}
+
+// haveCollinearPoints(ms, 4): only the last point is tested against the earlier pairs.
+EGL_HD bool last_point_collinear(const float* px, const float* py) {
+    const double xi = px[3], yi = py[3];
+    for (int j = 0; j < 3; ++j) {
+        const double dx1 = px[j] - xi, dy1 = py[j] - yi;
+        for (int k = 0; k < j; ++k) {
+            const double dx2 = px[k] - xi, dy2 = py[k] - yi;
+            if (fabs(dsub(dmul(dx2, dy1), dmul(dy2, dx1))) <=
+                (double)FLT_EPSILON * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2)))
+                return true;
+        }
+    }
+    return false;
+}
+
+// determinant of [[x0,y0,1],[x1,y1,1],[x2,y2,1]] in cv::determinant(Matx33d) order
+EGL_HD double det_rows1(const float* px, const float* py, int a, int b, int c) {
+    const double x0 = px[a], y0 = py[a], x1 = px[b], y1 = py[b], x2 = px[c], y2 = py[c];
+    const double t0 = dmul(x0, dsub(y1, y2));
+    const double t1 = dmul(y0, dsub(x1, x2));
+    const double t2 = dsub(dmul(x1, y2), dmul(x2, y1));
+    return dadd(dsub(t0, t1), t2);
+}
+
+// HomographyEstimatorCallback::checkSubset for a 4-point sample (src = image, dst = pitch).
+EGL_HD bool check_subset(const float* sx, const float* sy, const float* dx, const float* dy) {
+    if (last_point_collinear(sx, sy) || last_point_collinear(dx, dy)) return false;
+    int negative = 0;
+    negative += dmul(det_rows1(sx, sy, 0, 1, 2), det_rows1(dx, dy, 0, 1, 2)) < 0;
+    negative += dmul(det_rows1(sx, sy, 1, 2, 3), det_rows1(dx, dy, 1, 2, 3)) < 0;
+    negative += dmul(det_rows1(sx, sy, 0, 2, 3), det_rows1(dx, dy, 0, 2, 3)) < 0;
+    negative += dmul(det_rows1(sx, sy, 0, 1, 3), det_rows1(dx, dy, 0, 1, 3)) < 0;
+    return negative == 0 || negative == 4;
+}
+
+// ---- HomographyEstimatorCallback::computeError for one point, float, OpenCV's order ----------
+EGL_HD float reproj_err_f32(const float* Hf, float X, float Y, float x, float y) {
+    const float ww = fdiv(1.f, fadd(fadd(fmul(Hf[6], X), fmul(Hf[7], Y)), 1.f));
+    const float ex = fsub(fmul(fadd(fadd(fmul(Hf[0], X), fmul(Hf[1], Y)), Hf[2]), ww), x);
+    const float ey = fsub(fmul(fadd(fadd(fmul(Hf[3], X), fmul(Hf[4], Y)), Hf[5]), ww), y);
+    return fadd(fmul(ex, ex), fmul(ey, ey));
+}
+
+// RANSACUpdateNumIters (ptsetreg.cpp)
+EGL_HD int ransac_update_num_iters(double p, double ep, int model_points, int max_iters) {
+    p = fmax(p, 0.);
+    p = fmin(p, 1.);
+    ep = fmax(ep, 0.);
+    ep = fmin(ep, 1.);
+    double num = fmax(1. - p, DBL_MIN);
+    double denom = 1. - pow(1. - ep, (double)model_points);
+    if (denom < DBL_MIN) return 0;
+    num = log(num);
+    denom = log(denom);
+    return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : (int)rint(num / denom);
+}
+
+// ---- linear algebra on small dense matrices (double) ------------------------------------------
+
+// Solve the n x n system a[n][n+1] (augmented, row-major, stride n+1) by Gaussian elimination with
+// partial pivoting.  Returns false if a pivot is exactly zero / not finite.
+template <int N>
+EGL_HD bool gauss_solve(double* a, double* x) {
+    constexpr int S = N + 1;
+    for (int k = 0; k < N; ++k) {
+        int piv = k;
+        double best = fabs(a[k * S + k]);
+        for (int i = k + 1; i < N; ++i) {
+            const double v = fabs(a[i * S + k]);
+            if (v > best) {
+                best = v;
+                piv = i;
+            }
+        }
+        if (!(best > 0.0) || !isfinite(best)) return false;
+        if (piv != k)
+            for (int j = k; j < S; ++j) {
+                const double t = a[k * S + j];
+                a[k * S + j] = a[piv * S + j];
+                a[piv * S + j] = t;
+            }
+        const double inv = 1.0 / a[k * S + k];
+        for (int i = k + 1; i < N; ++i) {
+            const double m = a[i * S + k] * inv;
+            if (m != 0.0)
+                for (int j = k + 1; j < S; ++j) a[i * S + j] -= m * a[k * S + j];
+        }
+    }
+    for (int i = N - 1; i >= 0; --i) {
+        double s = a[i * S + N];
+        for (int j = i + 1; j < N; ++j) s -= a[i * S + j] * x[j];
+        x[i] = s / a[i * S + i];
+    }
+    return true;
+}
+
+// Cyclic Jacobi eigen-decomposition of a symmetric 9x9 matrix (row-major A, destroyed).
+// On return w[i] are the eigenvalues and column i of V (V[k*9+i]) the matching unit eigenvector.
+EGL_HD_NOINLINE void jacobi9(double* A, double* V, double* w) {
+    constexpr int n = 9;
+    for (int i = 0; i < n * n; ++i) V[i] = 0.0;
+    for (int i = 0; i < n; ++i) V[i * n + i] = 1.0;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int p = 0; p < n; ++p) {
+            diag += A[p * n + p] * A[p * n + p];
+            for (int q = p + 1; q < n; ++q) off += A[p * n + q] * A[p * n + q];
+        }
+        if (off <= 1e-32 * diag || off == 0.0) break;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = A[p * n + q];
+                if (apq == 0.0) continue;
+                const double app = A[p * n + p], aqq = A[q * n + q];
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; ++k) {  // columns p,q: A <- A J
+                    const double akp = A[k * n + p], akq = A[k * n + q];
+                    A[k * n + p] = c * akp - s * akq;
+                    A[k * n + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; ++k) {  // rows p,q: A <- J^T A
+                    const double apk = A[p * n + k], aqk = A[q * n + k];
+                    A[p * n + k] = c * apk - s * aqk;
+                    A[q * n + k] = s * apk + c * aqk;
+                }
+                A[p * n + q] = A[q * n + p] = 0.0;
+                for (int k = 0; k < n; ++k) {
+                    const double vkp = V[k * n + p], vkq = V[k * n + q];
+                    V[k * n + p] = c * vkp - s * vkq;
+                    V[k * n + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
+}
+
+// cv::solve(A, b, x, DECOMP_EIG) for a symmetric 9x9 A given its eigen-decomposition: the
+// back-substitution of SVBkSb with OpenCV's threshold (2*DBL_EPSILON * sum of eigenvalues), i.e.
+// a pseudo-inverse when A is singular (the 9-parameter homography has a scale gauge freedom).
+EGL_HD void eig_backsolve9(const double* V, const double* w, const double* b, double* x) {
+    double thr = 0.0;
+    for (int i = 0; i < 9; ++i) thr += w[i];
+    thr *= 2.0 * DBL_EPSILON;
+    for (int k = 0; k < 9; ++k) x[k] = 0.0;
+    for (int i = 0; i < 9; ++i) {
+        if (fabs(w[i]) <= thr) continue;
+        double s = 0.0;
+        for (int k = 0; k < 9; ++k) s += V[k * 9 + i] * b[k];
+        s /= w[i];
+        for (int k = 0; k < 9; ++k) x[k] += s * V[k * 9 + i];
+    }
+}
+
+// ---- HomographyEstimatorCallback::runKernel: normalised DLT on n >= 4 correspondences ---------
+// idx (may be null) selects the points; X,Y = image (src), x,y = pitch (dst) as float.
+// Accumulates the 9x9 normal matrix with the block structure
+//     LtL = sum_i (b b^T) (x) [[1,0,-x],[0,1,-y],[-x,-y,x^2+y^2]],  b = (X, Y, 1) normalised.
+EGL_HD_NOINLINE bool dlt_normal_matrix(const float* sx, const float* sy, const float* dx, const float* dy,
+                                       const uint8_t* idx, int n, double* LtL, double* norm /*[8]: cM,cm,sM,sm*/) {
+    double cMx = 0, cMy = 0, cmx = 0, cmy = 0;
+    for (int i = 0; i < n; ++i) {
+        const int j = idx ? idx[i] : i;
+        cmx += dx[j];
+        cmy += dy[j];
+        cMx += sx[j];
+        cMy += sy[j];
+    }
+    cmx /= n; cmy /= n; cMx /= n; cMy /= n;
+    double smx = 0, smy = 0, sMx = 0, sMy = 0;
+    for (int i = 0; i < n; ++i) {
+        const int j = idx ? idx[i] : i;
+        smx += fabs(dx[j] - cmx);
+        smy += fabs(dy[j] - cmy);
+        sMx += fabs(sx[j] - cMx);
+        sMy += fabs(sy[j] - cMy);
+    }
+    if (fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON)
+        return false;
+    smx = n / smx; smy = n / smy; sMx = n / sMx; sMy = n / sMy;
+    norm[0] = cMx; norm[1] = cMy; norm[2] = cmx; norm[3] = cmy;
+    norm[4] = sMx; norm[5] = sMy; norm[6] = smx; norm[7] = smy;
+    for (int i = 0; i < 81; ++i) LtL[i] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const int j = idx ? idx[i] : i;
+        const double x = (dx[j] - cmx) * smx, y = (dy[j] - cmy) * smy;
+        const double X = (sx[j] - cMx) * sMx, Y = (sy[j] - cMy) * sMy;
+        const double Lx[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x};
+        const double Ly[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
+        for (int a = 0; a < 9; ++a)
+            for (int b = a; b < 9; ++b) LtL[a * 9 + b] += Lx[a] * Lx[b] + Ly[a] * Ly[b];
+    }
+    for (int a = 0; a < 9; ++a)
+        for (int b = 0; b < a; ++b) LtL[a * 9 + b] = LtL[b * 9 + a];
+    return true;
+}
+
+// H = invHnorm * H0 * Hnorm2, then scaled so that H[8] == 1 (runKernel's convertTo(1/H22)).
+EGL_HD void dlt_denormalise(const double* h0, const double* norm, double* H) {
+    const double cMx = norm[0], cMy = norm[1], cmx = norm[2], cmy = norm[3];
+    const double sMx = norm[4], sMy = norm[5], smx = norm[6], smy = norm[7];
+    // T = invHnorm * H0 ; invHnorm = [[1/smx,0,cmx],[0,1/smy,cmy],[0,0,1]]
+    double T[9];
+    for (int c = 0; c < 3; ++c) {
+        T[0 * 3 + c] = (1.0 / smx) * h0[0 * 3 + c] + cmx * h0[2 * 3 + c];
+        T[1 * 3 + c] = (1.0 / smy) * h0[1 * 3 + c] + cmy * h0[2 * 3 + c];
+        T[2 * 3 + c] = h0[2 * 3 + c];
+    }
+    // H = T * Hnorm2 ; Hnorm2 = [[sMx,0,-cMx*sMx],[0,sMy,-cMy*sMy],[0,0,1]]
+    for (int r = 0; r < 3; ++r) {
+        H[r * 3 + 0] = T[r * 3 + 0] * sMx;
+        H[r * 3 + 1] = T[r * 3 + 1] * sMy;
+        H[r * 3 + 2] = T[r * 3 + 0] * (-cMx * sMx) + T[r * 3 + 1] * (-cMy * sMy) + T[r * 3 + 2];
+    }
+    const double s = 1.0 / H[8];
+    for (int i = 0; i < 9; ++i) H[i] *= s;
+}
+
+// runKernel on the points selected by idx[0..n).  scratch: 81+81+9 doubles.
+EGL_HD_NOINLINE bool run_kernel_ls(const float* sx, const float* sy, const float* dx, const float* dy,
+                                   const uint8_t* idx, int n, double* H, double* scratch) {
+    double* LtL = scratch;
+    double* V = scratch + 81;
+    double* w = scratch + 162;
+    double norm[8];
+    if (!dlt_normal_matrix(sx, sy, dx, dy, idx, n, LtL, norm)) return false;
+    jacobi9(LtL, V, w);
+    int m = 0;
+    for (int i = 1; i < 9; ++i)
+        if (w[i] < w[m]) m = i;
+    double h0[9];
+    for (int k = 0; k < 9; ++k) h0[k] = V[k * 9 + m];
+    dlt_denormalise(h0, norm, H);
+    return true;
+}
+
+// Minimal 4-point solve in double (the model cv2 evaluates per RANSAC iteration).  Same
+// normalisation as runKernel, but the 8x8 system with h33 = 1 in normalised coordinates is solved
+// by elimination instead of a 9x9 eigen-decomposition: identical up to ~1e-13 relative, far below
+// the float cast OpenCV applies before scoring.
+EGL_HD_NOINLINE bool dlt4_f64(const float* sx, const float* sy, const float* dx, const float* dy, double* H) {
+    double cMx = 0, cMy = 0, cmx = 0, cmy = 0;
+    for (int i = 0; i < 4; ++i) { cmx += dx[i]; cmy += dy[i]; cMx += sx[i]; cMy += sy[i]; }
+    cmx /= 4; cmy /= 4; cMx /= 4; cMy /= 4;
+    double smx = 0, smy = 0, sMx = 0, sMy = 0;
+    for (int i = 0; i < 4; ++i) {
+        smx += fabs(dx[i] - cmx); smy += fabs(dy[i] - cmy);
+        sMx += fabs(sx[i] - cMx); sMy += fabs(sy[i] - cMy);
+    }
+    if (fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON)
+        return false;
+    smx = 4 / smx; smy = 4 / smy; sMx = 4 / sMx; sMy = 4 / sMy;
+    double a[8 * 9];
+    for (int i = 0; i < 4; ++i) {
+        const double x = (dx[i] - cmx) * smx, y = (dy[i] - cmy) * smy;
+        const double X = (sx[i] - cMx) * sMx, Y = (sy[i] - cMy) * sMy;
+        double* r0 = a + (2 * i) * 9;
+        double* r1 = a + (2 * i + 1) * 9;
+        r0[0] = X; r0[1] = Y; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0; r0[6] = -x * X; r0[7] = -x * Y; r0[8] = x;
+        r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = X; r1[4] = Y; r1[5] = 1; r1[6] = -y * X; r1[7] = -y * Y; r1[8] = y;
+    }
+    double h0[9];
+    if (!gauss_solve<8>(a, h0)) return false;
+    h0[8] = 1.0;
+    const double norm[8] = {cMx, cMy, cmx, cmy, sMx, sMy, smx, smy};
+    dlt_denormalise(h0, norm, H);
+    for (int i = 0; i < 9; ++i)
+        if (!isfinite(H[i])) return false;
+    return true;
+}
+
+// ---- HomographyRefineCallback + LMSolverImpl::run (9 parameters, <= 10 iterations) ------------
+// Linearise at h: S = |r|^2, A = J^T J (9x9), v = J^T r, rmax = |r|_inf, over the points idx[0..n).
+EGL_HD_NOINLINE void lm_linearise(const double* h, const float* sx, const float* sy, const float* dx, const float* dy,
+                                  const uint8_t* idx, int n, double* A, double* v, double* S, double* rmax) {
+    // A = sum (b b^T) (x) [[1,0,-xi],[0,1,-yi],[-xi,-yi,xi^2+yi^2]],  b = (Mx, My, 1) * ww
+    double bb[6] = {0, 0, 0, 0, 0, 0}, bx[6] = {0, 0, 0, 0, 0, 0}, by[6] = {0, 0, 0, 0, 0, 0}, bq[6] = {0, 0, 0, 0, 0, 0};
+    double vx[3] = {0, 0, 0}, vy[3] = {0, 0, 0}, vq[3] = {0, 0, 0};
+    double s = 0, rm = 0;
+    for (int i = 0; i < n; ++i) {
+        const int j = idx ? idx[i] : i;
+        const double Mx = sx[j], My = sy[j];
+        double ww = h[6] * Mx + h[7] * My + h[8];
+        ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
+        const double xi = (h[0] * Mx + h[1] * My + h[2]) * ww;
+        const double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
+        const double rx = xi - dx[j], ry = yi - dy[j];
+        s += rx * rx + ry * ry;
+        rm = fmax(rm, fmax(fabs(rx), fabs(ry)));
+        const double b[3] = {Mx * ww, My * ww, ww};
+        const double q = xi * xi + yi * yi, g = xi * rx + yi * ry;
+        int e = 0;
+        for (int a = 0; a < 3; ++a) {
+            for (int c = a; c < 3; ++c, ++e) {
+                const double p = b[a] * b[c];
+                bb[e] += p;
+                bx[e] += p * xi;
+                by[e] += p * yi;
+                bq[e] += p * q;
+            }
+            vx[a] += b[a] * rx;
+            vy[a] += b[a] * ry;
+            vq[a] += b[a] * g;
+        }
+    }
+    for (int a = 0; a < 3; ++a)
+        for (int c = 0; c < 3; ++c) {
+            const int lo = a < c ? a : c, hi = a < c ? c : a;
+            const int e = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);  // packed upper-triangle index
+            A[(0 + a) * 9 + (0 + c)] = bb[e];
+            A[(3 + a) * 9 + (3 + c)] = bb[e];
+            A[(0 + a) * 9 + (3 + c)] = 0.0;
+            A[(3 + a) * 9 + (0 + c)] = 0.0;
+            A[(0 + a) * 9 + (6 + c)] = -bx[e];
+            A[(6 + a) * 9 + (0 + c)] = -bx[e];
+            A[(3 + a) * 9 + (6 + c)] = -by[e];
+            A[(6 + a) * 9 + (3 + c)] = -by[e];
+            A[(6 + a) * 9 + (6 + c)] = bq[e];
+        }
+    for (int a = 0; a < 3; ++a) {
+        v[a] = vx[a];
+        v[3 + a] = vy[a];
+        v[6 + a] = -vq[a];
+    }
+    *S = s;
+    *rmax = rm;
+}
+
+EGL_HD double lm_cost(const double* h, const float* sx, const float* sy, const float* dx, const float* dy,
+                      const uint8_t* idx, int n) {
+    double s = 0;
+    for (int i = 0; i < n; ++i) {
+        const int j = idx ? idx[i] : i;
+        const double Mx = sx[j], My = sy[j];
+        double ww = h[6] * Mx + h[7] * My + h[8];
+        ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
+        const double rx = (h[0] * Mx + h[1] * My + h[2]) * ww - dx[j];
+        const double ry = (h[3] * Mx + h[4] * My + h[5]) * ww - dy[j];
+        s += rx * rx + ry * ry;
+    }
+    return s;
+}
+
+// LMSolverImpl::run with maxIters = 10, eps = FLT_EPSILON, followed by the 1/h33 rescale of
+// findHomography.  scratch: 4*81 + 9 doubles.  Returns the iterations run.
+EGL_HD_NOINLINE int lm_refine(double* H, const float* sx, const float* sy, const float* dx, const float* dy,
+                              const uint8_t* idx, int n, double* scratch) {
+    double* A = scratch;         // J^T J
+    double* Ap = scratch + 81;   // damped copy, destroyed by jacobi9
+    double* V = scratch + 162;
+    double* w = scratch + 243;   // 9
+    double x[9], xd[9], v[9], d[9], D[9];
+    for (int i = 0; i < 9; ++i) x[i] = H[i];
+    double S, rmax;
+    lm_linearise(x, sx, sy, dx, dy, idx, n, A, v, &S, &rmax);
+    for (int i = 0; i < 9; ++i) D[i] = A[i * 9 + i];
+    const double Rlo = 0.25, Rhi = 0.75;
+    double lambda = 1, lc = 0.75;
+    int iter = 0;
+    for (;;) {
+        for (int i = 0; i < 81; ++i) Ap[i] = A[i];
+        for (int i = 0; i < 9; ++i) Ap[i * 9 + i] += lambda * D[i];
+        jacobi9(Ap, V, w);
+        eig_backsolve9(V, w, v, d);
+        for (int i = 0; i < 9; ++i) xd[i] = x[i] - d[i];
+        const double Sd = lm_cost(xd, sx, sy, dx, dy, idx, n);
+        double dS = 0;
+        for (int i = 0; i < 9; ++i) {
+            double t = 2.0 * v[i];
+            for (int k = 0; k < 9; ++k) t -= A[i * 9 + k] * d[k];
+            dS += d[i] * t;
+        }
+        const double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
+        if (R > Rhi) {
+            lambda *= 0.5;
+            if (lambda < lc) lambda = 0;
+        } else if (R < Rlo) {
+            double t = 0;
+            for (int i = 0; i < 9; ++i) t += d[i] * v[i];
+            double nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1) + 2;
+            nu = fmin(fmax(nu, 2.), 10.);
+            if (lambda == 0) {
+                // invert(A, Ap, DECOMP_EIG): pseudo-inverse; only its diagonal is used
+                for (int i = 0; i < 81; ++i) Ap[i] = A[i];
+                jacobi9(Ap, V, w);
+                double thr = 0;
+                for (int i = 0; i < 9; ++i) thr += w[i];
+                thr *= 2.0 * DBL_EPSILON;
+                double maxval = DBL_EPSILON;
+                for (int k = 0; k < 9; ++k) {
+                    double dk = 0;
+                    for (int i = 0; i < 9; ++i)
+                        if (fabs(w[i]) > thr) dk += V[k * 9 + i] * V[k * 9 + i] / w[i];
+                    maxval = fmax(maxval, fabs(dk));
+                }
+                lambda = lc = 1. / maxval;
+                nu *= 0.5;
+            }
+            lambda *= nu;
+        }
+        double dmax = 0;
+        for (int i = 0; i < 9; ++i) dmax = fmax(dmax, fabs(d[i]));
+        if (Sd < S) {
+            S = Sd;
+            for (int i = 0; i < 9; ++i) x[i] = xd[i];
+            lm_linearise(x, sx, sy, dx, dy, idx, n, A, v, &S, &rmax);
+        }
+        iter++;
+        const bool proceed = iter < 10 && dmax >= (double)FLT_EPSILON && rmax >= (double)FLT_EPSILON;
+        if (!proceed) break;
+    }
+    const double sc = fabs(x[8]) > (double)FLT_EPSILON ? 1. / x[8] : 1.;  // fundam.cpp scaleFor()
+    for (int i = 0; i < 9; ++i) H[i] = x[i] * sc;
+    return iter;
+}
+
+// Inliers of H over the n points: float scoring in OpenCV's order.  Returns the count and sets
+// bit i of *mask for inlier i (i = position in the point list).
+EGL_HD int inlier_mask_f32(const double* H, const float* sx, const float* sy, const float* dx, const float* dy, int n,
+                           float thr_sq, uint64_t* mask) {
+    float Hf[8];
+    for (int i = 0; i < 8; ++i) Hf[i] = (float)H[i];
+    uint64_t m = 0;
+    int c = 0;
+    for (int i = 0; i < n; ++i) {
+        const float e = reproj_err_f32(Hf, sx[i], sy[i], dx[i], dy[i]);
+        if (e <= thr_sq) {
+            m |= 1ull << i;
+            ++c;
+        }
+    }
+    *mask = m;
+    return c;
+}
+
+// The tail of cv2.findHomography after RANSAC picked `H` (best model) with inlier list mask:
+// runKernel on the inliers, LM polish, mask recomputed from the refined H.  scratch >= 333 doubles.
+EGL_HD_NOINLINE int refit_on_inliers(double* H, const float* sx, const float* sy, const float* dx, const float* dy, int n,
+                                     uint64_t ransac_mask, float thr_sq, uint64_t* final_mask, double* scratch) {
+    uint8_t idx[64];
+    int m = 0;
+    for (int i = 0; i < n; ++i)
+        if ((ransac_mask >> i) & 1) idx[m++] = (uint8_t)i;
+    double Hk[9];
+    if (run_kernel_ls(sx, sy, dx, dy, idx, m, Hk, scratch))
+        for (int i = 0; i < 9; ++i) H[i] = Hk[i];
+    lm_refine(H, sx, sy, dx, dy, idx, m, scratch);
+    return inlier_mask_f32(H, sx, sy, dx, dy, n, thr_sq, final_mask);
+}
+
+// ---- projection (cv::perspectiveTransform, float points, double matrix) ------------------------
+EGL_HD void perspective_point(const double* H, float px, float py, float* ox, float* oy) {
+    const double x = px, y = py;
+    double w = dadd(dadd(dmul(x, H[6]), dmul(y, H[7])), H[8]);
+    if (fabs(w) > DBL_EPSILON) {
+        w = 1. / w;
+        *ox = (float)dmul(dadd(dadd(dmul(x, H[0]), dmul(y, H[1])), H[2]), w);
+        *oy = (float)dmul(dadd(dadd(dmul(x, H[3]), dmul(y, H[4])), H[5]), w);
+    } else {
+        *ox = 0.f;
+        *oy = 0.f;
+    }
+}
+
+// numpy float32 -> int64 .astype(int) on x86 (cvttss2si): non-finite / out of range -> INT64_MIN
+EGL_HD long long trunc_like_numpy(float v) {
+    if (!(v > -9.2233720368547758e18f && v < 9.2233720368547758e18f)) return (long long)0x8000000000000000ull;
+    return (long long)v;
+}
+
+// find_x_at_y (coordinate_model.py:32-44) in Python-float semantics; ok=false where Python raises
+// ZeroDivisionError (division by an exact zero).
+EGL_HD double find_x_at_y(double x1, double y1, double x2, double y2, double y_target, bool* ok) {
+    const double ddx = x2 - x1;
+    if (ddx == 0.0) { *ok = false; return 0.0; }
+    const double m = (y2 - y1) / ddx;
+    const double c = dsub(y1, dmul(m, x1));
+    if (m == 0.0) { *ok = false; return 0.0; }
+    return (y_target - c) / m;
+}
+
+// ---- keypoint post-processing for one frame (coordinate_model.py:229-248) ----------------------
+// flat/score: per-channel argmax and maximum.  Writes xy[57][2] for every channel, the kept
+// channels in the reference's dict insertion order into order[], and returns their number.
+//   kept      : score > 0.01 (keypoint_hrnet.py:592) and not score < conf (:232), compared in double
+//               exactly like Python compares the float(score);
+//   position  : xi = int((x / (w-1)) * img_w), yi likewise -- two double roundings, as in Python;
+//   duplicates: channels sharing (xi, yi) keep the highest score; on an exact score tie the later
+//               channel wins the label but takes the dict slot of the first tied channel.
+EGL_HD_NOINLINE int postprocess_keypoints(const int32_t* flat, const float* score, int hm_h, int hm_w, int img_w,
+                                          int img_h, double conf, int32_t* xy, uint8_t* order) {
+    constexpr int C = 57;
+    bool kept[C];
+    const double wden = (double)(hm_w - 1 > 1 ? hm_w - 1 : 1), hden = (double)(hm_h - 1 > 1 ? hm_h - 1 : 1);
+    for (int c = 0; c < C; ++c) {
+        const int y = flat[c] / hm_w, x = flat[c] - y * hm_w;
+        const double sc = (double)score[c];
+        kept[c] = (sc > 0.01) && !(sc < conf);
+        xy[2 * c] = (int32_t)dmul((double)x / wden, (double)img_w);
+        xy[2 * c + 1] = (int32_t)dmul((double)y / hden, (double)img_h);
+    }
+    int n = 0;
+    for (int c = 0; c < C; ++c) {
+        if (!kept[c]) continue;
+        float gmax = score[c];
+        for (int o = 0; o < C; ++o)
+            if (kept[o] && xy[2 * o] == xy[2 * c] && xy[2 * o + 1] == xy[2 * c + 1] && score[o] > gmax) gmax = score[o];
+        if (score[c] != gmax) continue;  // a better channel owns this pixel
+        bool first = true;
+        int last = c;
+        for (int o = 0; o < C; ++o) {
+            if (!(kept[o] && xy[2 * o] == xy[2 * c] && xy[2 * o + 1] == xy[2 * c + 1] && score[o] == gmax)) continue;
+            if (o < c) first = false;
+            if (o > last) last = o;
+        }
+        if (first) order[n++] = (uint8_t)last;
+    }
+    return n;
+}
+
+// ---- fixed-K mode: sample generator and the FP32 minimal solve ------------------------------
+// counter-based sample generator: SplitMix64 keyed by (seed, frame, hypothesis); 4 distinct indices
+EGL_HD uint32_t splitmix_next(uint64_t& s) {
+    s += 0x9E3779B97F4A7C15ull;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z >> 32);
+}
+EGL_HD void seeded_subset(uint64_t seed, uint64_t frame, uint64_t K, uint64_t h, int N, int idx[4]) {
+    uint64_t s = seed ^ (0xD1B54A32D192ED03ull * (frame * K + h + 1));
+    for (int i = 0; i < 4; ++i) {
+        int v;
+        bool dup;
+        do {
+            v = (int)(((uint64_t)splitmix_next(s) * (uint64_t)N) >> 32);
+            dup = false;
+            for (int k = 0; k < i; ++k) dup |= (idx[k] == v);
+        } while (dup);
+        idx[i] = v;
+    }
+}
+
+// FP32 4-point DLT: normalise (centroid, mean absolute deviation per axis -- OpenCV's choice),
+// build [X Y 1 0 0 0 -xX -xY | x ; 0 0 0 X Y 1 -yX -yY | y], eliminate with partial pivoting in
+// registers (explicit fmaf in the update so the oracle's C mirror can reproduce every bit),
+// back-substitute, de-normalise, scale by 1/h33.  Returns false on a zero / non-finite pivot.
+EGL_HD bool dlt4_f32(const float* sx, const float* sy, const float* dx, const float* dy, float* H) {
+    float cMx = fmul(fadd(fadd(sx[0], sx[1]), fadd(sx[2], sx[3])), 0.25f);
+    float cMy = fmul(fadd(fadd(sy[0], sy[1]), fadd(sy[2], sy[3])), 0.25f);
+    float cmx = fmul(fadd(fadd(dx[0], dx[1]), fadd(dx[2], dx[3])), 0.25f);
+    float cmy = fmul(fadd(fadd(dy[0], dy[1]), fadd(dy[2], dy[3])), 0.25f);
+    float X[4], Y[4], x[4], y[4];
+EGL_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        X[i] = fsub(sx[i], cMx); Y[i] = fsub(sy[i], cMy);
+        x[i] = fsub(dx[i], cmx); y[i] = fsub(dy[i], cmy);
+    }
+    float sMx = fadd(fadd(fabsf(X[0]), fabsf(X[1])), fadd(fabsf(X[2]), fabsf(X[3])));
+    float sMy = fadd(fadd(fabsf(Y[0]), fabsf(Y[1])), fadd(fabsf(Y[2]), fabsf(Y[3])));
+    float smx = fadd(fadd(fabsf(x[0]), fabsf(x[1])), fadd(fabsf(x[2]), fabsf(x[3])));
+    float smy = fadd(fadd(fabsf(y[0]), fabsf(y[1])), fadd(fabsf(y[2]), fabsf(y[3])));
+    if (!(sMx > 0.f) || !(sMy > 0.f) || !(smx > 0.f) || !(smy > 0.f)) return false;
+    sMx = fdiv(4.f, sMx); sMy = fdiv(4.f, sMy); smx = fdiv(4.f, smx); smy = fdiv(4.f, smy);
+    float a[8][9];
+EGL_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        const float Xn = fmul(X[i], sMx), Yn = fmul(Y[i], sMy), xn = fmul(x[i], smx), yn = fmul(y[i], smy);
+        a[2 * i][0] = Xn; a[2 * i][1] = Yn; a[2 * i][2] = 1.f; a[2 * i][3] = 0.f; a[2 * i][4] = 0.f; a[2 * i][5] = 0.f;
+        a[2 * i][6] = -fmul(xn, Xn); a[2 * i][7] = -fmul(xn, Yn); a[2 * i][8] = xn;
+        a[2 * i + 1][0] = 0.f; a[2 * i + 1][1] = 0.f; a[2 * i + 1][2] = 0.f; a[2 * i + 1][3] = Xn; a[2 * i + 1][4] = Yn;
+        a[2 * i + 1][5] = 1.f; a[2 * i + 1][6] = -fmul(yn, Xn); a[2 * i + 1][7] = -fmul(yn, Yn); a[2 * i + 1][8] = yn;
+    }
+    bool ok = true;
+EGL_UNROLL
+    for (int k = 0; k < 8; ++k) {
+        // partial pivoting by compare-exchange: after the scan row k holds the first row (k..7)
+        // with the largest |a[.][k]|
+EGL_UNROLL
+        for (int i = k + 1; i < 8; ++i) {
+            const bool sw = fabsf(a[i][k]) > fabsf(a[k][k]);
+EGL_UNROLL
+            for (int j = k; j < 9; ++j) {
+                const float t = a[k][j];
+                a[k][j] = sw ? a[i][j] : t;
+                a[i][j] = sw ? t : a[i][j];
+            }
+        }
+        const float piv = a[k][k];
+        ok &= (fabsf(piv) > 0.f) && (fabsf(piv) < INFINITY);
+        const float inv = fdiv(1.f, piv);
+EGL_UNROLL
+        for (int i = k + 1; i < 8; ++i) {
+            const float m = fmul(a[i][k], inv);
+EGL_UNROLL
+            for (int j = k + 1; j < 9; ++j) a[i][j] = fmaf(-m, a[k][j], a[i][j]);
+        }
+    }
+    float h[9];
+EGL_UNROLL
+    for (int i = 7; i >= 0; --i) {
+        float s = a[i][8];
+EGL_UNROLL
+        for (int j = i + 1; j < 8; ++j) s = fmaf(-a[i][j], h[j], s);
+        h[i] = fdiv(s, a[i][i]);
+    }
+    h[8] = 1.f;
+    // T = invHnorm * h ; invHnorm = [[1/smx,0,cmx],[0,1/smy,cmy],[0,0,1]]
+    const float ismx = fdiv(1.f, smx), ismy = fdiv(1.f, smy);
+    float T[9];
+EGL_UNROLL
+    for (int c = 0; c < 3; ++c) {
+        T[c] = fmaf(cmx, h[6 + c], fmul(ismx, h[c]));
+        T[3 + c] = fmaf(cmy, h[6 + c], fmul(ismy, h[3 + c]));
+        T[6 + c] = h[6 + c];
+    }
+    // H = T * Hnorm2 ; Hnorm2 = [[sMx,0,-cMx*sMx],[0,sMy,-cMy*sMy],[0,0,1]]
+    const float tx = -fmul(cMx, sMx), ty = -fmul(cMy, sMy);
+    float G[9];
+EGL_UNROLL
+    for (int r = 0; r < 3; ++r) {
+        G[3 * r + 0] = fmul(T[3 * r + 0], sMx);
+        G[3 * r + 1] = fmul(T[3 * r + 1], sMy);
+        G[3 * r + 2] = fmaf(T[3 * r + 0], tx, fmaf(T[3 * r + 1], ty, T[3 * r + 2]));
+    }
+    const float sc = fdiv(1.f, G[8]);
+EGL_UNROLL
+    for (int i = 0; i < 8; ++i) H[i] = fmul(G[i], sc);
+    H[8] = 1.f;
+EGL_UNROLL
+    for (int i = 0; i < 8; ++i) ok &= (fabsf(H[i]) < INFINITY);
+    return ok;
+}
+
+
+// ---- line-intersection keypoint synthesis (coordinate_model.py:96-186) ------------------------
+struct SynthTables {  // generated from eagle_b200/pitch.py (csrc/line_families.inc)
+    const uint8_t* yfam_count; const uint8_t* yfam;  // [ny], [ny][maxm]
+    const uint8_t* xfam_count; const uint8_t* xfam;  // [nx], [nx][maxm]
+    const uint8_t* cross;                            // [ny][nx] channel at the crossing or 255
+    int ny, nx, maxm;
+};
+
+// cv::fitLine(pts, DIST_L2, 0, 0.01, 0.01) on the detected members of one family (fitLine2D_wods:
+// moments in double over float products, t = (float)atan2(2dxy, dx2-dy2)/2, direction (cos t, sin t)).
+// Returns false if fewer than 2 members are detected or the direction degenerates (:111).
+EGL_HD bool fit_family_line(const int32_t* xy, uint64_t detected, const uint8_t* members, int count, float* line) {
+    double x = 0, y = 0, x2 = 0, y2 = 0, xy_ = 0;
+    int n = 0;
+    for (int m = 0; m < count; ++m) {
+        const int ch = members[m];
+        if (!((detected >> ch) & 1ull)) continue;
+        const float px = (float)xy[2 * ch], py = (float)xy[2 * ch + 1];
+        x += px; y += py;
+        x2 += (double)fmul(px, px); y2 += (double)fmul(py, py); xy_ += (double)fmul(px, py);
+        ++n;
+    }
+    if (n < 2) return false;
+    const double w = (double)(float)n;
+    x /= w; y /= w; x2 /= w; y2 /= w; xy_ /= w;
+    const double dx2 = dsub(x2, dmul(x, x)), dy2 = dsub(y2, dmul(y, y)), dxy = dsub(xy_, dmul(x, y));
+    const float t = (float)atan2(dmul(2.0, dxy), dsub(dx2, dy2)) / 2.f;
+    // OpenCV calls the C library's cosf/sinf on the float angle; a correctly rounded double
+    // evaluation differs from glibc's cosf by 1 ulp in ~1 % of cases (DESIGN.md, F1 tolerance).
+    line[0] = (float)cos((double)t);
+    line[1] = (float)sin((double)t);
+    line[2] = (float)x;
+    line[3] = (float)y;
+    return !((double)fabsf(line[0]) + (double)fabsf(line[1]) < 1e-6);
+}
+
+// _intersect_lines (:117-138): 2x2 solve in double (LU with partial pivoting as LAPACK's gesv).
+EGL_HD bool intersect_lines(const float* l1, const float* l2, double* px, double* py) {
+    const double vx1 = l1[0], vy1 = l1[1], x01 = l1[2], y01 = l1[3];
+    const double vx2 = l2[0], vy2 = l2[1], x02 = l2[2], y02 = l2[3];
+    const double det = dsub(dmul(vx1, -vy2), dmul(vy1, -vx2));
+    if (fabs(det) < 1e-8) return false;
+    double a00 = vx1, a01 = -vx2, a10 = vy1, a11 = -vy2, b0 = x02 - x01, b1 = y02 - y01;
+    if (fabs(a10) > fabs(a00)) {
+        double t;
+        t = a00; a00 = a10; a10 = t;
+        t = a01; a01 = a11; a11 = t;
+        t = b0; b0 = b1; b1 = t;
+    }
+    if (a00 == 0.0) return false;
+    const double l = dmul(a10, 1.0 / a00);
+    const double u11 = dsub(a11, dmul(l, a01));
+    if (u11 == 0.0) return false;  // numpy raises LinAlgError -> the reference returns None
+    const double s1 = dsub(b1, dmul(l, b0)) / u11;
+    const double t0 = dsub(b0, dmul(a01, s1)) / a00;
+    *px = dadd(x01, dmul(t0, vx1));
+    *py = dadd(y01, dmul(t0, vy1));
+    return true;
+}
+
+EGL_HD int32_t round_half_even_i32(double v) {  // int(round(v)) saturated to int32
+    const double r = rint(v);
+    if (!(r > -2147483648.0)) return (int32_t)0x80000000;
+    if (!(r < 2147483647.0)) return 0x7fffffff;
+    return (int32_t)r;
+}
+
+// _synthesize_keypoints_with_line_intersections (:140-186) for one frame.  xy/order/count are the
+// frame's keypoint arrays; new landmarks are appended to order (and their xy written).  Returns the
+// new total.  Called only when the frame has >= 2 keypoints (:326).
+EGL_HD_NOINLINE int synthesize_keypoints(const SynthTables& T, int32_t* xy, uint8_t* order, int n, int max_new) {
+    uint64_t present = 0;
+    for (int j = 0; j < n; ++j) present |= 1ull << order[j];
+    const uint64_t off_plane = (1ull << 0) | (1ull << 1) | (1ull << 24) | (1ull << 25);
+    const uint64_t detected = present & ~off_plane;
+    float ly[32][4], lx[32][4];
+    uint32_t have_y = 0, have_x = 0;
+    for (int i = 0; i < T.ny; ++i)
+        if (fit_family_line(xy, detected, T.yfam + i * T.maxm, T.yfam_count[i], ly[i])) have_y |= 1u << i;
+    for (int i = 0; i < T.nx; ++i)
+        if (fit_family_line(xy, detected, T.xfam + i * T.maxm, T.xfam_count[i], lx[i])) have_x |= 1u << i;
+    int added = 0;
+    uint64_t added_mask = 0;
+    for (int iy = 0; iy < T.ny && added < max_new; ++iy) {
+        if (!((have_y >> iy) & 1u)) continue;
+        for (int ix = 0; ix < T.nx && added < max_new; ++ix) {
+            if (!((have_x >> ix) & 1u)) continue;
+            const int ch = T.cross[iy * T.nx + ix];
+            if (ch == 255 || ((present >> ch) & 1ull)) continue;
+            double px, py;
+            if (!intersect_lines(ly[iy], lx[ix], &px, &py)) continue;
+            xy[2 * ch] = round_half_even_i32(px);
+            xy[2 * ch + 1] = round_half_even_i32(py);
+            if (!((added_mask >> ch) & 1ull)) {  // a dict: a label can be (re)written, its slot stays
+                added_mask |= 1ull << ch;
+                if (n + added < 64) order[n + added] = (uint8_t)ch;
+                ++added;
+            }
+        }
+    }
+    return n + added;
+}
+
+}  // namespace egl

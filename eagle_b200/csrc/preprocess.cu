@@ -1,0 +1,147 @@
+// K1: uint8 BGR frame -> float32 RGB planes at 540x960, normalised (replaces
+// cv2.cvtColor(BGR2RGB) + A.Resize(540,960) + A.Normalize() + ToTensorV2 + .float(),
+// eagle/models/coordinate_model.py:62-64,221-222,489-491).
+//
+// The resize is OpenCV's INTER_LINEAR for uint8, reproduced bit for bit in integer arithmetic:
+// 11-bit fixed-point tap weights, horizontal pass S[sx]*a0 + S[sx+1]*a1, vertical pass
+// ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2, uint8 result BEFORE normalisation (at exact 2x
+// decimation OpenCV switches to its 2x2-mean fast path, which this recipe equals identically).
+//
+// HBM-bound.  One CTA per output row: the two source rows it needs are pulled into shared memory
+// with two bulk copies on the TMA engine (fully coalesced, no registers), then 240 threads x 4
+// output pixels compute all three channels from shared memory and write one float4 per plane
+// (512 contiguous bytes per warp and plane).  Every source byte and every output float crosses HBM
+// once when the vertical scale is >= 2 (1080p, 4K); at 720p neighbouring output rows share source
+// rows and the second read is served by L2.
+#include "common.cuh"
+#include "geometry_core.cuh"
+
+namespace egl {
+
+constexpr int kOutW = EGL_MODEL_W, kOutH = EGL_MODEL_H;
+constexpr int kPreThreads = kOutW / 4;  // 240
+
+// ImageNet mean/std of A.Normalize(): float32 mean*255 and 1/(std*255), formed as albucore forms them
+__device__ __forceinline__ void norm_consts(float* m, float* d) {
+    m[0] = __fmul_rn(0.485f, 255.f); m[1] = __fmul_rn(0.456f, 255.f); m[2] = __fmul_rn(0.406f, 255.f);
+    d[0] = __fdiv_rn(1.f, __fmul_rn(0.229f, 255.f));
+    d[1] = __fdiv_rn(1.f, __fmul_rn(0.224f, 255.f));
+    d[2] = __fdiv_rn(1.f, __fmul_rn(0.225f, 255.f));
+}
+
+// OpenCV's tap for output index d along an axis of `src` samples: offset, weights (x2048).
+__device__ __forceinline__ void axis_tap(int d, double scale, int* ofs, int* c0, int* c1) {
+    float f = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);
+    const int s = (int)floorf(f);
+    f = __fsub_rn(f, (float)s);
+    *ofs = s;
+    *c0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+    *c1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+__global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* __restrict__ frames, int H, int W,
+                                                                 size_t row_stride, size_t frame_stride, double scale_x,
+                                                                 double scale_y, int use_bulk, float* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char s_rows[];  // 2 rows, each padded to a multiple of 16 B
+    __shared__ uint64_t s_bar;
+    const int tid = threadIdx.x;
+    const int dy = blockIdx.x % kOutH;
+    const int f = blockIdx.x / kOutH;
+    const int row_bytes = 3 * W;
+    const int row_pad = (row_bytes + 15) & ~15;
+
+    int sy, b0, b1;
+    axis_tap(dy, scale_y, &sy, &b0, &b1);
+    const int y0 = min(max(sy, 0), H - 1), y1 = min(max(sy + 1, 0), H - 1);  // rows clamp, weights do not
+    const uint8_t* g0 = frames + (size_t)f * frame_stride + (size_t)y0 * row_stride;
+    const uint8_t* g1 = frames + (size_t)f * frame_stride + (size_t)y1 * row_stride;
+    if (use_bulk) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_fence_init();
+            mbar_expect_tx(&s_bar, 2u * (uint32_t)row_bytes);
+            bulk_g2s(s_rows, g0, (uint32_t)row_bytes, &s_bar);
+            bulk_g2s(s_rows + row_pad, g1, (uint32_t)row_bytes, &s_bar);
+        }
+    } else {
+        for (int i = tid; i < row_bytes; i += kPreThreads) {
+            s_rows[i] = g0[i];
+            s_rows[row_pad + i] = g1[i];
+        }
+    }
+
+    // horizontal taps of this thread's 4 output pixels (independent of the data: overlaps the copy)
+    int xo[4], xo1[4], a0[4], a1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int s, c0, c1;
+        axis_tap(4 * tid + k, scale_x, &s, &c0, &c1);
+        if (s < 0) { s = 0; c0 = 2048; c1 = 0; }
+        if (s >= W - 1) { s = W - 1; c0 = 2048; c1 = 0; }
+        xo[k] = 3 * s;
+        xo1[k] = 3 * min(s + 1, W - 1);
+        a0[k] = c0;
+        a1[k] = c1;
+    }
+    float mean[3], den[3];
+    norm_consts(mean, den);
+
+    if (use_bulk) {
+        __syncthreads();  // barrier init visible to the waiters
+        mbar_wait(&s_bar, 0);
+    } else {
+        __syncthreads();
+    }
+    const uint8_t* r0 = s_rows;
+    const uint8_t* r1 = s_rows + row_pad;
+    float4 o[3];
+    float* op = reinterpret_cast<float*>(o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {  // c indexes the SOURCE byte (B,G,R); plane = 2 - c (RGB)
+            const int top = (int)r0[xo[k] + c] * a0[k] + (int)r0[xo1[k] + c] * a1[k];
+            const int bot = (int)r1[xo[k] + c] * a0[k] + (int)r1[xo1[k] + c] * a1[k];
+            int v = (((b0 * (top >> 4)) >> 16) + ((b1 * (bot >> 4)) >> 16) + 2) >> 2;
+            v = min(max(v, 0), 255);
+            const int plane = 2 - c;
+            op[plane * 4 + k] = __fmul_rn(__fsub_rn((float)v, mean[plane]), den[plane]);
+        }
+    }
+    float* dst = out + ((size_t)f * 3 * kOutH + dy) * kOutW + 4 * tid;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) __stcs(reinterpret_cast<float4*>(dst + (size_t)p * kOutH * kOutW), o[p]);
+}
+
+}  // namespace egl
+
+using namespace egl;
+
+extern "C" int egl_preprocess_u8(const uint8_t* frames, int F, int H, int W, size_t row_stride, size_t frame_stride,
+                                 float* out, void* stream) {
+    EGL_REQUIRE(frames && out, EGL_ERR_NULL, "egl_preprocess_u8: null pointer");
+    EGL_REQUIRE(F >= 0 && H >= 2 && W >= 2, EGL_ERR_SHAPE, "egl_preprocess_u8: bad shape %dx%d", H, W);
+    EGL_REQUIRE(row_stride >= (size_t)3 * W && frame_stride >= row_stride * (size_t)H, EGL_ERR_SHAPE,
+                "egl_preprocess_u8: strides smaller than the frame");
+    EGL_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, EGL_ERR_ALIGN, "egl_preprocess_u8: out must be 16-byte aligned");
+    EGL_REQUIRE((long long)F * kOutH < (1ll << 31), EGL_ERR_SHAPE, "egl_preprocess_u8: too many frames for one launch");
+    if (F == 0) return 0;
+    const int row_bytes = 3 * W;
+    const int row_pad = (row_bytes + 15) & ~15;
+    const size_t smem = 2 * (size_t)row_pad;
+    EGL_REQUIRE(smem <= 200 * 1024, EGL_ERR_SHAPE, "egl_preprocess_u8: frame too wide (%d px)", W);
+    // bulk copies need 16-byte aligned rows of a 16-byte multiple length
+    const int use_bulk = (row_bytes % 16 == 0) && (row_stride % 16 == 0) && (frame_stride % 16 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(frames) & 15) == 0);
+    // OpenCV: inv_scale = dsize/ssize (double); scale = 1./inv_scale
+    const double scale_x = 1. / ((double)kOutW / (double)W);
+    const double scale_y = 1. / ((double)kOutH / (double)H);
+    if (smem > 48 * 1024) {
+        int rc = cuda_status(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                             "egl_preprocess_u8: cudaFuncSetAttribute");
+        if (rc) return rc;
+    }
+    preprocess_kernel<<<(unsigned)(F * kOutH), kPreThreads, smem, (cudaStream_t)stream>>>(frames, H, W, row_stride, frame_stride,
+                                                                                       scale_x, scale_y, use_bulk, out);
+    return cuda_status(cudaGetLastError(), "egl_preprocess_u8: kernel launch");
+}

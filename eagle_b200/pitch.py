@@ -91,3 +91,32 @@ assert OFF_PLANE == (0, 1, 24, 25)
 
 #: bit i set <=> landmark i may be used for the homography (coordinate_model.py:338-344).
 ON_PLANE_MASK = sum(1 << i for i in range(NUM_LANDMARKS) if i not in OFF_PLANE)
+
+#: Iteration order of the reference's GROUND_TRUTH_POINTS dict literal (pitch.py:209-267) as channel
+#: indices.  _build_pitch_groups (coordinate_model.py:76-94) walks that dict, so the order of the
+#: world-x / world-y line families used by the keypoint synthesis follows it.
+REFERENCE_DICT_ORDER = (42, 13, 12, 29, 28, 48, 55, 11, 9, 10, 8, 17, 19, 16, 18, 7, 5, 6, 4, 21, 23, 20,
+                        22, 0, 1, 2, 3, 24, 25, 26, 27, 15, 14, 40, 41, 45, 44, 52, 51, 30, 31, 32, 33, 34,
+                        35, 36, 37, 38, 39, 43, 50, 46, 47, 49, 53, 54, 56)
+
+
+def line_families():
+    """World-y and world-x landmark families and their crossing labels, as the reference builds
+    them (coordinate_model.py:76-94): keys rounded to 2 decimals, on-plane landmarks only, members
+    and families in dict order, first label wins a coordinate.
+
+    Returns (y_families, x_families, cross) where each family is a tuple of channels and
+    cross[iy][ix] is the channel of the landmark at that crossing or -1.
+    """
+    coord_to_label, xg, yg = {}, {}, {}
+    for ch in REFERENCE_DICT_ORDER:
+        x, y, z = WORLD_XYZ[ch]
+        if z != 0.0:
+            continue
+        xr, yr = round(float(x), 2), round(float(y), 2)
+        coord_to_label.setdefault((xr, yr), ch)
+        xg.setdefault(xr, []).append(ch)
+        yg.setdefault(yr, []).append(ch)
+    ykeys, xkeys = list(yg), list(xg)
+    cross = [[coord_to_label.get((xk, yk), -1) for xk in xkeys] for yk in ykeys]
+    return [tuple(yg[k]) for k in ykeys], [tuple(xg[k]) for k in xkeys], cross

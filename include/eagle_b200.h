@@ -1,0 +1,145 @@
+/*
+ * eagle_b200.h -- C ABI of the B200-native per-frame geometry path.
+ *
+ * The reference (nreHieW/Eagle) is pure Python and has no FFI of its own; the entry points below
+ * are what a binding for its geometry path attaches to.  Each one replaces the reference
+ * statements cited beside it (paths relative to the reference root).  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no exceptions; no allocation; no global state other
+ *     than a thread-local last-error string.
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all memory.
+ *   - functions only ENQUEUE work on `stream` (cudaStream_t passed as void*) and return at once.
+ *   - return value: 0 = enqueued, >0 = argument error (EGL_ERR_*), <0 = -(cudaError_t).
+ *   - per-frame soft failures (too few landmarks, degenerate geometry) are reported in the
+ *     per-frame status[] array, never through the return code: the reference never raises on this
+ *     path either (coordinate_model.py:350-352,366-367).
+ */
+#ifndef EAGLE_B200_H_
+#define EAGLE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGL_ABI_VERSION 1
+
+#define EGL_NUM_LANDMARKS 57 /* heatmap channels; eagle/utils/pitch.py:1-59 */
+#define EGL_ORDER_STRIDE 64  /* bytes per frame in kp_order[] */
+#define EGL_MODEL_H 540      /* A.Resize(540, 960); coordinate_model.py:63 */
+#define EGL_MODEL_W 960
+
+/* argument errors */
+#define EGL_ERR_NULL 1
+#define EGL_ERR_SHAPE 2
+#define EGL_ERR_ALIGN 3
+#define EGL_ERR_MODE 4
+
+/* status[] values written by egl_fit_homography */
+#define EGL_FIT_OK 0         /* H, masks valid */
+#define EGL_FIT_FEW_POINTS 1 /* < 4 on-plane landmarks: reference sets compute_homography=True (:350-352) */
+#define EGL_FIT_NO_MODEL 2   /* RANSAC found no model (cv2.findHomography returned None, :363-367) */
+
+/* fit modes */
+#define EGL_FIT_CV2_COMPAT 1 /* OpenCV's RNG, sampling, adaptive stopping: picks the model cv2 picks */
+#define EGL_FIT_FIXED_K 0    /* K hypotheses per frame from an explicit table or the seeded generator */
+
+int egl_version(void);
+const char *egl_last_error(void);
+
+/* Number of SMs of the current device (grid sizing is a multiple of it). */
+int egl_sm_count(void);
+
+/*
+ * K1  uint8 BGR frames -> normalised float32 RGB planes for the keypoint network.
+ * Replaces cv2.cvtColor(BGR2RGB) + A.Resize(540,960) + A.Normalize() + ToTensorV2 + .float()
+ * (coordinate_model.py:62-64, :221-222, :489-491): OpenCV's fixed-point INTER_LINEAR resize
+ * (uint8 result, bit-exact), then (v - 255*mean) * (1/(255*std)), HWC -> CHW.
+ *   frames  [F][H][row_stride] uint8, pixel = B,G,R; row_stride >= 3*W bytes; frame_stride bytes
+ *   out     [F][3][540][960] float32
+ */
+int egl_preprocess_u8(const uint8_t *frames, int F, int H, int W, size_t row_stride, size_t frame_stride,
+                      float *out, void *stream);
+
+/*
+ * K2  heatmaps -> landmark pixel positions.
+ * Replaces KeypointModel.get_keypoints (keypoint_hrnet.py:583-594: per channel flat argmax, first
+ * maximum in row-major order, score = max) and the keypoint post-processing block
+ * (coordinate_model.py:229-248: drop score < keypoint_conf, xi = int(x/(w-1) * img_w),
+ * yi = int(y/(h-1) * img_h), labels sharing a pixel keep the best score).
+ *   hm         [F][57][hm_h][hm_w] float32, 16-byte aligned, hm_h*hm_w % 4 == 0
+ *   kp_flat    [F][57] int32   argmax flat index (all channels)
+ *   kp_score   [F][57] float   maximum (all channels)
+ *   kp_xy      [F][57][2] int32 image pixel (valid for channels listed in kp_order)
+ *   kp_order   [F][64] uint8   kept channels in the reference's dict insertion order
+ *   kp_count   [F][2] int32    {entries in kp_order, entries that came from the heatmaps}
+ */
+int egl_decode_heatmaps(const float *hm, int F, int hm_h, int hm_w, int img_w, int img_h, double keypoint_conf,
+                        int32_t *kp_flat, float *kp_score, int32_t *kp_xy, uint8_t *kp_order, int32_t *kp_count,
+                        void *stream);
+
+/*
+ * F1  line-intersection keypoint synthesis, appended to kp_order / kp_xy in place.
+ * Replaces CoordinateModel._synthesize_keypoints_with_line_intersections
+ * (coordinate_model.py:140-186, with :76-138): per world-y and world-x line family with >= 2
+ * detected on-plane members, cv2.fitLine(DIST_L2); intersections that are labelled landmarks not
+ * yet present are added (rounded half-to-even), at most max_new (30).
+ */
+int egl_synthesize_keypoints(int32_t *kp_xy, uint8_t *kp_order, int32_t *kp_count, int F, int max_new, void *stream);
+
+/*
+ * K3  robust image->pitch homography per frame.
+ * Replaces the correspondence gather (coordinate_model.py:335-349: on-plane channels of kp_order,
+ * in order) and cv2.findHomography(img_pts, world_pts, cv2.RANSAC, 5.0) (:354-357), including
+ * OpenCV's least-squares refit on the inliers, Levenberg-Marquardt polish and the final mask
+ * recomputed from the refined H.
+ *   mode EGL_FIT_CV2_COMPAT: K = iteration cap (2000 = OpenCV's default), hyp/seed ignored.
+ *   mode EGL_FIT_FIXED_K:    K hypotheses per frame; hyp = [F][K][4] uint8 indices into the frame's
+ *                            point list, or NULL to draw them from the counter-based generator (seed).
+ *   thr       reprojection threshold in pitch metres (5.0); confidence 0.995 = OpenCV's default
+ *   H         [F][9] float64 row-major, H[8] == 1 (unchanged when status != EGL_FIT_OK)
+ *   used_mask / inlier_mask [F] uint64, bit = channel
+ *   status    [F] int32 (EGL_FIT_*)
+ *   info      [F][4] int32 {points used, inliers, winning hypothesis index, hypotheses evaluated}
+ */
+int egl_fit_homography(const int32_t *kp_xy, const uint8_t *kp_order, const int32_t *kp_count, int F, int mode,
+                       int K, const uint8_t *hyp, uint64_t seed, double thr, double confidence, double *H,
+                       uint64_t *used_mask, uint64_t *inlier_mask, int32_t *status, int32_t *info, void *stream);
+
+/*
+ * Cadence: which fit does frame f project with?  Replaces the reference's homography state machine
+ * (coordinate_model.py:333 "i % homography_interval == 0 or compute_homography", :350-367 retry on
+ * failure, :375-378 H_use = current else previous) evaluated over fits computed for every frame.
+ *   status    [F] int32 from egl_fit_homography
+ *   interval  homography_interval (>= 1); carry_in = row of H valid before frame 0, or -1
+ *   h_index   [F] int32 out: row of H for frame f, -1 = none yet
+ *   attempted [F] uint8 out: 1 where the reference would have called findHomography on frame f
+ */
+int egl_select_homography(const int32_t *status, int F, int interval, int carry_in, int32_t *h_index,
+                          uint8_t *attempted, void *stream);
+
+/*
+ * K4  projection of all foot points of every frame + visible-pitch boundaries.
+ * Replaces the per-object cv2.perspectiveTransform loop (coordinate_model.py:369-392), the corner
+ * projection and find_x_at_y (:396-414, :32-44).
+ *   H        [*][9] float64; h_index [F] int32 = row of H to use for frame f, or -1 for "no
+ *            homography yet" (reference H_use logic, :375-378); NULL = identity mapping f -> f
+ *   pts      [F][P][2] float32 foot points (Bottom_center), npts [F] int32 (<= P)
+ *   out_f    [F][P][2] float32 projected pitch coordinates before truncation
+ *   out_i    [F][P][2] int64   C-truncated (numpy .astype(int)); INT64_MIN for non-finite
+ *   inb      [F][P] uint8      1 = 0 <= X <= 105 and 0 <= Y <= 68 (-> Transformed_Coordinates kept)
+ *   bounds   [F][4] float64    x of [bottom_left, top_left, top_right, bottom_right]; all NaN when
+ *                              the reference would emit [None]*4
+ */
+int egl_project_points(const double *H, const int32_t *h_index, const float *pts, const int32_t *npts, int F, int P,
+                       int img_w, int img_h, float *out_f, int64_t *out_i, uint8_t *inb, double *bounds,
+                       void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EAGLE_B200_H_ */

@@ -41,7 +41,7 @@ def preprocess_reference_calls(frame_bgr: np.ndarray) -> np.ndarray:
 
 def _axis_taps(src: int, dst: int):
     """Per-output-index (offset, coef0, coef1) of OpenCV's linear resize along one axis."""
-    scale = src / dst
+    scale = 1.0 / (dst / src)  # hal::resize: inv_scale = dsize/ssize, scale = 1./inv_scale
     ofs = np.empty(dst, np.int64)
     c0 = np.empty(dst, np.int64)
     c1 = np.empty(dst, np.int64)

@@ -1,0 +1,121 @@
+// TEST ARTEFACT: compiles eagle_b200/csrc/geometry_core.cuh -- the exact scalar code the CUDA
+// kernels execute -- for the host with g++ -ffp-contract=off, so that its arithmetic can be compared
+// with the oracle on a machine without a GPU (tests/test_host_core.py).  Never used by the product.
+#include <stdint.h>
+#include <string.h>
+#define __constant__ static const
+#include "../../include/eagle_b200.h"
+#include "../../eagle_b200/csrc/geometry_core.cuh"
+
+namespace egl {
+#include "../../eagle_b200/csrc/line_families.inc"
+}
+using namespace egl;
+
+extern "C" {
+
+int hc_postprocess(const int32_t* flat, const float* score, int hm_h, int hm_w, int img_w, int img_h, double conf,
+                   int32_t* xy, uint8_t* order) {
+    return postprocess_keypoints(flat, score, hm_h, hm_w, img_w, img_h, conf, xy, order);
+}
+
+int hc_synthesize(int32_t* xy, uint8_t* order, int n, int max_new) {
+    SynthTables T{kYFamCount, &kYFam[0][0], kXFamCount, &kXFam[0][0], &kCross[0][0], kNumYFam, kNumXFam, kMaxFam};
+    return synthesize_keypoints(T, xy, order, n, max_new);
+}
+
+// sequential replay of ransac_cv2_kernel + refit_kernel for one point list
+int hc_fit_cv2(const float* sx, const float* sy, const float* dx, const float* dy, int N, double thr, double confidence,
+               int max_iters, double* H, uint64_t* mask, int32_t* info) {
+    const float thr_sq = (float)(thr * thr);
+    double scratch[333];
+    info[0] = N; info[1] = 0; info[2] = -1; info[3] = 0;
+    *mask = 0;
+    if (N < 4) return EGL_FIT_FEW_POINTS;
+    if (N == 4) {
+        if (!run_kernel_ls(sx, sy, dx, dy, nullptr, 4, H, scratch)) return EGL_FIT_NO_MODEL;
+        *mask = 0xF; info[1] = 4; info[2] = 0;
+        return EGL_FIT_OK;
+    }
+    CvRng rng{~0ull};
+    int niters = max_iters < 1 ? 1 : max_iters, iter = 0, best = 0;
+    for (; iter < niters; ++iter) {
+        int idx[4];
+        bool found = false;
+        float qx[4], qy[4], rx[4], ry[4];
+        for (int attempt = 0; attempt < 10000 && !found; ++attempt) {
+            draw_subset(rng, N, idx);
+            for (int k = 0; k < 4; ++k) { qx[k] = sx[idx[k]]; qy[k] = sy[idx[k]]; rx[k] = dx[idx[k]]; ry[k] = dy[idx[k]]; }
+            found = check_subset(qx, qy, rx, ry);
+        }
+        if (!found) break;
+        double Hm[9];
+        if (!dlt4_f64(qx, qy, rx, ry, Hm)) continue;
+        uint64_t m;
+        const int c = inlier_mask_f32(Hm, sx, sy, dx, dy, N, thr_sq, &m);
+        if (c > (best > 3 ? best : 3)) {
+            best = c; *mask = m; info[2] = iter;
+            memcpy(H, Hm, sizeof(Hm));
+            niters = ransac_update_num_iters(confidence, (double)(N - c) / N, 4, niters);
+        }
+    }
+    info[3] = iter;
+    if (best == 0) return EGL_FIT_NO_MODEL;
+    uint64_t fm;
+    info[1] = refit_on_inliers(H, sx, sy, dx, dy, N, *mask, thr_sq, &fm, scratch);
+    *mask = fm;
+    return EGL_FIT_OK;
+}
+
+// sequential replay of ransac_fixedk_kernel (hypothesis stage only): best model in float, its
+// position mask, count and index
+int hc_fixedk_stage(const float* sx, const float* sy, const float* dx, const float* dy, int N, int K, const uint8_t* hyp,
+                    uint64_t seed, uint64_t frame, double thr, float* Hbest, uint64_t* mask, int32_t* info) {
+    const float thr_sq = (float)(thr * thr);
+    int best = 0, best_h = -1;
+    for (int h = 0; h < K; ++h) {
+        int idx[4];
+        if (hyp) { for (int k = 0; k < 4; ++k) idx[k] = hyp[4 * h + k]; }
+        else seeded_subset(seed, frame, (uint64_t)K, (uint64_t)h, N, idx);
+        bool ok = idx[0] < N && idx[1] < N && idx[2] < N && idx[3] < N;
+        ok = ok && idx[0] != idx[1] && idx[0] != idx[2] && idx[0] != idx[3] && idx[1] != idx[2] && idx[1] != idx[3] && idx[2] != idx[3];
+        if (!ok) continue;
+        float qx[4], qy[4], rx[4], ry[4];
+        for (int k = 0; k < 4; ++k) { qx[k] = sx[idx[k]]; qy[k] = sy[idx[k]]; rx[k] = dx[idx[k]]; ry[k] = dy[idx[k]]; }
+        if (!check_subset(qx, qy, rx, ry)) continue;
+        float Hf[9];
+        if (!dlt4_f32(qx, qy, rx, ry, Hf)) continue;
+        int c = 0;
+        for (int i = 0; i < N; ++i) c += reproj_err_f32(Hf, sx[i], sy[i], dx[i], dy[i]) <= thr_sq;
+        if (c > best) { best = c; best_h = h; memcpy(Hbest, Hf, 9 * sizeof(float)); }
+    }
+    info[0] = N; info[1] = best; info[2] = best_h; info[3] = K;
+    *mask = 0;
+    if (best <= 3) return EGL_FIT_NO_MODEL;
+    double Hd[9];
+    for (int k = 0; k < 8; ++k) Hd[k] = Hbest[k];
+    Hd[8] = 1.0;
+    inlier_mask_f32(Hd, sx, sy, dx, dy, N, thr_sq, mask);
+    return EGL_FIT_OK;
+}
+
+int hc_refit(double* H, const float* sx, const float* sy, const float* dx, const float* dy, int N, uint64_t ransac_mask,
+             double thr, uint64_t* final_mask) {
+    double scratch[333];
+    return refit_on_inliers(H, sx, sy, dx, dy, N, ransac_mask, (float)(thr * thr), final_mask, scratch);
+}
+
+int hc_dlt4_f32(const float* sx, const float* sy, const float* dx, const float* dy, float* H) { return dlt4_f32(sx, sy, dx, dy, H); }
+int hc_dlt4_f64(const float* sx, const float* sy, const float* dx, const float* dy, double* H) { return dlt4_f64(sx, sy, dx, dy, H); }
+int hc_check_subset(const float* sx, const float* sy, const float* dx, const float* dy) { return check_subset(sx, sy, dx, dy); }
+void hc_seeded_subset(uint64_t seed, uint64_t frame, uint64_t K, uint64_t h, int N, int* idx) { seeded_subset(seed, frame, K, h, N, idx); }
+
+void hc_project(const double* H, const float* pts, int n, float* out_f, int64_t* out_i) {
+    for (int i = 0; i < n; ++i) {
+        perspective_point(H, pts[2 * i], pts[2 * i + 1], &out_f[2 * i], &out_f[2 * i + 1]);
+        out_i[2 * i] = trunc_like_numpy(out_f[2 * i]);
+        out_i[2 * i + 1] = trunc_like_numpy(out_f[2 * i + 1]);
+    }
+}
+
+}  // extern "C"
