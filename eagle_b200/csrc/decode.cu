@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(kDecThreads, 1) argmax_kernel(DecodeArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long m0 = a.total_maps * blockIdx.x / gridDim.x;
     const long long m1 = a.total_maps * (blockIdx.x + 1) / gridDim.x;
-    const long long nchunks = (m1 - m0) * a.chunks_per_map;
+    const int cpm = a.chunks_per_map, chunk_f4 = a.chunk_f4, map_f4 = a.map_f4;
+    const int nchunks = (int)(m1 - m0) * cpm;  // < 2^31: a CTA owns at most total_maps/gridDim maps
     if (nchunks == 0) return;
 
     if (tid == 0) {
@@ -58,47 +59,55 @@ __global__ void __launch_bounds__(kDecThreads, 1) argmax_kernel(DecodeArgs a) {
     }
     __syncthreads();
 
-    auto issue = [&](long long c) {  // called by thread 0 only
-        const long long map = m0 + c / a.chunks_per_map;
-        const int k = (int)(c % a.chunks_per_map);
-        const int off = k * a.chunk_f4;
-        const int n = min(a.chunk_f4, a.map_f4 - off);
-        const int stage = (int)(c % kStages);
-        mbar_expect_tx(&full[stage], (uint32_t)n * 16u);
-        bulk_g2s(ring + (size_t)stage * a.chunk_f4, a.hm + map * a.map_f4 + off, (uint32_t)n * 16u, &full[stage]);
+    // producer state (thread 0 only): next chunk to request
+    const float4* issue_src = a.hm + m0 * map_f4;  // advances chunk by chunk; maps are contiguous
+    int issue_k = 0, issue_stage = 0, issued = 0;
+    auto issue = [&]() {
+        const int off = issue_k * chunk_f4;
+        const int n = min(chunk_f4, map_f4 - off);
+        mbar_expect_tx(&full[issue_stage], (uint32_t)n * 16u);
+        bulk_g2s(ring + (size_t)issue_stage * chunk_f4, issue_src, (uint32_t)n * 16u, &full[issue_stage]);
+        issue_src += n;
+        if (++issue_k == cpm) issue_k = 0;
+        if (++issue_stage == kStages) issue_stage = 0;
+        ++issued;
     };
-    if (tid == 0) {
-        const long long pre = nchunks < kStages ? nchunks : kStages;
-        for (long long c = 0; c < pre; ++c) issue(c);
-    }
+    if (tid == 0)
+        while (issued < kStages && issued < nchunks) issue();
 
     // (max, flat index) of the current map as seen by this thread.  The index starts at the first
-    // element the thread will visit so that an all -inf map still decodes to index 0 like np.argmax.
-    const int first_bi = tid < a.chunk_f4 ? tid * 4 : 0x7fffffff;
+    // element the thread visits so that an all -inf map still decodes to index 0 like np.argmax.
+    const int first_bi = tid < chunk_f4 ? tid * 4 : 0x7fffffff;
     float bv = -INFINITY;
     int bi = first_bi;
     bool bnan = false;
-    for (long long c = 0; c < nchunks; ++c) {
-        const int stage = (int)(c % kStages);
-        const int k = (int)(c % a.chunks_per_map);
-        const int off = k * a.chunk_f4;
-        const int n = min(a.chunk_f4, a.map_f4 - off);
-        if (k == 0) { bv = -INFINITY; bi = first_bi; bnan = false; }
-        mbar_wait(&full[stage], (uint32_t)((c / kStages) & 1));
-        const float4* src = ring + (size_t)stage * a.chunk_f4;
-        // ascending flat index per thread, strict '>' keeps the first maximum
+    int stage = 0, k = 0;
+    uint32_t phase = 0;
+    long long map = m0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int off = k * chunk_f4;
+        const int n = min(chunk_f4, map_f4 - off);
+        mbar_wait(&full[stage], phase);
+        const float4* src = ring + (size_t)stage * chunk_f4;
+        // Each thread walks its float4s in ascending flat index.  Fast path: one 4-way max and a
+        // NaN probe (the sum); only when the float4 holds a new maximum (rare: ~ln(n) times per
+        // map) or a NaN is the exact element-by-element np.argmax update executed.
 #pragma unroll 4
         for (int i = tid; i < n; i += kDecThreads) {
             const float4 v = src[i];
-            const int base = (off + i) * 4;
-            const float e[4] = {v.x, v.y, v.z, v.w};
+            const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+            const float sum = (v.x + v.y) + (v.z + v.w);
+            if (m > bv || sum != sum) {
+                const int base = (off + i) * 4;
+                const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool take = !bnan && (e[j] > bv || e[j] != e[j]);
-                if (take) { bv = e[j]; bi = base + j; bnan = e[j] != e[j]; }
+                for (int j = 0; j < 4; ++j) {
+                    const bool take = !bnan && (e[j] > bv || e[j] != e[j]);
+                    if (take) { bv = e[j]; bi = base + j; bnan = e[j] != e[j]; }
+                }
             }
         }
-        const bool last = (k == a.chunks_per_map - 1);
+        const bool last = (k == cpm - 1);
         if (last) {
             float v = bv;
             int ix = bi;
@@ -109,9 +118,10 @@ __global__ void __launch_bounds__(kDecThreads, 1) argmax_kernel(DecodeArgs a) {
                 if (better(ov, oi, v, ix)) { v = ov; ix = oi; }
             }
             if (lane == 0) { s_val[warp] = v; s_idx[warp] = ix; }
+            bv = -INFINITY; bi = first_bi; bnan = false;
         }
         __syncthreads();  // all reads of this stage are done (and s_val/s_idx are visible)
-        if (tid == 0 && c + kStages < nchunks) issue(c + kStages);
+        if (tid == 0 && issued < nchunks) issue();
         if (last && warp == 0) {
             float v = lane < kDecWarps ? s_val[lane] : -INFINITY;
             int ix = lane < kDecWarps ? s_idx[lane] : 0x7fffffff;
@@ -122,11 +132,12 @@ __global__ void __launch_bounds__(kDecThreads, 1) argmax_kernel(DecodeArgs a) {
                 if (better(ov, oi, v, ix)) { v = ov; ix = oi; }
             }
             if (lane == 0) {
-                const long long map = m0 + c / a.chunks_per_map;
                 a.kp_flat[map] = ix;
                 a.kp_score[map] = v;
             }
         }
+        if (++k == cpm) { k = 0; ++map; }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
     }
 }
 
