@@ -10,14 +10,14 @@
 //     to 5 x 32 KB in flight per SM with no registers tied up by loads.  The 8 warps scan a chunk
 //     with LDS.128, keeping (max, first flat index) per thread; per map a warp-shuffle arg-max and
 //     a cross-warp step produce the result.  Ties resolve to the lowest flat index = np.argmax.
-//   * postprocess_kernel -- one thread per frame over the 57 (index, score) pairs: confidence
+//   * postprocess_kernel -- one warp per frame over the 57 (index, score) pairs: confidence
 //     filter, scale to image pixels, duplicate-pixel arbitration, reference dict order.
 #include "common.cuh"
 #include "geometry_core.cuh"
 
 namespace egl {
 
-constexpr int kDecThreads = 256;
+constexpr int kDecThreads = 512;
 constexpr int kDecWarps = kDecThreads / 32;
 constexpr int kStages = 6;
 constexpr int kChunkF4Max = 2025;  // float4 per stage: 32,400 B
@@ -89,22 +89,28 @@ __global__ void __launch_bounds__(kDecThreads, 1) argmax_kernel(DecodeArgs a) {
         const int n = min(chunk_f4, map_f4 - off);
         mbar_wait(&full[stage], phase);
         const float4* src = ring + (size_t)stage * chunk_f4;
-        // Each thread walks its float4s in ascending flat index.  Fast path: one 4-way max and a
-        // NaN probe (the sum); only when the float4 holds a new maximum (rare: ~ln(n) times per
-        // map) or a NaN is the exact element-by-element np.argmax update executed.
+        // Each thread walks its float4s in ascending flat index, branch-free: 4-way max, first lane
+        // of the float4 equal to it, and a predicated update when it beats the running maximum
+        // (strict '>' keeps the earliest index).  NaNs -- which np.argmax ranks above everything --
+        // are detected by the sum probe and handled on a cold, exact element-by-element path.
 #pragma unroll 4
         for (int i = tid; i < n; i += kDecThreads) {
             const float4 v = src[i];
             const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
             const float sum = (v.x + v.y) + (v.z + v.w);
-            if (m > bv || sum != sum) {
-                const int base = (off + i) * 4;
+            const int base = (off + i) * 4;
+            if (sum != sum) {  // NaN (or +inf and -inf together) in this float4: exact slow path
                 const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const bool take = !bnan && (e[j] > bv || e[j] != e[j]);
                     if (take) { bv = e[j]; bi = base + j; bnan = e[j] != e[j]; }
                 }
+            } else {
+                const int j = v.x == m ? 0 : (v.y == m ? 1 : (v.z == m ? 2 : 3));
+                const bool upd = !bnan && m > bv;
+                bv = upd ? m : bv;
+                bi = upd ? base + j : bi;
             }
         }
         const bool last = (k == cpm - 1);
@@ -141,23 +147,85 @@ __global__ void __launch_bounds__(kDecThreads, 1) argmax_kernel(DecodeArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(64) postprocess_kernel(const int32_t* __restrict__ kp_flat, const float* __restrict__ kp_score,
-                                                         int F, int hm_h, int hm_w, int img_w, int img_h, double conf,
-                                                         int32_t* kp_xy, uint8_t* kp_order, int32_t* kp_count) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+// Keypoint post-processing, one warp per frame (the sequential statement of the same rules is
+// postprocess_keypoints() in geometry_core.cuh, which the CPU tests pin against the reference):
+// lane l owns channels l and l+32; the 57 (pixel, score, kept) triples are staged in shared memory
+// and every lane scans them for its duplicate-pixel group; ballots turn the "emits" flags into the
+// reference's dict order.
+constexpr int kPostWarps = 4;
+
+__global__ void __launch_bounds__(kPostWarps * 32) postprocess_kernel(const int32_t* __restrict__ kp_flat,
+                                                                     const float* __restrict__ kp_score, int F, int hm_h,
+                                                                     int hm_w, int img_w, int img_h, double conf,
+                                                                     int32_t* kp_xy, uint8_t* kp_order, int32_t* kp_count) {
+    __shared__ int s_x[kPostWarps][64], s_y[kPostWarps][64];
+    __shared__ float s_s[kPostWarps][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * kPostWarps + warp;
     if (f >= F) return;
-    int32_t flat[kLandmarks], xy[2 * kLandmarks];
-    float score[kLandmarks];
-    uint8_t order[EGL_ORDER_STRIDE];
-    for (int c = 0; c < kLandmarks; ++c) {
-        flat[c] = kp_flat[(size_t)f * kLandmarks + c];
-        score[c] = kp_score[(size_t)f * kLandmarks + c];
+    const double wden = (double)(hm_w - 1 > 1 ? hm_w - 1 : 1), hden = (double)(hm_h - 1 > 1 ? hm_h - 1 : 1);
+    unsigned kept_bits[2];
+    int own_x[2], own_y[2];
+    float own_s[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        bool kept = false;
+        int xi = 0, yi = 0;
+        float sc = 0.f;
+        if (c < kLandmarks) {
+            const int fl = kp_flat[(size_t)f * kLandmarks + c];
+            sc = kp_score[(size_t)f * kLandmarks + c];
+            const int y = fl / hm_w, x = fl - y * hm_w;
+            const double scd = (double)sc;
+            kept = (scd > 0.01) && !(scd < conf);
+            xi = (int)__dmul_rn((double)x / wden, (double)img_w);
+            yi = (int)__dmul_rn((double)y / hden, (double)img_h);
+            kp_xy[((size_t)f * kLandmarks + c) * 2] = xi;
+            kp_xy[((size_t)f * kLandmarks + c) * 2 + 1] = yi;
+        }
+        s_x[warp][c] = xi; s_y[warp][c] = yi; s_s[warp][c] = sc;
+        own_x[h] = xi; own_y[h] = yi; own_s[h] = sc;
+        kept_bits[h] = __ballot_sync(kFull, kept);
     }
-    const int n = postprocess_keypoints(flat, score, hm_h, hm_w, img_w, img_h, conf, xy, order);
-    for (int c = 0; c < 2 * kLandmarks; ++c) kp_xy[(size_t)f * 2 * kLandmarks + c] = xy[c];
-    for (int j = 0; j < EGL_ORDER_STRIDE; ++j) kp_order[(size_t)f * EGL_ORDER_STRIDE + j] = j < n ? order[j] : 0xFF;
-    kp_count[2 * f] = n;
-    kp_count[2 * f + 1] = n;
+    __syncwarp();
+    const unsigned long long kept_mask = ((unsigned long long)kept_bits[1] << 32) | kept_bits[0];
+    unsigned emit_bits[2];
+    int label[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        bool emit = false;
+        int last = c;
+        if ((kept_mask >> c) & 1ull) {
+            float gmax = own_s[h];
+            unsigned long long same = 0;
+            for (int o = 0; o < kLandmarks; ++o) {
+                const bool sm = ((kept_mask >> o) & 1ull) && s_x[warp][o] == own_x[h] && s_y[warp][o] == own_y[h];
+                if (sm) { same |= 1ull << o; gmax = fmaxf(gmax, s_s[warp][o]); }
+            }
+            if (own_s[h] == gmax) {  // this channel holds the group's best score
+                emit = true;
+                for (int o = 0; o < kLandmarks; ++o) {
+                    if (!((same >> o) & 1ull) || s_s[warp][o] != gmax) continue;
+                    if (o < c) emit = false;   // an earlier tied channel owns the dict slot
+                    if (o > last) last = o;    // ... but the latest tied channel provides the label
+                }
+            }
+        }
+        emit_bits[h] = __ballot_sync(kFull, emit);
+        label[h] = last;
+        if (emit) {
+            const int pos = (h ? __popc(emit_bits[0]) : 0) + __popc(emit_bits[h] & ((1u << lane) - 1u));
+            kp_order[(size_t)f * EGL_ORDER_STRIDE + pos] = (uint8_t)last;
+        }
+    }
+    const int n = __popc(emit_bits[0]) + __popc(emit_bits[1]);
+    for (int j = n + lane; j < EGL_ORDER_STRIDE; j += 32) kp_order[(size_t)f * EGL_ORDER_STRIDE + j] = 0xFF;
+    if (lane == 0) {
+        kp_count[2 * f] = n;
+        kp_count[2 * f + 1] = n;
+    }
 }
 
 }  // namespace egl
@@ -200,7 +268,7 @@ extern "C" int egl_decode_heatmaps(const float* hm, int F, int hm_h, int hm_w, i
     argmax_kernel<<<(unsigned)grid, kDecThreads, smem, s>>>(a);
     int rc = cuda_status(cudaGetLastError(), "egl_decode_heatmaps: argmax kernel launch");
     if (rc) return rc;
-    postprocess_kernel<<<(F + 63) / 64, 64, 0, s>>>(kp_flat, kp_score, F, hm_h, hm_w, img_w, img_h, keypoint_conf, kp_xy,
+    postprocess_kernel<<<(F + kPostWarps - 1) / kPostWarps, kPostWarps * 32, 0, s>>>(kp_flat, kp_score, F, hm_h, hm_w, img_w, img_h, keypoint_conf, kp_xy,
                                                     kp_order, kp_count);
     return cuda_status(cudaGetLastError(), "egl_decode_heatmaps: postprocess kernel launch");
 }

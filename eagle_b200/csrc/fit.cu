@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kCv2Warps * 32) ransac_cv2_kernel(FitArgs a) {
     }
     if (N == 4) {  // findHomography: npoints == 4 -> plain runKernel, mask of ones, no refinement
         if (lane == 0) {
-            double scratch[171];
+            double scratch[192];
             const bool ok = run_kernel_ls(pl.sx, pl.sy, pl.dx, pl.dy, nullptr, 4, H, scratch);
             park(a, f, ok ? EGL_FIT_OK : EGL_FIT_NO_MODEL, 4, ok ? 4 : 0, 0, 0, H, ok ? 0xFull : 0ull, used);
         }
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(kRefitThreads) refit_kernel(FitArgs a) {
     uint64_t pm = a.inlier_mask[f];
     int count = a.info[4 * f + 1];
     if (N > 4) {
-        double scratch[333];
+        double scratch[192];
         uint64_t fm;
         count = refit_on_inliers(H, sx, sy, dx, dy, N, pm, a.thr_sq, &fm, scratch);
         pm = fm;

@@ -167,63 +167,73 @@ EGL_HD bool gauss_solve(double* a, double* x) {
     return true;
 }
 
-// Cyclic Jacobi eigen-decomposition of a symmetric 9x9 matrix (row-major A, destroyed).
-// On return w[i] are the eigenvalues and column i of V (V[k*9+i]) the matching unit eigenvector.
-EGL_HD_NOINLINE void jacobi9(double* A, double* V, double* w) {
-    constexpr int n = 9;
-    for (int i = 0; i < n * n; ++i) V[i] = 0.0;
-    for (int i = 0; i < n; ++i) V[i * n + i] = 1.0;
-    for (int sweep = 0; sweep < 30; ++sweep) {
-        double off = 0.0, diag = 0.0;
-        for (int p = 0; p < n; ++p) {
-            diag += A[p * n + p] * A[p * n + p];
-            for (int q = p + 1; q < n; ++q) off += A[p * n + q] * A[p * n + q];
+// Unit eigenvector of the SMALLEST eigenvalue of a symmetric positive semi-definite 9x9 matrix
+// (row-major A, destroyed) by inverse iteration: one LU factorisation of A + sigma*I with a tiny
+// relative shift (so that an exactly singular A -- noise-free correspondences -- still factors),
+// then a few back-substitutions.  OpenCV takes the same vector from a full Jacobi
+// eigen-decomposition (cv::eigen); the two agree to rounding whenever that eigenvalue is simple,
+// and this costs ~1/20 of the work.  aug: 9*10 doubles of scratch.  Returns false for A == 0.
+EGL_HD_NOINLINE bool smallest_eigvec9(const double* A, double* aug, double* h) {
+    constexpr int n = 9, S = 10;
+    double tr = 0;
+    for (int i = 0; i < n; ++i) tr += A[i * n + i];
+    if (!(tr > 0.0) || !isfinite(tr)) return false;
+    const double sigma = tr * 1e-15;
+    double y[n], z[n];
+    for (int i = 0; i < n; ++i) y[i] = 1.0 / (1.37 + i);  // generic start, not orthogonal to anything special
+    double prev = 1e300;
+    for (int it = 0; it < 48; ++it) {
+        // (re)build the augmented system: elimination is redone per iteration (n^3/3 = 243 FMAs),
+        // which keeps the code to one routine; iterations needed: 2-5
+        for (int i = 0; i < n; ++i) {
+            for (int j = 0; j < n; ++j) aug[i * S + j] = A[i * n + j];
+            aug[i * S + i] += sigma;
+            aug[i * S + n] = y[i];
         }
-        if (off <= 1e-32 * diag || off == 0.0) break;
-        for (int p = 0; p < n - 1; ++p)
-            for (int q = p + 1; q < n; ++q) {
-                const double apq = A[p * n + q];
-                if (apq == 0.0) continue;
-                const double app = A[p * n + p], aqq = A[q * n + q];
-                const double theta = (aqq - app) / (2.0 * apq);
-                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < n; ++k) {  // columns p,q: A <- A J
-                    const double akp = A[k * n + p], akq = A[k * n + q];
-                    A[k * n + p] = c * akp - s * akq;
-                    A[k * n + q] = s * akp + c * akq;
-                }
-                for (int k = 0; k < n; ++k) {  // rows p,q: A <- J^T A
-                    const double apk = A[p * n + k], aqk = A[q * n + k];
-                    A[p * n + k] = c * apk - s * aqk;
-                    A[q * n + k] = s * apk + c * aqk;
-                }
-                A[p * n + q] = A[q * n + p] = 0.0;
-                for (int k = 0; k < n; ++k) {
-                    const double vkp = V[k * n + p], vkq = V[k * n + q];
-                    V[k * n + p] = c * vkp - s * vkq;
-                    V[k * n + q] = s * vkp + c * vkq;
-                }
-            }
+        if (!gauss_solve<9>(aug, z)) return false;
+        double nrm = 0, big = 0;
+        int bi = 0;
+        for (int i = 0; i < n; ++i) {
+            nrm += z[i] * z[i];
+            if (fabs(z[i]) > big) { big = fabs(z[i]); bi = i; }
+        }
+        if (!(nrm > 0.0) || !isfinite(nrm)) return false;
+        const double sc = (z[bi] < 0 ? -1.0 : 1.0) / sqrt(nrm);
+        double diff = 0;
+        for (int i = 0; i < n; ++i) {
+            z[i] *= sc;
+            diff = fmax(diff, fabs(z[i] - y[i]));
+            y[i] = z[i];
+        }
+        if (diff <= 4e-16 || (diff <= 1e-13 && diff >= prev)) break;  // converged / stagnated at rounding level
+        prev = diff;
     }
-    for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
+    for (int i = 0; i < n; ++i) h[i] = y[i];
+    return true;
 }
 
-// cv::solve(A, b, x, DECOMP_EIG) for a symmetric 9x9 A given its eigen-decomposition: the
-// back-substitution of SVBkSb with OpenCV's threshold (2*DBL_EPSILON * sum of eigenvalues), i.e.
-// a pseudo-inverse when A is singular (the 9-parameter homography has a scale gauge freedom).
-EGL_HD void eig_backsolve9(const double* V, const double* w, const double* b, double* x) {
-    double thr = 0.0;
-    for (int i = 0; i < 9; ++i) thr += w[i];
-    thr *= 2.0 * DBL_EPSILON;
-    for (int k = 0; k < 9; ++k) x[k] = 0.0;
-    for (int i = 0; i < 9; ++i) {
-        if (fabs(w[i]) <= thr) continue;
-        double s = 0.0;
-        for (int k = 0; k < 9; ++k) s += V[k * 9 + i] * b[k];
-        s /= w[i];
-        for (int k = 0; k < 9; ++k) x[k] += s * V[k * 9 + i];
+// Minimum-norm solution of the singular symmetric system A d = v whose null vector is x (the
+// 9-parameter homography cost is scale invariant, so J x = 0): solved through the bordered system
+// [[A, s*x],[s*x^T, 0]] [d; mu] = [v; 0].  This is what cv::solve(..., DECOMP_EIG) returns for such
+// an A (its back-substitution drops the zero eigenvalue).  aug: 10*11 doubles.
+EGL_HD_NOINLINE bool solve_gauge_fixed9(const double* A, const double* x, const double* v, double* aug, double* d) {
+    constexpr int n = 9, S = 11;
+    double xn = 0, dmax = 0;
+    for (int i = 0; i < n; ++i) { xn += x[i] * x[i]; dmax = fmax(dmax, fabs(A[i * n + i])); }
+    if (!(xn > 0.0) || !(dmax > 0.0)) return false;
+    const double s = dmax / sqrt(xn);
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) aug[i * S + j] = A[i * n + j];
+        aug[i * S + n] = s * x[i];
+        aug[i * S + n + 1] = v[i];
+        aug[n * S + i] = s * x[i];
     }
+    aug[n * S + n] = 0.0;
+    aug[n * S + n + 1] = 0.0;
+    double sol[10];
+    if (!gauss_solve<10>(aug, sol)) return false;
+    for (int i = 0; i < n; ++i) d[i] = sol[i];
+    return true;
 }
 
 // ---- HomographyEstimatorCallback::runKernel: normalised DLT on n >= 4 correspondences ---------
@@ -290,21 +300,18 @@ EGL_HD void dlt_denormalise(const double* h0, const double* norm, double* H) {
     for (int i = 0; i < 9; ++i) H[i] *= s;
 }
 
-// runKernel on the points selected by idx[0..n).  scratch: 81+81+9 doubles.
+// runKernel on the points selected by idx[0..n).  scratch: 81 + 90 doubles.
 EGL_HD_NOINLINE bool run_kernel_ls(const float* sx, const float* sy, const float* dx, const float* dy,
                                    const uint8_t* idx, int n, double* H, double* scratch) {
     double* LtL = scratch;
-    double* V = scratch + 81;
-    double* w = scratch + 162;
+    double* aug = scratch + 81;
     double norm[8];
     if (!dlt_normal_matrix(sx, sy, dx, dy, idx, n, LtL, norm)) return false;
-    jacobi9(LtL, V, w);
-    int m = 0;
-    for (int i = 1; i < 9; ++i)
-        if (w[i] < w[m]) m = i;
     double h0[9];
-    for (int k = 0; k < 9; ++k) h0[k] = V[k * 9 + m];
+    if (!smallest_eigvec9(LtL, aug, h0)) return false;
     dlt_denormalise(h0, norm, H);
+    for (int i = 0; i < 9; ++i)
+        if (!isfinite(H[i])) return false;
     return true;
 }
 
@@ -416,13 +423,14 @@ EGL_HD double lm_cost(const double* h, const float* sx, const float* sy, const f
 }
 
 // LMSolverImpl::run with maxIters = 10, eps = FLT_EPSILON, followed by the 1/h33 rescale of
-// findHomography.  scratch: 4*81 + 9 doubles.  Returns the iterations run.
+// findHomography.  OpenCV solves each damped system with cv::solve(DECOMP_EIG); here the damped
+// (positive definite) system goes through Gaussian elimination and the undamped, gauge-singular one
+// through solve_gauge_fixed9 -- the same solutions up to rounding.  scratch: 81 + 110 doubles.
+// Returns the iterations run.
 EGL_HD_NOINLINE int lm_refine(double* H, const float* sx, const float* sy, const float* dx, const float* dy,
                               const uint8_t* idx, int n, double* scratch) {
     double* A = scratch;         // J^T J
-    double* Ap = scratch + 81;   // damped copy, destroyed by jacobi9
-    double* V = scratch + 162;
-    double* w = scratch + 243;   // 9
+    double* aug = scratch + 81;  // 10 x 11 augmented system
     double x[9], xd[9], v[9], d[9], D[9];
     for (int i = 0; i < 9; ++i) x[i] = H[i];
     double S, rmax;
@@ -432,10 +440,19 @@ EGL_HD_NOINLINE int lm_refine(double* H, const float* sx, const float* sy, const
     double lambda = 1, lc = 0.75;
     int iter = 0;
     for (;;) {
-        for (int i = 0; i < 81; ++i) Ap[i] = A[i];
-        for (int i = 0; i < 9; ++i) Ap[i * 9 + i] += lambda * D[i];
-        jacobi9(Ap, V, w);
-        eig_backsolve9(V, w, v, d);
+        bool ok;
+        if (lambda > 0) {
+            for (int i = 0; i < 9; ++i) {
+                for (int j = 0; j < 9; ++j) aug[i * 10 + j] = A[i * 9 + j];
+                aug[i * 10 + i] += lambda * D[i];
+                aug[i * 10 + 9] = v[i];
+            }
+            ok = gauss_solve<9>(aug, d);
+        } else {
+            ok = solve_gauge_fixed9(A, x, v, aug, d);
+        }
+        if (!ok)
+            for (int i = 0; i < 9; ++i) d[i] = 0.0;
         for (int i = 0; i < 9; ++i) xd[i] = x[i] - d[i];
         const double Sd = lm_cost(xd, sx, sy, dx, dy, idx, n);
         double dS = 0;
@@ -454,18 +471,13 @@ EGL_HD_NOINLINE int lm_refine(double* H, const float* sx, const float* sy, const
             double nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1) + 2;
             nu = fmin(fmax(nu, 2.), 10.);
             if (lambda == 0) {
-                // invert(A, Ap, DECOMP_EIG): pseudo-inverse; only its diagonal is used
-                for (int i = 0; i < 81; ++i) Ap[i] = A[i];
-                jacobi9(Ap, V, w);
-                double thr = 0;
-                for (int i = 0; i < 9; ++i) thr += w[i];
-                thr *= 2.0 * DBL_EPSILON;
+                // invert(A, Ap, DECOMP_EIG): pseudo-inverse of the gauge-singular A; only the largest
+                // diagonal entry is used.  Column k of A^+ = gauge-fixed solution for e_k.
                 double maxval = DBL_EPSILON;
                 for (int k = 0; k < 9; ++k) {
-                    double dk = 0;
-                    for (int i = 0; i < 9; ++i)
-                        if (fabs(w[i]) > thr) dk += V[k * 9 + i] * V[k * 9 + i] / w[i];
-                    maxval = fmax(maxval, fabs(dk));
+                    double e[9], col[9];
+                    for (int i = 0; i < 9; ++i) e[i] = (i == k) ? 1.0 : 0.0;
+                    if (solve_gauge_fixed9(A, x, e, aug, col)) maxval = fmax(maxval, fabs(col[k]));
                 }
                 lambda = lc = 1. / maxval;
                 nu *= 0.5;
@@ -508,7 +520,7 @@ EGL_HD int inlier_mask_f32(const double* H, const float* sx, const float* sy, co
 }
 
 // The tail of cv2.findHomography after RANSAC picked `H` (best model) with inlier list mask:
-// runKernel on the inliers, LM polish, mask recomputed from the refined H.  scratch >= 333 doubles.
+// runKernel on the inliers, LM polish, mask recomputed from the refined H.  scratch >= 192 doubles.
 EGL_HD_NOINLINE int refit_on_inliers(double* H, const float* sx, const float* sy, const float* dx, const float* dy, int n,
                                      uint64_t ransac_mask, float thr_sq, uint64_t* final_mask, double* scratch) {
     uint8_t idx[64];

@@ -70,7 +70,7 @@ class GeometryEngine:
         if out is None:
             out = torch.empty((F, 3, N.MODEL_H, N.MODEL_W), dtype=torch.float32, device=frames.device)
         with torch.cuda.device(frames.device):
-            N.check(N.lib.egl_preprocess_u8(_ptr(frames), F, H, W, frames.stride(1), frames.stride(0),
+            N.check(N.lib.egl_preprocess_u8(_ptr(frames), F, H, W, frames.stride(1), frames.stride(0) if F > 1 else H * frames.stride(1),
                                             _ptr(out), _stream()), "egl_preprocess_u8")
         return out
 

@@ -28,7 +28,7 @@ int hc_synthesize(int32_t* xy, uint8_t* order, int n, int max_new) {
 int hc_fit_cv2(const float* sx, const float* sy, const float* dx, const float* dy, int N, double thr, double confidence,
                int max_iters, double* H, uint64_t* mask, int32_t* info) {
     const float thr_sq = (float)(thr * thr);
-    double scratch[333];
+    double scratch[192];
     info[0] = N; info[1] = 0; info[2] = -1; info[3] = 0;
     *mask = 0;
     if (N < 4) return EGL_FIT_FEW_POINTS;
@@ -101,7 +101,7 @@ int hc_fixedk_stage(const float* sx, const float* sy, const float* dx, const flo
 
 int hc_refit(double* H, const float* sx, const float* sy, const float* dx, const float* dy, int N, uint64_t ransac_mask,
              double thr, uint64_t* final_mask) {
-    double scratch[333];
+    double scratch[192];
     return refit_on_inliers(H, sx, sy, dx, dy, N, ransac_mask, (float)(thr * thr), final_mask, scratch);
 }
 
