@@ -2,24 +2,30 @@
 // and the keypoint post-processing at eagle/models/coordinate_model.py:229-248).
 //
 // HBM-bound: every float of the (F,57,135,240) heatmap tensor is read exactly once (7,387,200 B per
-// frame) and 8 bytes per channel are written.  Layout of the work:
-//   * argmax_kernel -- persistent, one CTA per SM.  CTA c owns a CONTIGUOUS range of maps
-//     (total_maps*c/G ...), so each SM streams one long sequential region of HBM.  The maps are
-//     pulled through a 6-stage shared-memory ring by the TMA engine (cp.async.bulk, 32,400-byte
-//     chunks = a quarter of a 135x240 map, completion signalled on an mbarrier per stage), i.e. up
-//     to 5 x 32 KB in flight per SM with no registers tied up by loads.  The 8 warps scan a chunk
-//     with LDS.128, keeping (max, first flat index) per thread; per map a warp-shuffle arg-max and
-//     a cross-warp step produce the result.  Ties resolve to the lowest flat index = np.argmax.
+// frame, dram__bytes_read == algorithmic bytes in the ncu capture) and 8 bytes per channel are
+// written.  A pure streaming reduction has no data reuse, so the question is only how to keep enough
+// bytes in flight per SM; three layouts are compiled in and were measured on B200 at F = 2250
+// (16.6 GB per launch, CUDA events; MEASURED_PEAKS.json copy bandwidth = 6545 GB/s):
+//   argmax_ldg_kernel        one CTA per map, 256 threads, 8 independent 128-bit streaming loads
+//                            (ld.global.cs) in flight per thread, 8 CTAs per SM      7.49 TB/s  <- default
+//   argmax_kernel<3,256,2>   TMA ring: cp.async.bulk into a 3 x 32 KB shared-memory ring per CTA,
+//                            mbarrier completion, 2 CTAs per SM                       6.99 TB/s
+//   argmax_warp_ring_kernel  warp-private TMA rings (8 warps x 2 x 10.8 KB), no block sync  6.95 TB/s
+//   argmax_kernel<6,512,1>   one CTA per SM, 6 x 32 KB ring                           5.07 TB/s
+// Staging through shared memory buys nothing when nothing is reused -- it adds a shared-memory round
+// trip and a hand-off per chunk -- so the register-streaming kernel is the default and the TMA rings
+// stay selectable (EGL_DECODE_VARIANT) for measurement.  All layouts share the scan: per float4 a
+// 4-way max, the first lane equal to it and a predicated update (strict '>' keeps the earliest index,
+// i.e. np.argmax's first-maximum rule); NaNs are routed to an exact cold path.
 //   * postprocess_kernel -- one warp per frame over the 57 (index, score) pairs: confidence
 //     filter, scale to image pixels, duplicate-pixel arbitration, reference dict order.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "geometry_core.cuh"
 
 namespace egl {
 
-constexpr int kDecThreads = 512;
-constexpr int kDecWarps = kDecThreads / 32;
-constexpr int kStages = 6;
 constexpr int kChunkF4Max = 2025;  // float4 per stage: 32,400 B
 
 struct DecodeArgs {
@@ -39,7 +45,9 @@ __device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
     return v > bv || (v == bv && i < bi);
 }
 
-__global__ void __launch_bounds__(kDecThreads, 1) argmax_kernel(DecodeArgs a) {
+template <int kStages, int kDecThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kDecThreads, kMinBlocks) argmax_kernel(DecodeArgs a) {
+    constexpr int kDecWarps = kDecThreads / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* ring = reinterpret_cast<float4*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * a.chunk_f4 * sizeof(float4));
@@ -147,6 +155,152 @@ __global__ void __launch_bounds__(kDecThreads, 1) argmax_kernel(DecodeArgs a) {
     }
 }
 
+// Warp-private TMA rings: every warp streams its own contiguous range of maps through its own
+// kStages-deep shared-memory ring (lane 0 issues the bulk copies and all 32 lanes scan), so there is
+// no block-wide synchronisation anywhere -- a warp only ever waits for its own data.
+template <int kWarps, int kStages>
+__global__ void __launch_bounds__(kWarps * 32, 1) argmax_warp_ring_kernel(DecodeArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk_f4 = a.chunk_f4, cpm = a.chunks_per_map, map_f4 = a.map_f4;
+    float4* ring = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * kStages * chunk_f4;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarps * kStages * chunk_f4 * sizeof(float4)) + warp * kStages;
+    const long long gw = (long long)blockIdx.x * kWarps + warp, GW = (long long)gridDim.x * kWarps;
+    const long long m0 = a.total_maps * gw / GW, m1 = a.total_maps * (gw + 1) / GW;
+    const int nchunks = (int)(m1 - m0) * cpm;
+    if (nchunks == 0) return;
+    if (lane == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    const float4* issue_src = a.hm + m0 * map_f4;
+    int issue_k = 0, issue_stage = 0, issued = 0;
+    auto issue = [&]() {  // lane 0 only
+        const int off = issue_k * chunk_f4;
+        const int n = min(chunk_f4, map_f4 - off);
+        mbar_expect_tx(&full[issue_stage], (uint32_t)n * 16u);
+        bulk_g2s(ring + (size_t)issue_stage * chunk_f4, issue_src, (uint32_t)n * 16u, &full[issue_stage]);
+        issue_src += n;
+        if (++issue_k == cpm) issue_k = 0;
+        if (++issue_stage == kStages) issue_stage = 0;
+        ++issued;
+    };
+    if (lane == 0)
+        while (issued < kStages && issued < nchunks) issue();
+    const int first_bi = lane < chunk_f4 ? lane * 4 : 0x7fffffff;
+    float bv = -INFINITY;
+    int bi = first_bi;
+    bool bnan = false;
+    int stage = 0, k = 0;
+    uint32_t phase = 0;
+    long long map = m0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int off = k * chunk_f4;
+        const int n = min(chunk_f4, map_f4 - off);
+        mbar_wait(&full[stage], phase);
+        const float4* src = ring + (size_t)stage * chunk_f4;
+#pragma unroll 4
+        for (int i = lane; i < n; i += 32) {
+            const float4 v = src[i];
+            const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+            const float sum = (v.x + v.y) + (v.z + v.w);
+            const int base = (off + i) * 4;
+            if (sum != sum) {
+                const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool take = !bnan && (e[j] > bv || e[j] != e[j]);
+                    if (take) { bv = e[j]; bi = base + j; bnan = e[j] != e[j]; }
+                }
+            } else {
+                const int j = v.x == m ? 0 : (v.y == m ? 1 : (v.z == m ? 2 : 3));
+                const bool upd = !bnan && m > bv;
+                bv = upd ? m : bv;
+                bi = upd ? base + j : bi;
+            }
+        }
+        __syncwarp();  // every lane is done with this stage before lane 0 hands it back to the TMA engine
+        if (lane == 0 && issued < nchunks) issue();
+        if (k == cpm - 1) {
+            float v = bv;
+            int ix = bi;
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                const float ov = __shfl_xor_sync(kFull, v, m);
+                const int oi = __shfl_xor_sync(kFull, ix, m);
+                if (better(ov, oi, v, ix)) { v = ov; ix = oi; }
+            }
+            if (lane == 0) { a.kp_flat[map] = ix; a.kp_score[map] = v; }
+            bv = -INFINITY; bi = first_bi; bnan = false;
+        }
+        if (++k == cpm) { k = 0; ++map; }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    }
+}
+
+// Alternative without the TMA ring (kept for A/B measurements, EGL_DECODE_VARIANT=ldg): one CTA per
+// map, 256 threads, 8 independent 128-bit streaming loads in flight per thread.
+__global__ void __launch_bounds__(256) argmax_ldg_kernel(DecodeArgs a) {
+    __shared__ float s_val[8];
+    __shared__ int s_idx[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long map = blockIdx.x;
+    const float4* src = a.hm + map * a.map_f4;
+    const int n = a.map_f4;
+    float bv = -INFINITY;
+    int bi = tid < n ? tid * 4 : 0x7fffffff;
+    bool bnan = false;
+    for (int i0 = tid; i0 < n; i0 += 256 * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 256;
+            v[u] = i < n ? __ldcs(src + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int base = (i0 + u * 256) * 4;
+            const float m = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
+            const float sum = (v[u].x + v[u].y) + (v[u].z + v[u].w);
+            if (sum != sum) {
+                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool take = !bnan && (e[j] > bv || e[j] != e[j]);
+                    if (take) { bv = e[j]; bi = base + j; bnan = e[j] != e[j]; }
+                }
+            } else {
+                const int j = v[u].x == m ? 0 : (v[u].y == m ? 1 : (v[u].z == m ? 2 : 3));
+                const bool upd = !bnan && m > bv;
+                bv = upd ? m : bv;
+                bi = upd ? base + j : bi;
+            }
+        }
+    }
+    float v = bv;
+    int ix = bi;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        const float ov = __shfl_xor_sync(kFull, v, m);
+        const int oi = __shfl_xor_sync(kFull, ix, m);
+        if (better(ov, oi, v, ix)) { v = ov; ix = oi; }
+    }
+    if (lane == 0) { s_val[warp] = v; s_idx[warp] = ix; }
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < 8 ? s_val[lane] : -INFINITY;
+        ix = lane < 8 ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+        for (int m = 4; m > 0; m >>= 1) {
+            const float ov = __shfl_xor_sync(kFull, v, m);
+            const int oi = __shfl_xor_sync(kFull, ix, m);
+            if (better(ov, oi, v, ix)) { v = ov; ix = oi; }
+        }
+        if (lane == 0) { a.kp_flat[map] = ix; a.kp_score[map] = v; }
+    }
+}
+
 // Keypoint post-processing, one warp per frame (the sequential statement of the same rules is
 // postprocess_keypoints() in geometry_core.cuh, which the CPU tests pin against the reference):
 // lane l owns channels l and l+32; the 57 (pixel, score, kept) triples are staged in shared memory
@@ -251,22 +405,55 @@ extern "C" int egl_decode_heatmaps(const float* hm, int F, int hm_h, int hm_w, i
     a.chunk_f4 = (a.map_f4 + a.chunks_per_map - 1) / a.chunks_per_map;  // balanced chunks, <= kChunkF4Max
     a.kp_flat = kp_flat;
     a.kp_score = kp_score;
-    const size_t smem = (size_t)kStages * a.chunk_f4 * sizeof(float4) + kStages * sizeof(uint64_t);
-    static thread_local int configured_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (configured_dev != dev) {
-        int rc = cuda_status(cudaFuncSetAttribute(argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  (int)((size_t)kStages * kChunkF4Max * sizeof(float4) + kStages * sizeof(uint64_t))),
-                             "egl_decode_heatmaps: cudaFuncSetAttribute");
-        if (rc) return rc;
-        configured_dev = dev;
-    }
     int sms = egl_sm_count();
     if (sms <= 0) return -1;
-    long long grid = a.total_maps < sms ? a.total_maps : sms;
-    argmax_kernel<<<(unsigned)grid, kDecThreads, smem, s>>>(a);
-    int rc = cuda_status(cudaGetLastError(), "egl_decode_heatmaps: argmax kernel launch");
+    // Launch variants (EGL_DECODE_VARIANT, measurement switch; default 4 = register-streaming kernel).
+    static const char* variant_env = getenv("EGL_DECODE_VARIANT");
+    const int variant = variant_env ? atoi(variant_env) : 4;
+    int rc = 0;
+    auto launch_ring = [&](auto kernel, int stages, int threads, int ctas_per_sm, int chunk_div) -> int {
+        DecodeArgs b = a;
+        b.chunks_per_map = (a.map_f4 + kChunkF4Max / chunk_div - 1) / (kChunkF4Max / chunk_div);
+        b.chunk_f4 = (a.map_f4 + b.chunks_per_map - 1) / b.chunks_per_map;
+        const size_t smem = (size_t)stages * b.chunk_f4 * sizeof(float4) + stages * sizeof(uint64_t);
+        int r = cuda_status(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "egl_decode_heatmaps: cudaFuncSetAttribute");
+        if (r) return r;
+        long long grid = (long long)sms * ctas_per_sm;
+        if (grid > a.total_maps) grid = a.total_maps;
+        kernel<<<(unsigned)grid, threads, smem, s>>>(b);
+        return 0;
+    };
+    auto launch_warp_ring = [&](auto kernel, int warps, int stages, int chunks) -> int {
+        DecodeArgs b = a;
+        b.chunks_per_map = chunks;
+        b.chunk_f4 = (a.map_f4 + chunks - 1) / chunks;
+        const size_t smem = (size_t)warps * stages * b.chunk_f4 * sizeof(float4) + (size_t)warps * stages * sizeof(uint64_t);
+        if (smem > 227 * 1024) { set_error("egl_decode_heatmaps: variant needs %zu B of shared memory", smem); return EGL_ERR_SHAPE; }
+        int r = cuda_status(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "egl_decode_heatmaps: cudaFuncSetAttribute");
+        if (r) return r;
+        long long grid = sms;
+        if (grid * warps > a.total_maps) grid = (a.total_maps + warps - 1) / warps;
+        kernel<<<(unsigned)grid, warps * 32, smem, s>>>(b);
+        return 0;
+    };
+    switch (variant) {
+        case 1: rc = launch_ring(argmax_kernel<12, 512, 1>, 12, 512, 1, 2); break;   // 12 x 16 KB
+        case 2: rc = launch_ring(argmax_kernel<3, 256, 2>, 3, 256, 2, 1); break;    // 2 CTAs/SM, 3 x 32 KB each
+        case 3: rc = launch_ring(argmax_kernel<6, 256, 2>, 6, 256, 2, 2); break;    // 2 CTAs/SM, 6 x 16 KB each
+        case 5: rc = launch_ring(argmax_kernel<6, 1024, 1>, 6, 1024, 1, 1); break;
+        case 6: rc = launch_warp_ring(argmax_warp_ring_kernel<8, 2>, 8, 2, 12); break;    // 8 warps x 2 x 10.8 KB
+        case 7: rc = launch_warp_ring(argmax_warp_ring_kernel<16, 2>, 16, 2, 20); break;  // 16 warps x 2 x 6.5 KB
+        case 8: rc = launch_warp_ring(argmax_warp_ring_kernel<16, 3>, 16, 3, 30); break;  // 16 warps x 3 x 4.3 KB
+        case 9: rc = launch_warp_ring(argmax_warp_ring_kernel<32, 2>, 32, 2, 36); break;  // 32 warps x 2 x 3.6 KB
+        case 10: rc = launch_ring(argmax_kernel<2, 256, 3>, 2, 256, 3, 1); break;         // 3 CTAs/SM, 2 x 32 KB each
+        case 11: rc = launch_ring(argmax_kernel<3, 128, 4>, 3, 128, 4, 2); break;         // 4 CTAs/SM, 3 x 16 KB each
+        case 0: rc = launch_ring(argmax_kernel<6, 512, 1>, 6, 512, 1, 1); break;    // 6 x 32 KB, 1 CTA/SM
+        default: argmax_ldg_kernel<<<(unsigned)a.total_maps, 256, 0, s>>>(a); break;  // register streaming
+    }
+    if (rc) return rc;
+    rc = cuda_status(cudaGetLastError(), "egl_decode_heatmaps: argmax kernel launch");
     if (rc) return rc;
     postprocess_kernel<<<(F + kPostWarps - 1) / kPostWarps, kPostWarps * 32, 0, s>>>(kp_flat, kp_score, F, hm_h, hm_w, img_w, img_h, keypoint_conf, kp_xy,
                                                     kp_order, kp_count);

@@ -7,12 +7,14 @@
 // ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2, uint8 result BEFORE normalisation (at exact 2x
 // decimation OpenCV switches to its 2x2-mean fast path, which this recipe equals identically).
 //
-// HBM-bound.  One CTA per output row: the two source rows it needs are pulled into shared memory
-// with two bulk copies on the TMA engine (fully coalesced, no registers), then 240 threads x 4
-// output pixels compute all three channels from shared memory and write one float4 per plane
-// (512 contiguous bytes per warp and plane).  Every source byte and every output float crosses HBM
+// HBM-bound.  One CTA per band of R output rows: the source rows it needs are pulled into shared
+// memory with bulk copies on the TMA engine (fully coalesced, no registers), then 240 threads x 4
+// interleaved output pixels compute all three channels from shared memory (conflict-free byte reads)
+// and write one float per plane, pixel and row (128 contiguous bytes per warp and store).  Every source byte and every output float crosses HBM
 // once when the vertical scale is >= 2 (1080p, 4K); at 720p neighbouring output rows share source
 // rows and the second read is served by L2.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "geometry_core.cuh"
 
@@ -39,43 +41,66 @@ __device__ __forceinline__ void axis_tap(int d, double scale, int* ofs, int* c0,
     *c1 = __float2int_rn(__fmul_rn(f, 2048.f));
 }
 
+// R consecutive output rows per CTA.  The 2R source rows they need are requested up front (one
+// mbarrier, one bulk copy per distinct row: when the vertical scale is < 2 neighbouring output rows
+// share a source row, which is then fetched once and aliased), so a CTA keeps up to 2R rows in
+// flight and the per-CTA fixed costs (launch, barrier set-up, tap arithmetic) are amortised R-fold.
+template <int R>
 __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* __restrict__ frames, int H, int W,
                                                                  size_t row_stride, size_t frame_stride, double scale_x,
                                                                  double scale_y, int use_bulk, float* __restrict__ out) {
-    extern __shared__ __align__(128) unsigned char s_rows[];  // 2 rows, each padded to a multiple of 16 B
+    extern __shared__ __align__(128) unsigned char s_rows[];  // 2R row slots, each padded to a multiple of 16 B
     __shared__ uint64_t s_bar;
+    constexpr int kBands = kOutH / R;
+    static_assert(kOutH % R == 0, "R must divide 540");
     const int tid = threadIdx.x;
-    const int dy = blockIdx.x % kOutH;
-    const int f = blockIdx.x / kOutH;
+    const int dy0 = (blockIdx.x % kBands) * R;
+    const int f = blockIdx.x / kBands;
     const int row_bytes = 3 * W;
     const int row_pad = (row_bytes + 15) & ~15;
 
-    int sy, b0, b1;
-    axis_tap(dy, scale_y, &sy, &b0, &b1);
-    const int y0 = min(max(sy, 0), H - 1), y1 = min(max(sy + 1, 0), H - 1);  // rows clamp, weights do not
-    const uint8_t* g0 = frames + (size_t)f * frame_stride + (size_t)y0 * row_stride;
-    const uint8_t* g1 = frames + (size_t)f * frame_stride + (size_t)y1 * row_stride;
+    // vertical taps of the R rows; slot[] maps (row, tap) to a shared-memory slot, aliasing repeats
+    int b0[R], b1[R], ysrc[2 * R], slot[2 * R];
+    int nslots = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int sy;
+        axis_tap(dy0 + r, scale_y, &sy, &b0[r], &b1[r]);
+        ysrc[2 * r] = min(max(sy, 0), H - 1);  // rows clamp, weights do not
+        ysrc[2 * r + 1] = min(max(sy + 1, 0), H - 1);
+    }
+#pragma unroll
+    for (int q = 0; q < 2 * R; ++q) {
+        slot[q] = (q > 0 && ysrc[q] == ysrc[q - 1]) ? slot[q - 1] : nslots++;
+    }
+    const uint8_t* fbase = frames + (size_t)f * frame_stride;
     if (use_bulk) {
         if (tid == 0) {
             mbar_init(&s_bar, 1);
             mbar_fence_init();
-            mbar_expect_tx(&s_bar, 2u * (uint32_t)row_bytes);
-            bulk_g2s(s_rows, g0, (uint32_t)row_bytes, &s_bar);
-            bulk_g2s(s_rows + row_pad, g1, (uint32_t)row_bytes, &s_bar);
+            mbar_expect_tx(&s_bar, (uint32_t)nslots * (uint32_t)row_bytes);
+#pragma unroll
+            for (int q = 0; q < 2 * R; ++q)
+                if (q == 0 || slot[q] != slot[q - 1])
+                    bulk_g2s(s_rows + (size_t)slot[q] * row_pad, fbase + (size_t)ysrc[q] * row_stride, (uint32_t)row_bytes, &s_bar);
         }
     } else {
-        for (int i = tid; i < row_bytes; i += kPreThreads) {
-            s_rows[i] = g0[i];
-            s_rows[row_pad + i] = g1[i];
-        }
+#pragma unroll
+        for (int q = 0; q < 2 * R; ++q)
+            if (q == 0 || slot[q] != slot[q - 1])
+                for (int i = tid; i < row_bytes; i += kPreThreads)
+                    s_rows[(size_t)slot[q] * row_pad + i] = fbase[(size_t)ysrc[q] * row_stride + i];
     }
 
-    // horizontal taps of this thread's 4 output pixels (independent of the data: overlaps the copy)
+    // horizontal taps of this thread's 4 output pixels tid, tid+240, tid+480, tid+720 (independent of
+    // the data: overlaps the copy).  Interleaving the pixels over the threads keeps the byte reads of a
+    // warp on consecutive shared-memory words (no bank conflicts at any scale) and every store of a
+    // warp on one 128-byte line.
     int xo[4], xo1[4], a0[4], a1[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         int s, c0, c1;
-        axis_tap(4 * tid + k, scale_x, &s, &c0, &c1);
+        axis_tap(tid + kPreThreads * k, scale_x, &s, &c0, &c1);
         if (s < 0) { s = 0; c0 = 2048; c1 = 0; }
         if (s >= W - 1) { s = W - 1; c0 = 2048; c1 = 0; }
         xo[k] = 3 * s;
@@ -86,31 +111,26 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* 
     float mean[3], den[3];
     norm_consts(mean, den);
 
-    if (use_bulk) {
-        __syncthreads();  // barrier init visible to the waiters
-        mbar_wait(&s_bar, 0);
-    } else {
-        __syncthreads();
-    }
-    const uint8_t* r0 = s_rows;
-    const uint8_t* r1 = s_rows + row_pad;
-    float4 o[3];
-    float* op = reinterpret_cast<float*>(o);
+    __syncthreads();  // barrier init (bulk) / staged rows (fallback) visible
+    if (use_bulk) mbar_wait(&s_bar, 0);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int r = 0; r < R; ++r) {
+        const uint8_t* r0 = s_rows + (size_t)slot[2 * r] * row_pad;
+        const uint8_t* r1 = s_rows + (size_t)slot[2 * r + 1] * row_pad;
+        float* dst = out + ((size_t)f * 3 * kOutH + dy0 + r) * kOutW + tid;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {  // c indexes the SOURCE byte (B,G,R); plane = 2 - c (RGB)
-            const int top = (int)r0[xo[k] + c] * a0[k] + (int)r0[xo1[k] + c] * a1[k];
-            const int bot = (int)r1[xo[k] + c] * a0[k] + (int)r1[xo1[k] + c] * a1[k];
-            int v = (((b0 * (top >> 4)) >> 16) + ((b1 * (bot >> 4)) >> 16) + 2) >> 2;
-            v = min(max(v, 0), 255);
-            const int plane = 2 - c;
-            op[plane * 4 + k] = __fmul_rn(__fsub_rn((float)v, mean[plane]), den[plane]);
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {  // c indexes the SOURCE byte (B,G,R); plane = 2 - c (RGB)
+                const int top = (int)r0[xo[k] + c] * a0[k] + (int)r0[xo1[k] + c] * a1[k];
+                const int bot = (int)r1[xo[k] + c] * a0[k] + (int)r1[xo1[k] + c] * a1[k];
+                int v = (((b0[r] * (top >> 4)) >> 16) + ((b1[r] * (bot >> 4)) >> 16) + 2) >> 2;
+                v = min(max(v, 0), 255);
+                const int plane = 2 - c;
+                __stcs(dst + (size_t)plane * kOutH * kOutW + kPreThreads * k, __fmul_rn(__fsub_rn((float)v, mean[plane]), den[plane]));
+            }
         }
     }
-    float* dst = out + ((size_t)f * 3 * kOutH + dy) * kOutW + 4 * tid;
-#pragma unroll
-    for (int p = 0; p < 3; ++p) __stcs(reinterpret_cast<float4*>(dst + (size_t)p * kOutH * kOutW), o[p]);
 }
 
 }  // namespace egl
@@ -128,20 +148,38 @@ extern "C" int egl_preprocess_u8(const uint8_t* frames, int F, int H, int W, siz
     if (F == 0) return 0;
     const int row_bytes = 3 * W;
     const int row_pad = (row_bytes + 15) & ~15;
-    const size_t smem = 2 * (size_t)row_pad;
-    EGL_REQUIRE(smem <= 200 * 1024, EGL_ERR_SHAPE, "egl_preprocess_u8: frame too wide (%d px)", W);
     // bulk copies need 16-byte aligned rows of a 16-byte multiple length
     const int use_bulk = (row_bytes % 16 == 0) && (row_stride % 16 == 0) && (frame_stride % 16 == 0) &&
                          ((reinterpret_cast<uintptr_t>(frames) & 15) == 0);
     // OpenCV: inv_scale = dsize/ssize (double); scale = 1./inv_scale
     const double scale_x = 1. / ((double)kOutW / (double)W);
     const double scale_y = 1. / ((double)kOutH / (double)H);
-    if (smem > 48 * 1024) {
-        int rc = cuda_status(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                             "egl_preprocess_u8: cudaFuncSetAttribute");
-        if (rc) return rc;
+    // output rows per CTA: as many as keep >= 2 CTAs' worth of row slots within shared memory
+    static const char* rows_env = getenv("EGL_PREPROCESS_ROWS");
+    int R = rows_env ? atoi(rows_env) : 4;
+    while (R > 1 && (size_t)2 * R * row_pad > 100 * 1024) R >>= 1;
+    const size_t smem = (size_t)2 * R * row_pad;
+    EGL_REQUIRE(smem <= 200 * 1024, EGL_ERR_SHAPE, "egl_preprocess_u8: frame too wide (%d px)", W);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto launch = [&](auto kernel, int rows) -> int {
+        if (smem > 48 * 1024) {
+            int rc = cuda_status(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                                 "egl_preprocess_u8: cudaFuncSetAttribute");
+            if (rc) return rc;
+        }
+        kernel<<<(unsigned)(F * (kOutH / rows)), kPreThreads, smem, st>>>(frames, H, W, row_stride, frame_stride, scale_x, scale_y,
+                                                                         use_bulk, out);
+        return 0;
+    };
+    int rc;
+    switch (R) {
+        case 1: rc = launch(preprocess_kernel<1>, 1); break;
+        case 2: rc = launch(preprocess_kernel<2>, 2); break;
+        case 3: rc = launch(preprocess_kernel<3>, 3); break;
+        case 4: rc = launch(preprocess_kernel<4>, 4); break;
+        case 6: rc = launch(preprocess_kernel<6>, 6); break;
+        default: rc = launch(preprocess_kernel<2>, 2); break;
     }
-    preprocess_kernel<<<(unsigned)(F * kOutH), kPreThreads, smem, (cudaStream_t)stream>>>(frames, H, W, row_stride, frame_stride,
-                                                                                       scale_x, scale_y, use_bulk, out);
+    if (rc) return rc;
     return cuda_status(cudaGetLastError(), "egl_preprocess_u8: kernel launch");
 }

@@ -1,0 +1,50 @@
+"""The C-ABI library loads and exports every function include/eagle_b200.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    txt = open(os.path.join(ROOT, "include", "eagle_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(egl_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_declares_expected_entry_points():
+    fns = declared_functions()
+    for name in ("egl_preprocess_u8", "egl_decode_heatmaps", "egl_synthesize_keypoints", "egl_fit_homography",
+                 "egl_select_homography", "egl_project_points", "egl_version", "egl_last_error", "egl_sm_count"):
+        assert name in fns
+
+
+def test_library_exports_every_declared_symbol():
+    from eagle_b200 import _native
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/eagle_b200.h but not exported"
+    assert sorted(_native.EXPORTS) == declared_functions()
+    assert _native.lib.egl_version() == _native.ABI_VERSION
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    """Null pointers / bad shapes are rejected before any CUDA call, with a message."""
+    from eagle_b200 import _native as N
+    rc = N.lib.egl_decode_heatmaps(None, 1, 135, 240, 1920, 1080, 0.3, None, None, None, None, None, None)
+    assert rc == 1 and b"null pointer" in N.lib.egl_last_error()
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.addressof(buf)
+    rc = N.lib.egl_decode_heatmaps(p, 1, 3, 5, 1920, 1080, 0.3, p, p, p, p, p, None)  # 15 elements: not a multiple of 4
+    assert rc == 2
+    rc = N.lib.egl_fit_homography(p, p, p, 1, 7, 10, None, 0, 5.0, 0.995, p, p, p, p, p, None)
+    assert rc == 4 and b"unknown mode" in N.lib.egl_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    """No module under eagle_b200/ (nor bench.py's GPU arm imports) may depend on oracle/."""
+    pkg = os.path.join(ROOT, "eagle_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn

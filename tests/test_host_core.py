@@ -1,0 +1,106 @@
+"""The kernels' scalar core (eagle_b200/csrc/geometry_core.cuh), compiled for the host, against the
+oracle and the live cv2.  This is the same source the GPU executes; the -m gpu tests then check the
+device build and the kernel orchestration around it."""
+import json
+import os
+import warnings
+
+import cv2
+import numpy as np
+import pytest
+
+import hostcore
+from eagle_b200 import synthetic
+from eagle_b200.pitch import WORLD_XY_F32
+from oracle import decode, homography, landmarks, synthesis
+
+ON = [i for i in range(57) if i not in (0, 1, 24, 25)]
+
+
+def random_case(rng, t):
+    W, H = [(1280, 720), (1920, 1080), (3840, 2160)][t % 3]
+    cam = synthetic.sample_cameras(1, W, H, rng)[0]
+    n = int(rng.integers(5, 54)); sel = np.sort(rng.choice(ON, n, replace=False))
+    px = synthetic.project_points(cam, WORLD_XY_F32[sel].astype(np.float64)) + rng.normal(0, rng.choice([0, .5, 2.]), (n, 2))
+    no = int(n * rng.uniform(0, .5)); oi = rng.choice(n, no, replace=False)
+    px[oi] = rng.uniform([0, 0], [W, H], (no, 2))
+    return np.rint(px).astype(np.float32), WORLD_XY_F32[sel]
+
+
+def test_cv2_compatible_fit_matches_live_cv2():
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for t in range(150):
+        img, wor = random_case(rng, t)
+        Hc, mc = cv2.findHomography(img, wor, cv2.RANSAC, 5.0)
+        st, Hh, mh, info = hostcore.fit_cv2(img, wor)
+        if Hc is None:
+            assert st != 0
+            continue
+        assert st == 0
+        assert np.array_equal(mc.ravel(), mh), t
+        if mc.sum() >= 6:
+            worst = max(worst, float(np.max(np.abs(Hc - Hh) / np.abs(Hc))))
+    assert worst < 1e-5, worst  # north-star tolerance is 1e-4
+
+
+def test_minimal_solvers_agree_with_opencv_run_kernel():
+    rng = np.random.default_rng(2)
+    for t in range(100):
+        img, wor = random_case(rng, t)
+        idx = rng.choice(len(img), 4, replace=False)
+        if not homography.check_subset(img[idx], wor[idx]):
+            assert not hostcore.check_subset(img[idx], wor[idx])
+            continue
+        assert hostcore.check_subset(img[idx], wor[idx])
+        Hk = homography.run_kernel(img[idx], wor[idx])
+        ok64, H64 = hostcore.dlt4_f64(img[idx], wor[idx])
+        assert ok64 and np.max(np.abs(H64 - Hk) / (np.abs(Hk) + 1e-12)) < 1e-7
+        ok32, H32 = hostcore.dlt4_f32(img[idx], wor[idx])
+        assert ok32 and np.max(np.abs(H32 - Hk) / (np.abs(Hk) + 1e-3)) < 5e-2
+
+
+def test_postprocess_matches_reference_decoded_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "decode_small.npz"))
+    hm = g["heatmaps"]; N, C, h, w = hm.shape
+    post = json.loads(str(g["postprocessed_json"]))
+    for key, want in post.items():
+        wh, n = key.split(":"); W, H = (int(v) for v in wh.split("x")); n = int(n)
+        flat = hm[n].reshape(C, -1).argmax(1); score = hm[n].reshape(C, -1).max(1)
+        xy, order = hostcore.postprocess(flat, score, h, w, W, H)
+        got = {landmarks.INDEX_TO_NAME[int(c)]: [int(xy[c, 0]), int(xy[c, 1])] for c in order}
+        assert got == want and list(got) == list(want), key
+
+
+def test_synthesis_matches_oracle():
+    warnings.simplefilter("ignore")
+    clip = synthetic.make_clip(24, 1920, 1080, seed=3, ghost_prob=0.05)
+    added = 0
+    for i in range(24):
+        kp = decode.decode_frame(clip["heatmaps"][i], 1920, 1080)
+        want = synthesis.synthesize(kp)
+        xy = np.zeros((57, 2), np.int32); order = []
+        for name, (x, y) in kp.items():
+            c = landmarks.NAME_TO_INDEX[name]; xy[c] = (x, y); order.append(c)
+        xy2, order2 = hostcore.synthesize(xy, np.array(order, np.uint8))
+        got = {landmarks.INDEX_TO_NAME[int(c)]: (int(xy2[c, 0]), int(xy2[c, 1])) for c in order2}
+        assert list(got) == list(want)
+        assert all(tuple(want[k]) == got[k] for k in want)
+        added += len(want) - len(kp)
+    assert added > 20  # the fixture does exercise the synthesis
+
+
+def test_projection_matches_cv2():
+    rng = np.random.default_rng(0)
+    H = np.linalg.inv(synthetic.sample_cameras(1, 1920, 1080, rng)[0]); H /= H[2, 2]
+    pts = rng.uniform(0, 1920, (2000, 2)).astype(np.float32)
+    of, oi = hostcore.project(H, pts)
+    ref = cv2.perspectiveTransform(pts[None], H)[0]
+    assert np.array_equal(of, ref) and np.array_equal(oi, ref.astype(int))
+
+
+def test_seeded_generator_is_distinct_and_in_range():
+    for N in (4, 5, 17, 53):
+        for h in range(200):
+            idx = hostcore.seeded_subset(123, 7, 4096, h, N)
+            assert len(set(idx.tolist())) == 4 and idx.min() >= 0 and idx.max() < N
