@@ -222,7 +222,7 @@ def main():
     kp = eng.alloc_keypoints(F); fit = eng.alloc_fit(F); proj = eng.alloc_projection(F, MAX_OBJ)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     launches = {"n": 0}
-    side = torch.cuda.Stream(dev)   # latency-bound tail (fit/refit/project) runs beside the streaming K1
+    side = torch.cuda.Stream(dev, priority=-1)   # high priority: latency-bound tail (fit/refit/project) runs beside the streaming K1
     fork = torch.cuda.Event()
 
     def step(i=None):

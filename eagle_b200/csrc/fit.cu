@@ -8,9 +8,10 @@
 //                       operation order, then replays OpenCV's sequential accept / adaptive
 //                       iteration-count rule over the 32 results.  Picks the model cv2 picks.
 //   ransac_fixedk_kernel (mode EGL_FIT_FIXED_K)    one CTA per frame, one THREAD per hypothesis:
-//                       the 4-point DLT is normalised, the 8x8 system eliminated with partial
-//                       pivoting entirely in FP32 registers, all N points scored by the same
-//                       thread; block-wide arg-max (ties -> lowest hypothesis index).  FP32-ALU bound.
+//                       points normalised once per frame, the 8x8 DLT system of each 4-point sample
+//                       solved by block elimination entirely in FP32 registers, all N points scored
+//                       by the same thread with a division-free test (13 FP32 ops per point);
+//                       block-wide arg-max (ties -> lowest hypothesis index).  FP32-ALU bound.
 //   refit_kernel        one thread per frame, FP64: OpenCV's tail of findHomography -- normalised
 //                       DLT on the inliers (9x9 Jacobi), <= 10 Levenberg-Marquardt iterations over
 //                       nine parameters, mask recomputed from the refined H.
@@ -221,27 +222,36 @@ __global__ void __launch_bounds__(kCv2Warps * 32) ransac_cv2_kernel(FitArgs a) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kFixedThreads = 128;
 
-__global__ void __launch_bounds__(kFixedThreads) ransac_fixedk_kernel(FitArgs a) {
+__global__ void __launch_bounds__(kFixedThreads) ransac_fixedk_kernel(FitArgs a, float inv_thr, double thr) {
     __shared__ PointList s_pl;
-    __shared__ float4 s_pt[kMaxPts];  // (X, Y, x, y) packed for one broadcast LDS.128 per point
+    __shared__ float4 s_pt[kMaxPts];  // normalised (X', Y', x', y'): one broadcast LDS.128 per point
     __shared__ int s_cnt[kFixedThreads / 32], s_hyp[kFixedThreads / 32];
     __shared__ float s_H[8];
-    __shared__ int s_N;
+    __shared__ FixedKNorm s_nm;
+    __shared__ int s_N, s_ok;
     __shared__ unsigned long long s_used;
     const int f = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) {
         uint64_t used;
         const int n = gather_points_warp(a, f, s_pl, &used);
-        if (lane == 0) { s_N = n; s_used = used; }
+        if (lane == 0) {
+            s_N = n;
+            s_used = used;
+            s_ok = n >= 4 && fixedk_normalise(s_pl.sx, s_pl.sy, s_pl.dx, s_pl.dy, n, inv_thr, &s_nm);
+        }
     }
     __syncthreads();
     const int N = s_N;
-    if (N < 4) {
-        if (tid == 0) park(a, f, EGL_FIT_FEW_POINTS, N, 0, -1, 0, nullptr, 0, s_used);
+    if (N < 4 || !s_ok) {
+        if (tid == 0) park(a, f, N < 4 ? EGL_FIT_FEW_POINTS : EGL_FIT_NO_MODEL, N, 0, -1, 0, nullptr, 0, s_used);
         return;
     }
-    for (int i = tid; i < N; i += kFixedThreads) s_pt[i] = make_float4(s_pl.sx[i], s_pl.sy[i], s_pl.dx[i], s_pl.dy[i]);
+    for (int i = tid; i < N; i += kFixedThreads) {
+        float o[4];
+        fixedk_normalise_point(s_nm, s_pl.sx[i], s_pl.sy[i], s_pl.dx[i], s_pl.dy[i], o);
+        s_pt[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
     __syncthreads();
 
     int best_cnt = 0, best_h = 0x7fffffff;
@@ -257,28 +267,27 @@ __global__ void __launch_bounds__(kFixedThreads) ransac_fixedk_kernel(FitArgs a)
         bool ok = idx[0] < N && idx[1] < N && idx[2] < N && idx[3] < N;
         ok = ok && idx[0] != idx[1] && idx[0] != idx[2] && idx[0] != idx[3] && idx[1] != idx[2] && idx[1] != idx[3] &&
              idx[2] != idx[3];
-        float qx[4], qy[4], rx[4], ry[4];
+        float p[4][4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float4 p = s_pt[ok ? idx[k] : 0];
-            qx[k] = p.x; qy[k] = p.y; rx[k] = p.z; ry[k] = p.w;
+            const float4 q = s_pt[ok ? idx[k] : k];
+            p[k][0] = q.x; p[k][1] = q.y; p[k][2] = q.z; p[k][3] = q.w;
         }
-        ok = ok && check_subset(qx, qy, rx, ry);
-        float Hf[9];
-        ok = dlt4_f32(qx, qy, rx, ry, Hf) && ok;
+        float Hn[8];
+        ok = fixedk_hypothesis(p, Hn) && ok;
         int cnt = 0;
         if (ok) {
 #pragma unroll 4
             for (int i = 0; i < N; ++i) {
-                const float4 p = s_pt[i];
-                cnt += reproj_err_f32(Hf, p.x, p.y, p.z, p.w) <= a.thr_sq;
+                const float4 q = s_pt[i];
+                cnt += fixedk_inlier(Hn, q.x, q.y, q.z, q.w);
             }
         }
         if (cnt > best_cnt) {  // ascending h per thread: strict > keeps the earliest
             best_cnt = cnt;
             best_h = h;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) best_H[k] = Hf[k];
+            for (int k = 0; k < 8; ++k) best_H[k] = Hn[k];
         }
     }
     // block arg-max: most inliers, ties -> lowest hypothesis index
@@ -301,27 +310,27 @@ __global__ void __launch_bounds__(kFixedThreads) ransac_fixedk_kernel(FitArgs a)
     }
     __syncthreads();
     if (warp == 0) {
-        // inliers of the winner: lanes are points, ballots make the mask
+        // winner back in image -> pitch units; its inlier list in OpenCV's float scoring (lanes are
+        // points, ballots make the mask) is what the refit starts from
+        double Hd[9];
         uint64_t pm = 0;
         if (have) {
+            float Hn[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) Hn[k] = s_H[k];
+            fixedk_denormalise(Hn, s_nm, thr, Hd);
             float Hf[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) Hf[k] = s_H[k];
+            for (int k = 0; k < 8; ++k) Hf[k] = (float)Hd[k];
             for (int pass = 0; pass < 2; ++pass) {
                 const int i = pass * 32 + lane;
-                bool in = false;
-                if (i < N) {
-                    const float4 p = s_pt[i];
-                    in = reproj_err_f32(Hf, p.x, p.y, p.z, p.w) <= a.thr_sq;
-                }
+                const bool in = i < N && reproj_err_f32(Hf, s_pl.sx[i], s_pl.sy[i], s_pl.dx[i], s_pl.dy[i]) <= a.thr_sq;
                 pm |= (uint64_t)__ballot_sync(kFull, in) << (32 * pass);
             }
         }
         if (lane == 0) {
-            double Hd[9];
-            for (int k = 0; k < 8; ++k) Hd[k] = (double)s_H[k];
-            Hd[8] = 1.0;
-            park(a, f, have ? EGL_FIT_OK : EGL_FIT_NO_MODEL, N, have ? c : 0, have ? hh : -1, a.K, Hd, pm, s_used);
+            const bool good = have && __popcll(pm) >= 4;
+            park(a, f, good ? EGL_FIT_OK : EGL_FIT_NO_MODEL, N, good ? __popcll(pm) : 0, have ? hh : -1, a.K, Hd, pm, s_used);
         }
     }
 }
@@ -379,7 +388,7 @@ extern "C" int egl_fit_homography(const int32_t* kp_xy, const uint8_t* kp_order,
     if (mode == EGL_FIT_CV2_COMPAT) {
         ransac_cv2_kernel<<<(F + kCv2Warps - 1) / kCv2Warps, kCv2Warps * 32, 0, s>>>(a);
     } else {
-        ransac_fixedk_kernel<<<F, kFixedThreads, 0, s>>>(a);
+        ransac_fixedk_kernel<<<F, kFixedThreads, 0, s>>>(a, (float)(1.0 / thr), thr);
     }
     int rc = cuda_status(cudaGetLastError(), "egl_fit_homography: hypothesis kernel launch");
     if (rc) return rc;

@@ -628,97 +628,162 @@ EGL_HD void seeded_subset(uint64_t seed, uint64_t frame, uint64_t K, uint64_t h,
     }
 }
 
-// FP32 4-point DLT: normalise (centroid, mean absolute deviation per axis -- OpenCV's choice),
-// build [X Y 1 0 0 0 -xX -xY | x ; 0 0 0 X Y 1 -yX -yY | y], eliminate with partial pivoting in
-// registers (explicit fmaf in the update so the oracle's C mirror can reproduce every bit),
-// back-substitute, de-normalise, scale by 1/h33.  Returns false on a zero / non-finite pivot.
-EGL_HD bool dlt4_f32(const float* sx, const float* sy, const float* dx, const float* dy, float* H) {
-    float cMx = fmul(fadd(fadd(sx[0], sx[1]), fadd(sx[2], sx[3])), 0.25f);
-    float cMy = fmul(fadd(fadd(sy[0], sy[1]), fadd(sy[2], sy[3])), 0.25f);
-    float cmx = fmul(fadd(fadd(dx[0], dx[1]), fadd(dx[2], dx[3])), 0.25f);
-    float cmy = fmul(fadd(fadd(dy[0], dy[1]), fadd(dy[2], dy[3])), 0.25f);
-    float X[4], Y[4], x[4], y[4];
-EGL_UNROLL
-    for (int i = 0; i < 4; ++i) {
-        X[i] = fsub(sx[i], cMx); Y[i] = fsub(sy[i], cMy);
-        x[i] = fsub(dx[i], cmx); y[i] = fsub(dy[i], cmy);
+// ---- fixed-K hypothesis arithmetic (FP32, every operation explicit so that oracle/ransac_f32.c
+// can mirror it bit for bit; DESIGN.md "fixed-K arithmetic") --------------------------------------
+//
+// Per FRAME (once): the N correspondences are normalised
+//     X' = (X - cX) * sX,  Y' = (Y - cY) * sY      cX = (sum X)/N, sX = N / sum|X - cX|   (image)
+//     x' = (x - cx) * rt,  y' = (y - cy) * rt      cx = (sum x)/N, rt = 1/thr             (pitch)
+// sums taken sequentially in point order.  Scaling the pitch side by 1/thr turns the inlier test
+// |proj - dst|^2 <= thr^2 into  (nx - x'w)^2 + (ny - y'w)^2 <= w^2  with w the projective
+// denominator: no division and no threshold multiply per point.
+// Per HYPOTHESIS: the 8x8 DLT system of the 4 sampled points (h33 = 1)
+//     X h0 + Y h1 + h2 - xX h6 - xY h7 = x ,   X h3 + Y h4 + h5 - yX h6 - yY h7 = y
+// is solved by block elimination in registers: the left null vector n of the 4x3 matrix [X Y 1]
+// (its 3x3 cofactors) removes h0..h5 and leaves a 2x2 system for (h6, h7); h0..h5 follow from the
+// three best-conditioned rows by Cramer's rule.  Two reciprocals per hypothesis.
+struct FixedKNorm {
+    float cX, cY, sX, sY, cx, cy, rt;
+};
+
+EGL_HD bool fixedk_normalise(const float* sx, const float* sy, const float* dx, const float* dy, int n, float inv_thr,
+                             FixedKNorm* nm) {
+    float sX = 0.f, sY = 0.f, sx_ = 0.f, sy_ = 0.f;
+    for (int i = 0; i < n; ++i) {
+        sX = fadd(sX, sx[i]); sY = fadd(sY, sy[i]);
+        sx_ = fadd(sx_, dx[i]); sy_ = fadd(sy_, dy[i]);
     }
-    float sMx = fadd(fadd(fabsf(X[0]), fabsf(X[1])), fadd(fabsf(X[2]), fabsf(X[3])));
-    float sMy = fadd(fadd(fabsf(Y[0]), fabsf(Y[1])), fadd(fabsf(Y[2]), fabsf(Y[3])));
-    float smx = fadd(fadd(fabsf(x[0]), fabsf(x[1])), fadd(fabsf(x[2]), fabsf(x[3])));
-    float smy = fadd(fadd(fabsf(y[0]), fabsf(y[1])), fadd(fabsf(y[2]), fabsf(y[3])));
-    if (!(sMx > 0.f) || !(sMy > 0.f) || !(smx > 0.f) || !(smy > 0.f)) return false;
-    sMx = fdiv(4.f, sMx); sMy = fdiv(4.f, sMy); smx = fdiv(4.f, smx); smy = fdiv(4.f, smy);
-    float a[8][9];
-EGL_UNROLL
-    for (int i = 0; i < 4; ++i) {
-        const float Xn = fmul(X[i], sMx), Yn = fmul(Y[i], sMy), xn = fmul(x[i], smx), yn = fmul(y[i], smy);
-        a[2 * i][0] = Xn; a[2 * i][1] = Yn; a[2 * i][2] = 1.f; a[2 * i][3] = 0.f; a[2 * i][4] = 0.f; a[2 * i][5] = 0.f;
-        a[2 * i][6] = -fmul(xn, Xn); a[2 * i][7] = -fmul(xn, Yn); a[2 * i][8] = xn;
-        a[2 * i + 1][0] = 0.f; a[2 * i + 1][1] = 0.f; a[2 * i + 1][2] = 0.f; a[2 * i + 1][3] = Xn; a[2 * i + 1][4] = Yn;
-        a[2 * i + 1][5] = 1.f; a[2 * i + 1][6] = -fmul(yn, Xn); a[2 * i + 1][7] = -fmul(yn, Yn); a[2 * i + 1][8] = yn;
+    const float fn = (float)n;
+    nm->cX = fdiv(sX, fn); nm->cY = fdiv(sY, fn); nm->cx = fdiv(sx_, fn); nm->cy = fdiv(sy_, fn);
+    float aX = 0.f, aY = 0.f;
+    for (int i = 0; i < n; ++i) {
+        aX = fadd(aX, fabsf(fsub(sx[i], nm->cX)));
+        aY = fadd(aY, fabsf(fsub(sy[i], nm->cY)));
     }
-    bool ok = true;
-EGL_UNROLL
-    for (int k = 0; k < 8; ++k) {
-        // partial pivoting by compare-exchange: after the scan row k holds the first row (k..7)
-        // with the largest |a[.][k]|
-EGL_UNROLL
-        for (int i = k + 1; i < 8; ++i) {
-            const bool sw = fabsf(a[i][k]) > fabsf(a[k][k]);
-EGL_UNROLL
-            for (int j = k; j < 9; ++j) {
-                const float t = a[k][j];
-                a[k][j] = sw ? a[i][j] : t;
-                a[i][j] = sw ? t : a[i][j];
-            }
-        }
-        const float piv = a[k][k];
-        ok &= (fabsf(piv) > 0.f) && (fabsf(piv) < INFINITY);
-        const float inv = fdiv(1.f, piv);
-EGL_UNROLL
-        for (int i = k + 1; i < 8; ++i) {
-            const float m = fmul(a[i][k], inv);
-EGL_UNROLL
-            for (int j = k + 1; j < 9; ++j) a[i][j] = fmaf(-m, a[k][j], a[i][j]);
-        }
-    }
-    float h[9];
-EGL_UNROLL
-    for (int i = 7; i >= 0; --i) {
-        float s = a[i][8];
-EGL_UNROLL
-        for (int j = i + 1; j < 8; ++j) s = fmaf(-a[i][j], h[j], s);
-        h[i] = fdiv(s, a[i][i]);
-    }
-    h[8] = 1.f;
-    // T = invHnorm * h ; invHnorm = [[1/smx,0,cmx],[0,1/smy,cmy],[0,0,1]]
-    const float ismx = fdiv(1.f, smx), ismy = fdiv(1.f, smy);
-    float T[9];
-EGL_UNROLL
-    for (int c = 0; c < 3; ++c) {
-        T[c] = fmaf(cmx, h[6 + c], fmul(ismx, h[c]));
-        T[3 + c] = fmaf(cmy, h[6 + c], fmul(ismy, h[3 + c]));
-        T[6 + c] = h[6 + c];
-    }
-    // H = T * Hnorm2 ; Hnorm2 = [[sMx,0,-cMx*sMx],[0,sMy,-cMy*sMy],[0,0,1]]
-    const float tx = -fmul(cMx, sMx), ty = -fmul(cMy, sMy);
-    float G[9];
-EGL_UNROLL
-    for (int r = 0; r < 3; ++r) {
-        G[3 * r + 0] = fmul(T[3 * r + 0], sMx);
-        G[3 * r + 1] = fmul(T[3 * r + 1], sMy);
-        G[3 * r + 2] = fmaf(T[3 * r + 0], tx, fmaf(T[3 * r + 1], ty, T[3 * r + 2]));
-    }
-    const float sc = fdiv(1.f, G[8]);
-EGL_UNROLL
-    for (int i = 0; i < 8; ++i) H[i] = fmul(G[i], sc);
-    H[8] = 1.f;
-EGL_UNROLL
-    for (int i = 0; i < 8; ++i) ok &= (fabsf(H[i]) < INFINITY);
-    return ok;
+    if (!(aX > 0.f) || !(aY > 0.f)) return false;
+    nm->sX = fdiv(fn, aX);
+    nm->sY = fdiv(fn, aY);
+    nm->rt = inv_thr;
+    return true;
 }
 
+EGL_HD void fixedk_normalise_point(const FixedKNorm& nm, float X, float Y, float x, float y, float* o) {
+    o[0] = fmul(fsub(X, nm.cX), nm.sX);
+    o[1] = fmul(fsub(Y, nm.cY), nm.sY);
+    o[2] = fmul(fsub(x, nm.cx), nm.rt);
+    o[3] = fmul(fsub(y, nm.cy), nm.rt);
+}
+
+// det of rows (Xa,Ya,1),(Xb,Yb,1),(Xc,Yc,1):  Xa(Yb-Yc) - Ya(Xb-Xc) + (Xb Yc - Xc Yb)
+EGL_HD float det3_f32(float Xa, float Ya, float Xb, float Yb, float Xc, float Yc) {
+    const float t = fmaf(Xb, Yc, -fmul(Xc, Yb));
+    return fmaf(Xa, fsub(Yb, Yc), fmaf(-Ya, fsub(Xb, Xc), t));
+}
+
+// One hypothesis from 4 normalised correspondences p[k] = (X', Y', x', y').  Returns false when the
+// sample is rejected (OpenCV's checkSubset rules evaluated in float on the normalised points: last
+// point collinear with an earlier pair on either side, or orientation not preserved) or degenerate.
+EGL_HD bool fixedk_hypothesis(const float (*p)[4], float* H /*8*/) {
+    float X[4], Y[4], x[4], y[4];
+EGL_UNROLL
+    for (int k = 0; k < 4; ++k) { X[k] = p[k][0]; Y[k] = p[k][1]; x[k] = p[k][2]; y[k] = p[k][3]; }
+    // oriented areas of the four triples, image side (S) and pitch side (D)
+    const float S012 = det3_f32(X[0], Y[0], X[1], Y[1], X[2], Y[2]);
+    const float S123 = det3_f32(X[1], Y[1], X[2], Y[2], X[3], Y[3]);
+    const float S023 = det3_f32(X[0], Y[0], X[2], Y[2], X[3], Y[3]);
+    const float S013 = det3_f32(X[0], Y[0], X[1], Y[1], X[3], Y[3]);
+    const float D012 = det3_f32(x[0], y[0], x[1], y[1], x[2], y[2]);
+    const float D123 = det3_f32(x[1], y[1], x[2], y[2], x[3], y[3]);
+    const float D023 = det3_f32(x[0], y[0], x[2], y[2], x[3], y[3]);
+    const float D013 = det3_f32(x[0], y[0], x[1], y[1], x[3], y[3]);
+    const float tiny = 1e-6f;
+    bool ok = fabsf(S123) > tiny && fabsf(S023) > tiny && fabsf(S013) > tiny && fabsf(D123) > tiny && fabsf(D023) > tiny &&
+              fabsf(D013) > tiny;
+    const int neg = (fmul(S012, D012) < 0.f) + (fmul(S123, D123) < 0.f) + (fmul(S023, D023) < 0.f) + (fmul(S013, D013) < 0.f);
+    ok = ok && (neg == 0 || neg == 4);
+    // left null vector of [X Y 1]: n0 = S123, n1 = -S023, n2 = S013, n3 = -S012
+    float n[4] = {S123, -S023, S013, -S012};
+    // pivot: move the row with the largest |n| to slot 3 (the other three rows then have the largest 3x3 determinant)
+EGL_UNROLL
+    for (int k = 0; k < 3; ++k) {
+        const bool sw = fabsf(n[k]) > fabsf(n[3]);
+        float t;
+        t = n[3]; n[3] = sw ? n[k] : t; n[k] = sw ? t : n[k];
+        t = X[3]; X[3] = sw ? X[k] : t; X[k] = sw ? t : X[k];
+        t = Y[3]; Y[3] = sw ? Y[k] : t; Y[k] = sw ? t : Y[k];
+        t = x[3]; x[3] = sw ? x[k] : t; x[k] = sw ? t : x[k];
+        t = y[3]; y[3] = sw ? y[k] : t; y[k] = sw ? t : y[k];
+    }
+    // 2x2 system for (h6, h7):  sum n_i * row_i
+    float a11 = 0.f, a12 = 0.f, a21 = 0.f, a22 = 0.f, b1 = 0.f, b2 = 0.f;
+EGL_UNROLL
+    for (int k = 0; k < 4; ++k) {
+        const float nx = fmul(n[k], x[k]), ny = fmul(n[k], y[k]);
+        a11 = fmaf(-nx, X[k], a11); a12 = fmaf(-nx, Y[k], a12); b1 = fadd(b1, nx);
+        a21 = fmaf(-ny, X[k], a21); a22 = fmaf(-ny, Y[k], a22); b2 = fadd(b2, ny);
+    }
+    const float Dt = fmaf(a11, a22, -fmul(a12, a21));
+    const float rD = fdiv(1.f, Dt);
+    const float h6 = fmul(fmaf(b1, a22, -fmul(a12, b2)), rD);
+    const float h7 = fmul(fmaf(a11, b2, -fmul(b1, a21)), rD);
+    // h0..h5 from rows 0,1,2:  [X Y 1] (h0,h1,h2)^T = x*w,  (h3,h4,h5)^T likewise with y*w
+    float u[3], v[3];
+EGL_UNROLL
+    for (int k = 0; k < 3; ++k) {
+        const float w = fmaf(h6, X[k], fmaf(h7, Y[k], 1.f));
+        u[k] = fmul(x[k], w);
+        v[k] = fmul(y[k], w);
+    }
+    const float dP = det3_f32(X[0], Y[0], X[1], Y[1], X[2], Y[2]);
+    const float rP = fdiv(1.f, dP);
+    const float c0 = fsub(Y[1], Y[2]), c1 = fsub(Y[2], Y[0]), c2 = fsub(Y[0], Y[1]);
+    const float d0 = fsub(X[2], X[1]), d1 = fsub(X[0], X[2]), d2 = fsub(X[1], X[0]);
+    const float e0 = fmaf(X[1], Y[2], -fmul(X[2], Y[1])), e1 = fmaf(X[2], Y[0], -fmul(X[0], Y[2])),
+                e2 = fmaf(X[0], Y[1], -fmul(X[1], Y[0]));
+    H[0] = fmul(fmaf(u[0], c0, fmaf(u[1], c1, fmul(u[2], c2))), rP);
+    H[1] = fmul(fmaf(u[0], d0, fmaf(u[1], d1, fmul(u[2], d2))), rP);
+    H[2] = fmul(fmaf(u[0], e0, fmaf(u[1], e1, fmul(u[2], e2))), rP);
+    H[3] = fmul(fmaf(v[0], c0, fmaf(v[1], c1, fmul(v[2], c2))), rP);
+    H[4] = fmul(fmaf(v[0], d0, fmaf(v[1], d1, fmul(v[2], d2))), rP);
+    H[5] = fmul(fmaf(v[0], e0, fmaf(v[1], e1, fmul(v[2], e2))), rP);
+    H[6] = h6;
+    H[7] = h7;
+    float acc = 0.f;
+EGL_UNROLL
+    for (int k = 0; k < 8; ++k) acc = fadd(acc, fabsf(H[k]));
+    return ok && (acc < INFINITY);  // false for inf / NaN entries
+}
+
+// Inlier test of one normalised point under a normalised hypothesis (division-free).
+EGL_HD bool fixedk_inlier(const float* H, float X, float Y, float x, float y) {
+    const float w = fmaf(H[6], X, fmaf(H[7], Y, 1.f));
+    const float ex = fmaf(-x, w, fmaf(H[0], X, fmaf(H[1], Y, H[2])));
+    const float ey = fmaf(-y, w, fmaf(H[3], X, fmaf(H[4], Y, H[5])));
+    const float e = fmaf(ex, ex, fmul(ey, ey));
+    return fmaf(-w, w, e) <= 0.f;
+}
+
+// Back to image -> pitch units (double): H = Td^-1 * Hn * Ts, scaled so that H[8] == 1.
+EGL_HD void fixedk_denormalise(const float* Hn, const FixedKNorm& nm, double thr, double* H) {
+    const double h[9] = {Hn[0], Hn[1], Hn[2], Hn[3], Hn[4], Hn[5], Hn[6], Hn[7], 1.0};
+    const double sX = nm.sX, sY = nm.sY, cX = nm.cX, cY = nm.cY, cx = nm.cx, cy = nm.cy;
+    // A = Hn * Ts,  Ts = [[sX,0,-cX sX],[0,sY,-cY sY],[0,0,1]]
+    double A[9];
+    for (int r = 0; r < 3; ++r) {
+        A[3 * r + 0] = h[3 * r + 0] * sX;
+        A[3 * r + 1] = h[3 * r + 1] * sY;
+        A[3 * r + 2] = h[3 * r + 2] - h[3 * r + 0] * cX * sX - h[3 * r + 1] * cY * sY;
+    }
+    // Td^-1 = [[thr,0,cx],[0,thr,cy],[0,0,1]]
+    double G[9];
+    for (int c = 0; c < 3; ++c) {
+        G[c] = thr * A[c] + cx * A[6 + c];
+        G[3 + c] = thr * A[3 + c] + cy * A[6 + c];
+        G[6 + c] = A[6 + c];
+    }
+    const double s = 1.0 / G[8];
+    for (int i = 0; i < 9; ++i) H[i] = G[i] * s;
+}
 
 // ---- line-intersection keypoint synthesis (coordinate_model.py:96-186) ------------------------
 struct SynthTables {  // generated from eagle_b200/pitch.py (csrc/line_families.inc)

@@ -48,12 +48,12 @@ def fit_cv2(img_pts, world_pts, thr=5.0, confidence=0.995, max_iters=2000):
 
 def fixedk_stage(img_pts, world_pts, K, hyp=None, seed=0, frame=0, thr=5.0):
     sx, sy, dx, dy = split(img_pts, world_pts)
-    H = np.zeros(9, np.float32); mask = C.c_uint64(0); info = np.zeros(4, np.int32)
+    H = np.zeros(9, np.float64); mask = C.c_uint64(0); info = np.zeros(4, np.int32)
     hp = None
     if hyp is not None:
         hyp = np.ascontiguousarray(hyp, np.uint8); hp = _p(hyp, C.c_uint8)
     st = lib().hc_fixedk_stage(_p(sx, C.c_float), _p(sy, C.c_float), _p(dx, C.c_float), _p(dy, C.c_float), len(sx), K, hp,
-                               C.c_uint64(seed), C.c_uint64(frame), C.c_double(thr), _p(H, C.c_float), C.byref(mask), _p(info, C.c_int32))
+                               C.c_uint64(seed), C.c_uint64(frame), C.c_double(thr), _p(H, C.c_double), C.byref(mask), _p(info, C.c_int32))
     m = np.array([(mask.value >> i) & 1 for i in range(len(sx))], np.uint8)
     return st, H.reshape(3, 3), m, info
 
@@ -65,13 +65,6 @@ def refit(H, img_pts, world_pts, ransac_mask, thr=5.0):
     n = lib().hc_refit(_p(Hc, C.c_double), _p(sx, C.c_float), _p(sy, C.c_float), _p(dx, C.c_float), _p(dy, C.c_float), len(sx),
                        C.c_uint64(bits), C.c_double(thr), C.byref(fm))
     return Hc.reshape(3, 3), np.array([(fm.value >> i) & 1 for i in range(len(sx))], np.uint8), n
-
-
-def dlt4_f32(img4, world4):
-    sx, sy, dx, dy = split(img4, world4)
-    H = np.zeros(9, np.float32)
-    ok = lib().hc_dlt4_f32(_p(sx, C.c_float), _p(sy, C.c_float), _p(dx, C.c_float), _p(dy, C.c_float), _p(H, C.c_float))
-    return bool(ok), H.reshape(3, 3)
 
 
 def dlt4_f64(img4, world4):

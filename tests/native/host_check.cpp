@@ -67,12 +67,20 @@ int hc_fit_cv2(const float* sx, const float* sy, const float* dx, const float* d
     return EGL_FIT_OK;
 }
 
-// sequential replay of ransac_fixedk_kernel (hypothesis stage only): best model in float, its
-// position mask, count and index
+// sequential replay of ransac_fixedk_kernel (hypothesis stage only): winner denormalised to double,
+// its position mask in OpenCV's float scoring, count and index
 int hc_fixedk_stage(const float* sx, const float* sy, const float* dx, const float* dy, int N, int K, const uint8_t* hyp,
-                    uint64_t seed, uint64_t frame, double thr, float* Hbest, uint64_t* mask, int32_t* info) {
+                    uint64_t seed, uint64_t frame, double thr, double* Hbest, uint64_t* mask, int32_t* info) {
     const float thr_sq = (float)(thr * thr);
+    info[0] = N; info[1] = 0; info[2] = -1; info[3] = K;
+    *mask = 0;
+    FixedKNorm nm;
+    if (N < 4) return EGL_FIT_FEW_POINTS;
+    if (!fixedk_normalise(sx, sy, dx, dy, N, (float)(1.0 / thr), &nm)) return EGL_FIT_NO_MODEL;
+    float pts[64][4];
+    for (int i = 0; i < N; ++i) fixedk_normalise_point(nm, sx[i], sy[i], dx[i], dy[i], pts[i]);
     int best = 0, best_h = -1;
+    float Hw[8];
     for (int h = 0; h < K; ++h) {
         int idx[4];
         if (hyp) { for (int k = 0; k < 4; ++k) idx[k] = hyp[4 * h + k]; }
@@ -80,23 +88,19 @@ int hc_fixedk_stage(const float* sx, const float* sy, const float* dx, const flo
         bool ok = idx[0] < N && idx[1] < N && idx[2] < N && idx[3] < N;
         ok = ok && idx[0] != idx[1] && idx[0] != idx[2] && idx[0] != idx[3] && idx[1] != idx[2] && idx[1] != idx[3] && idx[2] != idx[3];
         if (!ok) continue;
-        float qx[4], qy[4], rx[4], ry[4];
-        for (int k = 0; k < 4; ++k) { qx[k] = sx[idx[k]]; qy[k] = sy[idx[k]]; rx[k] = dx[idx[k]]; ry[k] = dy[idx[k]]; }
-        if (!check_subset(qx, qy, rx, ry)) continue;
-        float Hf[9];
-        if (!dlt4_f32(qx, qy, rx, ry, Hf)) continue;
+        float p[4][4];
+        for (int k = 0; k < 4; ++k) memcpy(p[k], pts[idx[k]], sizeof(p[k]));
+        float Hn[8];
+        if (!fixedk_hypothesis(p, Hn)) continue;
         int c = 0;
-        for (int i = 0; i < N; ++i) c += reproj_err_f32(Hf, sx[i], sy[i], dx[i], dy[i]) <= thr_sq;
-        if (c > best) { best = c; best_h = h; memcpy(Hbest, Hf, 9 * sizeof(float)); }
+        for (int i = 0; i < N; ++i) c += fixedk_inlier(Hn, pts[i][0], pts[i][1], pts[i][2], pts[i][3]);
+        if (c > best) { best = c; best_h = h; memcpy(Hw, Hn, sizeof(Hw)); }
     }
-    info[0] = N; info[1] = best; info[2] = best_h; info[3] = K;
-    *mask = 0;
+    info[2] = best_h;
     if (best <= 3) return EGL_FIT_NO_MODEL;
-    double Hd[9];
-    for (int k = 0; k < 8; ++k) Hd[k] = Hbest[k];
-    Hd[8] = 1.0;
-    inlier_mask_f32(Hd, sx, sy, dx, dy, N, thr_sq, mask);
-    return EGL_FIT_OK;
+    fixedk_denormalise(Hw, nm, thr, Hbest);
+    info[1] = inlier_mask_f32(Hbest, sx, sy, dx, dy, N, thr_sq, mask);
+    return info[1] >= 4 ? EGL_FIT_OK : EGL_FIT_NO_MODEL;
 }
 
 int hc_refit(double* H, const float* sx, const float* sy, const float* dx, const float* dy, int N, uint64_t ransac_mask,
@@ -105,7 +109,6 @@ int hc_refit(double* H, const float* sx, const float* sy, const float* dx, const
     return refit_on_inliers(H, sx, sy, dx, dy, N, ransac_mask, (float)(thr * thr), final_mask, scratch);
 }
 
-int hc_dlt4_f32(const float* sx, const float* sy, const float* dx, const float* dy, float* H) { return dlt4_f32(sx, sy, dx, dy, H); }
 int hc_dlt4_f64(const float* sx, const float* sy, const float* dx, const float* dy, double* H) { return dlt4_f64(sx, sy, dx, dy, H); }
 int hc_check_subset(const float* sx, const float* sy, const float* dx, const float* dy) { return check_subset(sx, sy, dx, dy); }
 void hc_seeded_subset(uint64_t seed, uint64_t frame, uint64_t K, uint64_t h, int N, int* idx) { seeded_subset(seed, frame, K, h, N, idx); }

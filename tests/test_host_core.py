@@ -56,8 +56,6 @@ def test_minimal_solvers_agree_with_opencv_run_kernel():
         Hk = homography.run_kernel(img[idx], wor[idx])
         ok64, H64 = hostcore.dlt4_f64(img[idx], wor[idx])
         assert ok64 and np.max(np.abs(H64 - Hk) / (np.abs(Hk) + 1e-12)) < 1e-7
-        ok32, H32 = hostcore.dlt4_f32(img[idx], wor[idx])
-        assert ok32 and np.max(np.abs(H32 - Hk) / (np.abs(Hk) + 1e-3)) < 5e-2
 
 
 def test_postprocess_matches_reference_decoded_golden(golden_dir):
@@ -104,3 +102,23 @@ def test_seeded_generator_is_distinct_and_in_range():
         for h in range(200):
             idx = hostcore.seeded_subset(123, 7, 4096, h, N)
             assert len(set(idx.tolist())) == 4 and idx.min() >= 0 and idx.max() < N
+
+
+def test_fixed_k_core_equals_independent_c_mirror():
+    """The kernel's FP32 hypothesis arithmetic (host build) vs oracle/ransac_f32.c, written separately
+    from the specification: same winner, same normalised-test count, same H to rounding."""
+    from oracle import ransac_f32
+    xy, valid, flags, cams = synthetic.stress_point_sets(10, 1920, 1080, seed=5)
+    K = 768
+    for f in range(10):
+        img = xy[f, ON].astype(np.float32); wor = WORLD_XY_F32[ON]
+        table = ransac_f32.seeded_table(77, f, K, 53)
+        assert all(np.array_equal(table[h], hostcore.seeded_subset(77, f, K, h, 53)) for h in range(0, K, 29))
+        st, Hb, m, info = hostcore.fixedk_stage(img, wor, K, None, seed=77, frame=f)
+        r = ransac_f32.fixedk_frame(img, wor, table)
+        assert st == 0 and info[2] == r["best_index"]
+        assert np.max(np.abs(ransac_f32.denormalise(r["h"], r["norm"], 5.0) - Hb) / np.abs(Hb)) < 1e-12
+        H, mask, _ = ransac_f32.fit_fixedk(img, wor, table)
+        Hr, fm, n = hostcore.refit(Hb, img, wor, m)
+        assert np.array_equal(mask.ravel(), fm) and np.max(np.abs(H - Hr) / np.abs(Hr)) < 1e-6
+        assert not any(fm[k] for k, c in enumerate(ON) if flags[f, c])
