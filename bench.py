@@ -222,32 +222,21 @@ def main():
     kp = eng.alloc_keypoints(F); fit = eng.alloc_fit(F); proj = eng.alloc_projection(F, MAX_OBJ)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     launches = {"n": 0}
-    side = torch.cuda.Stream(dev, priority=-1)   # high priority: latency-bound tail (fit/refit/project) runs beside the streaming K1
-    fork = torch.cuda.Event()
-
     def step(i=None):
-        """The hot path over this rank's F frames, inputs resident in HBM.  8 kernel launches.
+        """The hot path over this rank's F frames, inputs resident in HBM.  8 kernel launches, one stream.
 
-        Stream layout: K2 (decode) runs alone on the main stream; then the latency-bound tail
-        (synthesis, RANSAC, refit, cadence, projection: ~2k threads of FP64) goes to a side stream
-        while the main stream streams K1 (preprocess, HBM-bound) -- the two do not compete for the
-        same resource.  K1's output feeds the keypoint network, which is not part of this path, so
-        nothing downstream in the step depends on it."""
-        main = torch.cuda.current_stream()
+        K1's output feeds the keypoint network, which is not part of this path, so nothing in the step
+        depends on it; it is simply run last."""
         if i is not None: ev[i][0].record()
         eng.decode(hm, W, H, 0.3, out=kp)                                # K2  (2 launches)
         if i is not None: ev[i][1].record()
-        fork.record(main)
-        with torch.cuda.stream(side):
-            side.wait_event(fork)
-            eng.synthesize(kp)                                           # F1  (1)
-            eng.fit(kp, out=fit)                                         # K3  (2)
-            h_index, attempted = eng.select(fit.status, 1)               # cadence (1)
-            eng.project(fit.H, foot, count, W, H, h_index=h_index, out=proj)  # K4  (1)
-            if i is not None: ev[i][3].record(side)
-        eng.preprocess(frames, out=x)                                    # K1  (1 launch)
+        eng.synthesize(kp)                                               # F1  (1)
+        eng.fit(kp, out=fit)                                             # K3  (2)
+        h_index, attempted = eng.select(fit.status, 1)                   # cadence (1)
+        eng.project(fit.H, foot, count, W, H, h_index=h_index, out=proj)  # K4  (1)
         if i is not None: ev[i][2].record()
-        main.wait_stream(side)
+        eng.preprocess(frames, out=x)                                    # K1  (1 launch)
+        if i is not None: ev[i][3].record()
         launches["n"] += 8
         if world > 1:
             rec = pack_results([fit.H, fit.inlier_mask, fit.status, proj.coords, proj.in_bounds, proj.bounds])
@@ -283,8 +272,8 @@ def main():
 
     # per-kernel split of the step (same events, same stream) -- explains `value`
     pre_ms = statistics.mean(ev[i][0].elapsed_time(ev[i][1]) for i in range(args.steps))   # decode (argmax+postprocess), alone
-    tail_ms = statistics.mean(ev[i][1].elapsed_time(ev[i][3]) for i in range(args.steps))  # synth+fit+select+project (side stream)
-    k1_ms = statistics.mean(ev[i][1].elapsed_time(ev[i][2]) for i in range(args.steps))    # preprocess (main stream, beside the tail)
+    tail_ms = statistics.mean(ev[i][1].elapsed_time(ev[i][2]) for i in range(args.steps))  # synth+fit+select+project
+    k1_ms = statistics.mean(ev[i][2].elapsed_time(ev[i][3]) for i in range(args.steps))    # preprocess
     peak, peak_src = peaks()
     achieved = F * HM_BYTES / (pre_ms * 1e-3) / 1e9
     roofline = {"kernel": "egl::argmax_ldg_kernel (K2 heatmap decode; interval also holds postprocess_kernel, <1%)", "bound": "hbm",
@@ -380,7 +369,7 @@ def main():
             "config": {"workload": WORKLOAD, "frame": [H, W], "frames_per_gpu": F, "heatmaps": [57, 135, 240], "objects_per_frame": MAX_OBJ,
                        "fit": "cv2-compatible adaptive RANSAC (cap 2000) + LS refit + LM", "l2_policy": "inputs larger than L2 "
                        f"({F * (H * W * 3 + HM_BYTES) / 1e9:.1f} GB streamed per step vs 126 MB L2)", "parallelism": f"frame-range x{world}"},
-            "kernel_ms": {"decode_K2": pre_ms, "preprocess_K1_beside_tail": k1_ms, "synth_fit_select_project_side_stream": tail_ms},
+            "kernel_ms": {"decode_K2": pre_ms, "synth_fit_select_project": tail_ms, "preprocess_K1": k1_ms},
             "stage_fps_without_preprocess": F * world / ((pre_ms + tail_ms) * 1e-3),
             "preprocess_roofline": {"bound": "hbm", "achieved": F * (H * W * 3 + 3 * 540 * 960 * 4) / (k1_ms * 1e-3) / 1e9, "unit": "GB/s",
                                     "frac": F * (H * W * 3 + 3 * 540 * 960 * 4) / (k1_ms * 1e-3) / 1e9 / peak},
