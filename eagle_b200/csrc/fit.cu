@@ -12,9 +12,13 @@
 //                       solved by block elimination entirely in FP32 registers, all N points scored
 //                       by the same thread with a division-free test (13 FP32 ops per point);
 //                       block-wide arg-max (ties -> lowest hypothesis index).  FP32-ALU bound.
-//   refit_kernel        one thread per frame, FP64: OpenCV's tail of findHomography -- normalised
-//                       DLT on the inliers (9x9 Jacobi), <= 10 Levenberg-Marquardt iterations over
-//                       nine parameters, mask recomputed from the refined H.
+//   refit_warp_kernel   one warp per frame, FP64: OpenCV's tail of findHomography -- normalised DLT on
+//                       the inliers (smallest eigenvector of the 9x9 normal matrix), <= 10
+//                       Levenberg-Marquardt iterations over nine parameters, mask recomputed from the
+//                       refined H.  (refit_kernel = the same algorithm, one thread per frame, running
+//                       the host-checkable scalar code of geometry_core.cuh; EGL_REFIT_VARIANT=1.)
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "geometry_core.cuh"
 
@@ -368,6 +372,361 @@ __global__ void __launch_bounds__(kRefitThreads) refit_kernel(FitArgs a) {
     a.info[4 * f + 1] = count;
 }
 
+// ------------------------------------------------------------------------------------------------
+// refit, warp-cooperative: the same algorithm as refit_on_inliers() (geometry_core.cuh), one WARP per
+// frame.  Lanes are points for every sum over the correspondences (lane l owns points l and l+32;
+// sums by shuffle reduction) and rows for the small dense solves (row-parallel Gaussian elimination
+// with partial pivoting in shared memory).  Cuts the latency of the one-thread-per-frame kernel by
+// ~20x at clip sizes where there are fewer frames than the GPU has thread slots.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRefitWarps = 4;
+
+struct RefitShared {
+    PointList pl;
+    double A[81];
+    double aug[10 * 11];
+    double vec[12];
+};
+
+// Row-parallel Gaussian elimination with partial pivoting on the augmented n x (n+1) system in
+// shared memory (row stride S); lanes 0..n-1 own rows.  Result x[0..n) in shared memory.  All 32
+// lanes must call.  Returns false on a zero / non-finite pivot (uniform across the warp).
+template <int n, int S>
+__device__ bool warp_gauss_solve(double* aug, double* x) {
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < n; ++k) {
+        // pivot: largest |aug[r][k]|, r >= k, lowest row on ties
+        double best = (lane >= k && lane < n) ? fabs(aug[lane * S + k]) : -1.0;
+        int piv = lane;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            const double ob = shfl_xor_f64(best, m);
+            const int op = __shfl_xor_sync(kFull, piv, m);
+            if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
+        }
+        if (!(best > 0.0) || !isfinite(best)) return false;
+        if (piv != k && lane <= n) {  // lanes are columns for the swap
+            const double t = aug[k * S + lane];
+            aug[k * S + lane] = aug[piv * S + lane];
+            aug[piv * S + lane] = t;
+        }
+        __syncwarp();
+        if (lane > k && lane < n) {
+            const double m = aug[lane * S + k] * (1.0 / aug[k * S + k]);
+            if (m != 0.0)
+                for (int j = k + 1; j <= n; ++j) aug[lane * S + j] -= m * aug[k * S + j];
+        }
+        __syncwarp();
+    }
+    for (int i = n - 1; i >= 0; --i) {  // column-oriented back substitution
+        const double xi = aug[i * S + n] / aug[i * S + i];
+        __syncwarp();
+        if (lane < i) aug[lane * S + n] -= aug[lane * S + i] * xi;
+        if (lane == 0) x[i] = xi;
+        __syncwarp();
+    }
+    return true;
+}
+
+// sums over the inlier points of (b b^T) (x) C-terms: 24 block sums -> the 9x9 matrix (see
+// dlt_normal_matrix / lm_linearise for the block structure); v (9) and two scalars ride along.
+struct PointSums {
+    double bb[6], bx[6], by[6], bq[6];
+};
+
+__device__ __forceinline__ void accumulate_point(PointSums& s, const double* b, double cx, double cy, double q) {
+    int e = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = a; c < 3; ++c, ++e) {
+            const double p = b[a] * b[c];
+            s.bb[e] += p; s.bx[e] += p * cx; s.by[e] += p * cy; s.bq[e] += p * q;
+        }
+}
+
+__device__ __forceinline__ void reduce_and_store_matrix(PointSums& s, double* A) {
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+        s.bb[e] = warp_sum_f64(s.bb[e]); s.bx[e] = warp_sum_f64(s.bx[e]);
+        s.by[e] = warp_sum_f64(s.by[e]); s.bq[e] = warp_sum_f64(s.bq[e]);
+    }
+    const int lane = threadIdx.x & 31;
+    for (int t = lane; t < 81; t += 32) {
+        const int r = t / 9, c = t % 9;
+        const int br = r / 3, bc = c / 3, a = r % 3, cc = c % 3;
+        const int lo = a < cc ? a : cc, hi = a < cc ? cc : a;
+        const int e = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);
+        double v;
+        if (br == bc) v = (br == 2) ? s.bq[e] : s.bb[e];
+        else if (br + bc == 1) v = 0.0;
+        else v = -((br == 0 || bc == 0) ? s.bx[e] : s.by[e]);
+        A[t] = v;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kRefitWarps * 32) refit_warp_kernel(FitArgs a) {
+    __shared__ RefitShared s_all[kRefitWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * kRefitWarps + warp;
+    if (f >= a.F) return;
+    if (a.status[f] != EGL_FIT_OK) {
+        if (lane == 0) a.inlier_mask[f] = 0;
+        return;
+    }
+    RefitShared& sh = s_all[warp];
+    uint64_t used;
+    const int N = gather_points_warp(a, f, sh.pl, &used);
+    uint64_t pm = a.inlier_mask[f];  // position bits of the RANSAC winner's inliers
+    double H[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) H[i] = a.H[(size_t)f * 9 + i];
+    __syncwarp();
+    int count = a.info[4 * f + 1];
+    if (N > 4) {
+        const int m = __popcll(pm);
+        // this lane's (up to two) inlier points
+        bool act[2];
+        double Mx[2], My[2], mx[2], my[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            act[h] = i < N && ((pm >> i) & 1ull);
+            Mx[h] = act[h] ? (double)sh.pl.sx[i] : 0.0; My[h] = act[h] ? (double)sh.pl.sy[i] : 0.0;
+            mx[h] = act[h] ? (double)sh.pl.dx[i] : 0.0; my[h] = act[h] ? (double)sh.pl.dy[i] : 0.0;
+        }
+        // ---- runKernel on the inliers: normalisation, 9x9 normal matrix, smallest eigenvector -------
+        const double cMx = warp_sum_f64(Mx[0] + Mx[1]) / m, cMy = warp_sum_f64(My[0] + My[1]) / m;
+        const double cmx = warp_sum_f64(mx[0] + mx[1]) / m, cmy = warp_sum_f64(my[0] + my[1]) / m;
+        double aMx = 0, aMy = 0, amx = 0, amy = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (act[h]) { aMx += fabs(Mx[h] - cMx); aMy += fabs(My[h] - cMy); amx += fabs(mx[h] - cmx); amy += fabs(my[h] - cmy); }
+        aMx = warp_sum_f64(aMx); aMy = warp_sum_f64(aMy); amx = warp_sum_f64(amx); amy = warp_sum_f64(amy);
+        bool have_ls = !(fabs(amx) < DBL_EPSILON || fabs(amy) < DBL_EPSILON || fabs(aMx) < DBL_EPSILON || fabs(aMy) < DBL_EPSILON);
+        if (have_ls) {
+            const double sMx = m / aMx, sMy = m / aMy, smx = m / amx, smy = m / amy;
+            PointSums ps = {};
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (act[h]) {
+                    const double x = (mx[h] - cmx) * smx, y = (my[h] - cmy) * smy;
+                    const double b[3] = {(Mx[h] - cMx) * sMx, (My[h] - cMy) * sMy, 1.0};
+                    accumulate_point(ps, b, x, y, x * x + y * y);
+                }
+            reduce_and_store_matrix(ps, sh.A);
+            // inverse iteration (same as smallest_eigvec9)
+            double tr = 0;
+            for (int i = 0; i < 9; ++i) tr += sh.A[i * 9 + i];
+            have_ls = tr > 0.0 && isfinite(tr);
+            const double sigma = tr * 1e-15;
+            double y_l = lane < 9 ? 1.0 / (1.37 + lane) : 0.0;  // lane i < 9 holds y[i]
+            double prev = 1e300;
+            for (int it = 0; it < 48 && have_ls; ++it) {
+                for (int t = lane; t < 81; t += 32) {
+                    const int r = t / 9, c = t % 9;
+                    sh.aug[r * 10 + c] = sh.A[t] + (r == c ? sigma : 0.0);
+                }
+                if (lane < 9) sh.aug[lane * 10 + 9] = y_l;
+                __syncwarp();
+                if (!warp_gauss_solve<9, 10>(sh.aug, sh.vec)) { have_ls = false; break; }
+                double z = lane < 9 ? sh.vec[lane] : 0.0;
+                const double nrm = warp_sum_f64(z * z);
+                // sign: component of largest magnitude positive (lowest index on ties)
+                double big = fabs(z);
+                int bi = lane < 9 ? lane : 99;
+                double bz = z;
+#pragma unroll
+                for (int mm = 16; mm > 0; mm >>= 1) {
+                    const double ob = shfl_xor_f64(big, mm), oz = shfl_xor_f64(bz, mm);
+                    const int oi = __shfl_xor_sync(kFull, bi, mm);
+                    if (ob > big || (ob == big && oi < bi)) { big = ob; bi = oi; bz = oz; }
+                }
+                if (!(nrm > 0.0) || !isfinite(nrm)) { have_ls = false; break; }
+                const double sc = (bz < 0 ? -1.0 : 1.0) / sqrt(nrm);
+                z *= sc;
+                const double diff = warp_max_f64(lane < 9 ? fabs(z - y_l) : 0.0);
+                y_l = z;
+                __syncwarp();
+                if (diff <= 4e-16 || (diff <= 1e-13 && diff >= prev)) break;
+                prev = diff;
+            }
+            if (have_ls) {
+                double h0[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) h0[i] = shfl_f64(y_l, i);
+                const double norm[8] = {cMx, cMy, cmx, cmy, sMx, sMy, smx, smy};
+                double Hk[9];
+                dlt_denormalise(h0, norm, Hk);
+                bool fin = true;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) fin &= isfinite(Hk[i]);
+                if (fin)
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) H[i] = Hk[i];
+            }
+        }
+        // ---- LM polish (LMSolverImpl::run, 9 parameters, <= 10 iterations) ---------------------------
+        double x[9], v[9], D[9], d[9], xd[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) x[i] = H[i];
+        double S = 0, rmax = 0;
+        auto linearise = [&](const double* hh) {
+            PointSums ps = {};
+            double vx[3] = {0, 0, 0}, vy[3] = {0, 0, 0}, vq[3] = {0, 0, 0}, s = 0, rm = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (act[h]) {
+                    double ww = hh[6] * Mx[h] + hh[7] * My[h] + hh[8];
+                    ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
+                    const double xi = (hh[0] * Mx[h] + hh[1] * My[h] + hh[2]) * ww;
+                    const double yi = (hh[3] * Mx[h] + hh[4] * My[h] + hh[5]) * ww;
+                    const double rx = xi - mx[h], ry = yi - my[h];
+                    s += rx * rx + ry * ry;
+                    rm = fmax(rm, fmax(fabs(rx), fabs(ry)));
+                    const double b[3] = {Mx[h] * ww, My[h] * ww, ww};
+                    accumulate_point(ps, b, xi, yi, xi * xi + yi * yi);
+                    const double g = xi * rx + yi * ry;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { vx[q] += b[q] * rx; vy[q] += b[q] * ry; vq[q] += b[q] * g; }
+                }
+            reduce_and_store_matrix(ps, sh.A);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                v[q] = warp_sum_f64(vx[q]); v[3 + q] = warp_sum_f64(vy[q]); v[6 + q] = -warp_sum_f64(vq[q]);
+            }
+            S = warp_sum_f64(s);
+            rmax = warp_max_f64(rm);
+        };
+        auto cost = [&](const double* hh) {
+            double s = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (act[h]) {
+                    double ww = hh[6] * Mx[h] + hh[7] * My[h] + hh[8];
+                    ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
+                    const double rx = (hh[0] * Mx[h] + hh[1] * My[h] + hh[2]) * ww - mx[h];
+                    const double ry = (hh[3] * Mx[h] + hh[4] * My[h] + hh[5]) * ww - my[h];
+                    s += rx * rx + ry * ry;
+                }
+            return warp_sum_f64(s);
+        };
+        // gauge-fixed solve A d = rhs with null vector x (bordered 10x10), result in sh.vec
+        auto solve_gauge = [&](const double* rhs) -> bool {
+            double xn = 0, dmx = 0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) { xn += x[i] * x[i]; dmx = fmax(dmx, fabs(sh.A[i * 9 + i])); }
+            if (!(xn > 0.0) || !(dmx > 0.0)) return false;
+            const double sc = dmx / sqrt(xn);
+            for (int t = lane; t < 81; t += 32) sh.aug[(t / 9) * 11 + (t % 9)] = sh.A[t];
+            if (lane < 9) {
+                sh.aug[lane * 11 + 9] = sc * x[lane];
+                sh.aug[lane * 11 + 10] = rhs[lane];
+                sh.aug[9 * 11 + lane] = sc * x[lane];
+            }
+            if (lane == 0) { sh.aug[9 * 11 + 9] = 0.0; sh.aug[9 * 11 + 10] = 0.0; }
+            __syncwarp();
+            return warp_gauss_solve<10, 11>(sh.aug, sh.vec);
+        };
+        linearise(x);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) D[i] = sh.A[i * 9 + i];
+        const double Rlo = 0.25, Rhi = 0.75;
+        double lambda = 1, lc = 0.75;
+        int iter = 0;
+        for (;;) {
+            bool ok;
+            if (lambda > 0) {
+                for (int t = lane; t < 81; t += 32) {
+                    const int r = t / 9, c = t % 9;
+                    sh.aug[r * 10 + c] = sh.A[t] + (r == c ? lambda * D[r] : 0.0);
+                }
+                if (lane < 9) sh.aug[lane * 10 + 9] = v[lane];
+                __syncwarp();
+                ok = warp_gauss_solve<9, 10>(sh.aug, sh.vec);
+            } else {
+                ok = solve_gauge(v);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 9; ++i) { d[i] = ok ? sh.vec[i] : 0.0; xd[i] = x[i] - d[i]; }
+            const double Sd = cost(xd);
+            double dS = 0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                double t = 2.0 * v[i];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) t -= sh.A[i * 9 + k] * d[k];
+                dS += d[i] * t;
+            }
+            const double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
+            if (R > Rhi) {
+                lambda *= 0.5;
+                if (lambda < lc) lambda = 0;
+            } else if (R < Rlo) {
+                double t = 0;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) t += d[i] * v[i];
+                double nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1) + 2;
+                nu = fmin(fmax(nu, 2.), 10.);
+                if (lambda == 0) {
+                    double maxval = DBL_EPSILON;
+                    for (int k = 0; k < 9; ++k) {
+                        double e[9];
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) e[i] = (i == k) ? 1.0 : 0.0;
+                        __syncwarp();
+                        if (solve_gauge(e)) maxval = fmax(maxval, fabs(sh.vec[k]));
+                        __syncwarp();
+                    }
+                    lambda = lc = 1. / maxval;
+                    nu *= 0.5;
+                }
+                lambda *= nu;
+            }
+            double dmax = 0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) dmax = fmax(dmax, fabs(d[i]));
+            __syncwarp();
+            if (Sd < S) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) x[i] = xd[i];
+                linearise(x);
+            }
+            iter++;
+            const bool proceed = iter < 10 && dmax >= (double)FLT_EPSILON && rmax >= (double)FLT_EPSILON;
+            if (!proceed) break;
+        }
+        const double sc = fabs(x[8]) > (double)FLT_EPSILON ? 1. / x[8] : 1.;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) H[i] = x[i] * sc;
+        // ---- final mask from the refined H: lanes are points, ballots make the mask ------------------
+        float Hf[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) Hf[k] = (float)H[k];
+        pm = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            const int i = pass * 32 + lane;
+            const bool in = i < N && reproj_err_f32(Hf, sh.pl.sx[i], sh.pl.sy[i], sh.pl.dx[i], sh.pl.dy[i]) <= a.thr_sq;
+            pm |= (uint64_t)__ballot_sync(kFull, in) << (32 * pass);
+        }
+        count = __popcll(pm);
+        if (lane < 9) a.H[(size_t)f * 9 + lane] = H[lane < 9 ? lane : 0];
+    }
+    // position bits -> channel bits
+    uint64_t cm = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int i = pass * 32 + lane;
+        if (i < N && ((pm >> i) & 1ull)) cm |= 1ull << sh.pl.ch[i];
+    }
+    unsigned lo = __reduce_or_sync(kFull, (unsigned)cm), hi = __reduce_or_sync(kFull, (unsigned)(cm >> 32));
+    if (lane == 0) {
+        a.inlier_mask[f] = ((uint64_t)hi << 32) | lo;
+        a.info[4 * f + 1] = count;
+    }
+}
+
 }  // namespace egl
 
 using namespace egl;
@@ -392,6 +751,14 @@ extern "C" int egl_fit_homography(const int32_t* kp_xy, const uint8_t* kp_order,
     }
     int rc = cuda_status(cudaGetLastError(), "egl_fit_homography: hypothesis kernel launch");
     if (rc) return rc;
-    refit_kernel<<<(F + kRefitThreads - 1) / kRefitThreads, kRefitThreads, 0, s>>>(a);
+    // One warp per frame minimises latency (a 2250-frame clip is a single wave); one thread per frame
+    // has the higher throughput once there are more frames than resident warps (measured cross-over
+    // ~8k frames on B200).  EGL_REFIT_VARIANT = 1 / 2 forces the thread / warp kernel.
+    static const char* refit_env = getenv("EGL_REFIT_VARIANT");
+    const int refit_variant = refit_env ? atoi(refit_env) : 0;
+    if (refit_variant == 1 || (refit_variant == 0 && F > 8192))
+        refit_kernel<<<(F + kRefitThreads - 1) / kRefitThreads, kRefitThreads, 0, s>>>(a);
+    else
+        refit_warp_kernel<<<(F + kRefitWarps - 1) / kRefitWarps, kRefitWarps * 32, 0, s>>>(a);
     return cuda_status(cudaGetLastError(), "egl_fit_homography: refit kernel launch");
 }
