@@ -231,6 +231,8 @@ __global__ void __launch_bounds__(kFixedThreads) ransac_fixedk_kernel(FitArgs a,
     __shared__ float4 s_pt[kMaxPts];  // normalised (X', Y', x', y'): one broadcast LDS.128 per point
     __shared__ int s_cnt[kFixedThreads / 32], s_hyp[kFixedThreads / 32];
     __shared__ float s_H[8];
+    __shared__ float s_qH[kFixedThreads / 32][64][9];  // per-warp queue of accepted hypotheses (padded rows)
+    __shared__ int s_qh[kFixedThreads / 32][64];
     __shared__ FixedKNorm s_nm;
     __shared__ int s_N, s_ok;
     __shared__ unsigned long long s_used;
@@ -258,17 +260,50 @@ __global__ void __launch_bounds__(kFixedThreads) ransac_fixedk_kernel(FitArgs a,
     }
     __syncthreads();
 
+    // Two phases per batch of 32 candidates so that no lane idles while others score:
+    //   A  every lane draws one sample and solves it (cheap); samples rejected by the checkSubset
+    //      rules -- about half of them at 40 % outliers -- simply produce no queue entry;
+    //   B  accepted hypotheses are compacted (ballot) into a per-warp queue in shared memory and scored
+    //      32 at a time, one hypothesis per lane over all N points (the expensive part, all lanes busy).
+    // The result is order independent: most inliers, ties to the lowest hypothesis index.
+    float (*qH)[9] = s_qH[warp];
+    int* qh = s_qh[warp];
+    int qn = 0;
     int best_cnt = 0, best_h = 0x7fffffff;
     float best_H[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int h = tid; h < a.K; h += kFixedThreads) {
-        int idx[4];
-        if (a.hyp) {
-            const uchar4 q = reinterpret_cast<const uchar4*>(a.hyp)[(size_t)f * a.K + h];
-            idx[0] = q.x; idx[1] = q.y; idx[2] = q.z; idx[3] = q.w;
-        } else {
-            seeded_subset(a.seed, (uint64_t)f, (uint64_t)a.K, (uint64_t)h, N, idx);
+    auto score_queue = [&](int n_active) {  // lanes < n_active score queue entry `lane`
+        if (lane < n_active) {
+            float Hn[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) Hn[k] = qH[lane][k];
+            const int h = qh[lane];
+            int cnt = 0;
+#pragma unroll 4
+            for (int i = 0; i < N; ++i) {
+                const float4 q = s_pt[i];
+                cnt += fixedk_inlier(Hn, q.x, q.y, q.z, q.w);
+            }
+            if (cnt > best_cnt || (cnt == best_cnt && h < best_h)) {
+                best_cnt = cnt;
+                best_h = h;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) best_H[k] = Hn[k];
+            }
         }
-        bool ok = idx[0] < N && idx[1] < N && idx[2] < N && idx[3] < N;
+    };
+    for (int base = warp * 32; base < a.K; base += kFixedThreads) {
+        const int h = base + lane;
+        bool ok = h < a.K;
+        int idx[4] = {0, 1, 2, 3};
+        if (ok) {
+            if (a.hyp) {
+                const uchar4 q = reinterpret_cast<const uchar4*>(a.hyp)[(size_t)f * a.K + h];
+                idx[0] = q.x; idx[1] = q.y; idx[2] = q.z; idx[3] = q.w;
+            } else {
+                seeded_subset(a.seed, (uint64_t)f, (uint64_t)a.K, (uint64_t)h, N, idx);
+            }
+        }
+        ok = ok && idx[0] < N && idx[1] < N && idx[2] < N && idx[3] < N;
         ok = ok && idx[0] != idx[1] && idx[0] != idx[2] && idx[0] != idx[3] && idx[1] != idx[2] && idx[1] != idx[3] &&
              idx[2] != idx[3];
         float p[4][4];
@@ -279,21 +314,38 @@ __global__ void __launch_bounds__(kFixedThreads) ransac_fixedk_kernel(FitArgs a,
         }
         float Hn[8];
         ok = fixedk_hypothesis(p, Hn) && ok;
-        int cnt = 0;
+        const unsigned bal = __ballot_sync(kFull, ok);
         if (ok) {
-#pragma unroll 4
-            for (int i = 0; i < N; ++i) {
-                const float4 q = s_pt[i];
-                cnt += fixedk_inlier(Hn, q.x, q.y, q.z, q.w);
-            }
-        }
-        if (cnt > best_cnt) {  // ascending h per thread: strict > keeps the earliest
-            best_cnt = cnt;
-            best_h = h;
+            const int pos = qn + __popc(bal & ((1u << lane) - 1u));
 #pragma unroll
-            for (int k = 0; k < 8; ++k) best_H[k] = Hn[k];
+            for (int k = 0; k < 8; ++k) qH[pos][k] = Hn[k];
+            qh[pos] = h;
+        }
+        qn += __popc(bal);
+        __syncwarp();
+        if (qn >= 32) {
+            score_queue(32);
+            __syncwarp();
+            // move the leftover entries [32, qn) to the front
+            float t[8];
+            int th = 0;
+            const bool mv = lane < qn - 32;
+            if (mv) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t[k] = qH[32 + lane][k];
+                th = qh[32 + lane];
+            }
+            __syncwarp();
+            if (mv) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) qH[lane][k] = t[k];
+                qh[lane] = th;
+            }
+            qn -= 32;
+            __syncwarp();
         }
     }
+    score_queue(qn);
     // block arg-max: most inliers, ties -> lowest hypothesis index
     int c = best_cnt, hh = best_h;
 #pragma unroll
@@ -466,7 +518,7 @@ __device__ __forceinline__ void reduce_and_store_matrix(PointSums& s, double* A)
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kRefitWarps * 32) refit_warp_kernel(FitArgs a) {
+__global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs a) {
     __shared__ RefitShared s_all[kRefitWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.x * kRefitWarps + warp;
@@ -549,7 +601,7 @@ __global__ void __launch_bounds__(kRefitWarps * 32) refit_warp_kernel(FitArgs a)
                 const double diff = warp_max_f64(lane < 9 ? fabs(z - y_l) : 0.0);
                 y_l = z;
                 __syncwarp();
-                if (diff <= 4e-16 || (diff <= 1e-13 && diff >= prev)) break;
+                if (diff <= 1e-13 || (diff <= 1e-10 && diff >= prev)) break;
                 prev = diff;
             }
             if (have_ls) {

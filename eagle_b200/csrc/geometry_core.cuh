@@ -205,7 +205,7 @@ EGL_HD_NOINLINE bool smallest_eigvec9(const double* A, double* aug, double* h) {
             diff = fmax(diff, fabs(z[i] - y[i]));
             y[i] = z[i];
         }
-        if (diff <= 4e-16 || (diff <= 1e-13 && diff >= prev)) break;  // converged / stagnated at rounding level
+        if (diff <= 1e-13 || (diff <= 1e-10 && diff >= prev)) break;  // converged (far below what the LM polish needs) / stagnated
         prev = diff;
     }
     for (int i = 0; i < n; ++i) h[i] = y[i];

@@ -29,6 +29,20 @@ def sha(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def cadence_fixture(name, n_frames, width, height, seed, fps, num_homography, blank):
+    """Homography cadence (interval fps/num_homography, every frame a keypoint frame) incl. frames
+    whose heatmaps are blanked so that the fit fails and the reference retries on the next frame."""
+    clip = synthetic.make_clip(n_frames, width, height, seed=seed, with_frames=True, ghost_prob=0.05)
+    for b in blank:
+        clip["heatmaps"][b, 3:] = 0.0   # leaves channels 0-2 (two of them off-plane): < 4 usable landmarks
+    res, rec = ref_harness.run_reference(clip["frames"], clip["heatmaps"], clip["objects"], fps=fps,
+                                         num_homography=num_homography, num_keypoint_detection=fps)
+    np.savez_compressed(os.path.join(GOLDEN, name), n_frames=n_frames, width=width, height=height, seed=seed, fps=fps,
+                        num_homography=num_homography, blank=np.array(blank, np.int32), heatmaps_sha256=sha(clip["heatmaps"]),
+                        result_json=json.dumps(res, default=float, sort_keys=True), n_fits=len(rec.fits))
+    print(name, "frames", n_frames, "fits", len(rec.fits))
+
+
 def clip_fixture(name, n_frames, width, height, seed, ghost_prob):
     clip = synthetic.make_clip(n_frames, width, height, seed=seed, with_frames=True, ghost_prob=ghost_prob)
     res, rec = ref_harness.run_reference(clip["frames"], clip["heatmaps"], clip["objects"])
@@ -172,6 +186,7 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     clip_fixture("ref_clip_720p.npz", 8, 1280, 720, seed=7, ghost_prob=0.05)
     clip_fixture("ref_clip_1080p.npz", 6, 1920, 1080, seed=8, ghost_prob=0.10)
+    cadence_fixture("ref_cadence_720p.npz", 17, 1280, 720, seed=9, fps=5, num_homography=1, blank=[])
     decode_fixture()
     find_homography_fixture()
     resize_fixture()

@@ -1,9 +1,10 @@
 """Oracle: the per-frame geometry path end to end (test infrastructure; also the CPU baseline).
 
 Restates the frame loop of ``CoordinateModel.get_coordinates``
-(eagle/models/coordinate_model.py:277-415) for the cadence the benchmark uses -- every frame is a
-keypoint frame AND a homography frame (the reference called with ``fps == num_homography ==
-num_keypoint_detection``, so both intervals at :205-206 are 1) -- with
+(eagle/models/coordinate_model.py:277-415) for the cadence the accelerated path covers -- every frame
+is a keypoint frame (``num_keypoint_detection == fps``, keypoint interval 1 at :206) and the homography
+is refreshed every ``homography_interval`` frames or after a failed attempt (:205,:333,:350-367); the
+benchmark uses interval 1 -- with
   * the network forward replaced by "heatmaps are given" (decode = keypoint_hrnet.py:583-594),
   * ``detect_objects`` replaced by "boxes are given",
   * the optical-flow rescue for frames with < 4 model keypoints (:285-311) left out: such frames
@@ -29,7 +30,7 @@ def frame_time(i: int, fps: int) -> str:
 
 def get_coordinates(heatmaps, objects_per_frame, width: int, height: int, fps: int = 1,
                     keypoint_conf: float = 0.3, synthesis: bool = True, trace: list | None = None,
-                    fit=None) -> dict:
+                    fit=None, num_homography: int | None = None) -> dict:
     """Run the restated path over F frames.
 
     heatmaps: (F, 57, h, w) float32 (any array-like indexable by frame).
@@ -44,6 +45,9 @@ def get_coordinates(heatmaps, objects_per_frame, width: int, height: int, fps: i
     homography_matrix = None
     prev_homography_matrix = None
     prev_keypoints = {}
+    compute_homography = False
+    # :205 -- homography cadence; num_homography=None means "every frame" (interval 1)
+    homography_interval = 1 if num_homography is None else max(1, int(fps / max(1, num_homography)))
     F = len(objects_per_frame)
     for i in range(F):
         t = {} if trace is not None else None
@@ -56,10 +60,13 @@ def get_coordinates(heatmaps, objects_per_frame, width: int, height: int, fps: i
             t["synthesised"] = dict(keypoints)
         prev_keypoints = keypoints  # :330
         objects = objects_per_frame[i]
+        attempt = (i % homography_interval == 0) or compute_homography  # :333
         img_pts, world_pts, used_labels = _hom.gather_correspondences(keypoints)
         if t is not None:
-            t.update(img_pts=img_pts, world_pts=world_pts, used_labels=used_labels, H=None, mask=None)
-        if len(img_pts) >= 4:
+            t.update(img_pts=img_pts, world_pts=world_pts, used_labels=used_labels, H=None, mask=None, attempted=attempt)
+        if attempt and len(img_pts) < 4:
+            compute_homography = True  # :350-352
+        if attempt and len(img_pts) >= 4:
             if fit is None:
                 new_H, mask, _ = _hom.find_homography_cascade(img_pts, world_pts)
             else:
@@ -70,8 +77,11 @@ def get_coordinates(heatmaps, objects_per_frame, width: int, height: int, fps: i
                     prev_keypoints = keypoints
                 homography_matrix = new_H
                 prev_homography_matrix = homography_matrix
+                compute_homography = False
                 if t is not None:
                     t.update(H=new_H.copy(), mask=None if mask is None else mask.copy())
+            else:
+                compute_homography = True  # :366-367
         H_use = homography_matrix if homography_matrix is not None else prev_homography_matrix
         indiv, raw = _proj.project_objects(objects, H_use)
         bounds = _proj.boundaries(width, height, H_use)

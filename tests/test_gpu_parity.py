@@ -307,3 +307,62 @@ def test_fixed_k_bit_exact_against_c_mirror(engine, use_table):
         # the gross outliers planted by the generator are rejected
         assert not any(mo.ravel()[k] for k, c in enumerate(on) if flags[f, c])
     assert worst < 1e-6, worst
+
+
+def test_drop_in_get_coordinates_with_cadence(golden_dir):
+    """The reference-shaped front end (frames in, dict out; K1 -> network stand-in -> K2..K4) with the
+    reference's homography cadence (fps=5, num_homography=1), against the dict the UNMODIFIED reference
+    produced for the same clip (tests/golden/ref_cadence_720p.npz)."""
+    from eagle_b200 import synthetic
+    from eagle_b200.coordinate_model import CoordinateModel, GeometryPath
+    g = np.load(os.path.join(golden_dir, "ref_cadence_720p.npz"))
+    n, w, h = int(g["n_frames"]), int(g["width"]), int(g["height"])
+    clip = synthetic.make_clip(n, w, h, seed=int(g["seed"]), with_frames=True, ghost_prob=0.05)
+    assert sha(clip["heatmaps"]) == str(g["heatmaps_sha256"])
+    hm = torch.from_numpy(clip["heatmaps"]).cuda()
+    state = {"i": 0, "seen": 0}
+
+    def keypoint_model(x):  # stands in for HRNet-W48 + sigmoid: hands out the synthetic heatmaps in frame order
+        assert x.shape[1:] == (3, 540, 960) and x.dtype == torch.float32 and x.is_cuda
+        out = hm[state["i"]:state["i"] + x.shape[0]]
+        state["i"] += x.shape[0]
+        return out
+
+    objs = iter(clip["objects"])
+    model = CoordinateModel(keypoint_model=keypoint_model, detect_objects=lambda frame: next(objs), chunk=8)
+    got = model.get_coordinates(list(clip["frames"]), fps=int(g["fps"]), num_homography=int(g["num_homography"]),
+                                num_keypoint_detection=int(g["fps"]), verbose=False)
+    assert json.dumps(got, default=float, sort_keys=True) == str(g["result_json"])
+    # same through the lower-level path object
+    got2 = GeometryPath("cuda:0").run(hm, clip["objects"], w, h, fps=int(g["fps"]), homography_interval=5)
+    assert json.dumps(got2, default=float, sort_keys=True) == str(g["result_json"])
+    with pytest.raises(NotImplementedError):
+        model.get_coordinates(list(clip["frames"][:2]), fps=25, num_homography=1, num_keypoint_detection=3)
+
+
+def test_refit_thread_and_warp_kernels_agree():
+    """EGL_REFIT_VARIANT=1 (one thread per frame, the host-checkable scalar code) and =2 (one warp per
+    frame) are the same algorithm: identical masks, H equal to rounding.  Run in subprocesses because the
+    switch is read once per process."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from eagle_b200 import synthetic
+from eagle_b200.coordinate_model import GeometryPath
+clip = synthetic.make_clip(12, 1920, 1080, seed=77, ghost_prob=0.1)
+p = GeometryPath("cuda:0")
+kp, fit, hi, at, pr = p.run_device(torch.from_numpy(clip["heatmaps"]).cuda(), torch.zeros((12, 1, 2)).cuda(),
+                                   torch.zeros(12, dtype=torch.int32).cuda(), 1920, 1080)
+np.save(sys.argv[1], np.concatenate([fit.H.cpu().numpy().ravel(), fit.inlier_mask.cpu().numpy().astype(np.float64)]))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    outs = []
+    for variant in ("1", "2"):
+        f = tempfile.NamedTemporaryFile(suffix=".npy", delete=False).name
+        subprocess.check_call([sys.executable, "-c", code, f], env=dict(os.environ, EGL_REFIT_VARIANT=variant))
+        outs.append(np.load(f)); os.unlink(f)
+    a, b = outs
+    assert np.array_equal(a[-12:], b[-12:])                      # masks
+    assert np.max(np.abs(a[:-12] - b[:-12]) / np.abs(a[:-12])) < 1e-9   # H

@@ -154,3 +154,15 @@ def test_empty_and_few_point_frames():
         assert res[i]["Coordinates"]["Player"][1]["Transformed_Coordinates"] is None
         assert res[i]["Coordinates"]["Player"][1]["Image_Bottom_center"] == [2, 4]
     assert res[0]["Keypoints"] == {} and len(res[1]["Keypoints"]) == 3
+
+
+def test_homography_cadence_matches_reference(golden_dir):
+    """fps=5, num_homography=1 -> fit on frames 0,5,10,15 only; the rest reuse H (reference run)."""
+    g = np.load(os.path.join(golden_dir, "ref_cadence_720p.npz"))
+    clip = synthetic.make_clip(int(g["n_frames"]), int(g["width"]), int(g["height"]), seed=int(g["seed"]), ghost_prob=0.05)
+    assert sha(clip["heatmaps"]) == str(g["heatmaps_sha256"])
+    trace = []
+    res = pipeline.get_coordinates(clip["heatmaps"], clip["objects"], clip["width"], clip["height"], fps=int(g["fps"]),
+                                   num_homography=int(g["num_homography"]), trace=trace)
+    assert json.dumps(res, default=float, sort_keys=True) == str(g["result_json"])
+    assert sum(t["H"] is not None for t in trace) == int(g["n_fits"]) == 4
