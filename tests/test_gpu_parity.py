@@ -81,6 +81,17 @@ def test_decode_edge_cases_golden(engine, golden_dir):
             assert got == want and list(got) == list(want)
 
 
+def test_get_keypoints_signature_matches_reference(golden_dir):
+    """KeypointDecoder.get_keypoints == the reference's KeypointModel.get_keypoints on the same heatmaps
+    (tuples (channel, x_n, y_n, score), Python floats, score > 0.01 only)."""
+    from eagle_b200.keypoints import KeypointDecoder
+    g = np.load(os.path.join(golden_dir, "decode_small.npz"))
+    got = KeypointDecoder().get_keypoints(torch.from_numpy(g["heatmaps"]).cuda())
+    flat = np.array([(n, i, x, y, s) for n, lst in enumerate(got) for (i, x, y, s) in lst], np.float64)
+    assert np.array_equal(flat, g["keypoints"])
+    assert all(isinstance(t[0], int) and isinstance(t[1], float) and isinstance(t[3], float) for lst in got for t in lst)
+
+
 def test_decode_special_values(engine):
     hm = np.zeros((2, 57, 135, 240), np.float32)
     hm[0, 0] = -np.inf                     # all -inf -> index 0
