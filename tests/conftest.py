@@ -16,6 +16,17 @@ def pytest_configure(config):
     warnings.filterwarnings("ignore", category=DeprecationWarning)
 
 
+def pytest_sessionstart(session):
+    """Make sure the in-tree CUDA extension exists (nvcc cross-compiles without a GPU) so that a fresh
+    checkout can run the suite; a stale library is rebuilt.  Building is skipped silently when nvcc is
+    absent -- the tests that need the library then fail with its own "build me first" error."""
+    try:
+        from eagle_b200.build import build_native
+        build_native()
+    except Exception as e:  # noqa: BLE001
+        print(f"[conftest] could not build libeagle_b200.so: {e}")
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

@@ -166,3 +166,29 @@ def test_homography_cadence_matches_reference(golden_dir):
                                    num_homography=int(g["num_homography"]), trace=trace)
     assert json.dumps(res, default=float, sort_keys=True) == str(g["result_json"])
     assert sum(t["H"] is not None for t in trace) == int(g["n_fits"]) == 4
+
+
+def test_rho_lmeds_fallbacks_never_rescue_a_failed_ransac():
+    """coordinate_model.py:354-357 falls through to cv2.RHO / cv2.LMEDS when RANSAC returns None.  On
+    degenerate inputs (collinear, coincident, one-off-a-line) the cascade returns None exactly when
+    RANSAC alone does -- which is why the CUDA path reports EGL_FIT_NO_MODEL instead of porting them."""
+    rng = np.random.default_rng(0)
+    on = [i for i in range(57) if i not in (0, 1, 24, 25)]
+    n_none = 0
+    for t in range(120):
+        n = int(rng.integers(4, 30)); sel = np.sort(rng.choice(on, n, replace=False)); wor = WORLD_XY_F32[sel]
+        kind = t % 4
+        if kind == 0:
+            img = np.c_[np.arange(n) * 7 + 3, np.arange(n) * 14 + 9]
+        elif kind == 1:
+            img = np.tile(rng.integers(0, 1000, (1, 2)), (n, 1))
+        elif kind == 2:
+            img = np.c_[rng.integers(0, 1900, n), np.full(n, 500)]
+        else:
+            img = np.c_[np.arange(n) * 7 + 3, np.arange(n) * 14 + 9]; img[0] += (50, -20)
+        img = img.astype(np.float32)
+        Hr, _ = cv2.findHomography(img, wor, cv2.RANSAC, 5.0)
+        Hc, _, _ = homography.find_homography_cascade(img, wor)
+        assert (Hr is None) == (Hc is None)
+        n_none += Hr is None
+    assert n_none > 60
