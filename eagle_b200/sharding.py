@@ -62,3 +62,61 @@ def gather_to_rank0(records: torch.Tensor, counts: Sequence[int], group=None) ->
         return torch.cat([b[:counts[r]] for r, b in enumerate(bufs)])
     dist.gather(records, None, dst=0, group=group)
     return None
+
+
+def run_sharded(path, heatmaps_local: torch.Tensor, objects_local: Sequence[dict], width: int, height: int, fps: int,
+                homography_interval: int = 1, group=None):
+    """The geometry path for one clip sharded by contiguous frame range over the ranks of ``group``.
+
+    Every rank calls this with ITS frames' heatmaps (F_r,57,h,w on its GPU) and detector dicts, in rank
+    order of the clip.  The bandwidth- and compute-heavy kernels (decode, synthesis, RANSAC + refit) run
+    on each rank's range; the small per-frame results are gathered to rank 0, which evaluates the
+    homography cadence over the WHOLE clip (it carries state across shard boundaries exactly as the
+    reference's sequential loop does), projects and assembles the reference-format dict.  Returns that
+    dict on rank 0 and None elsewhere.  Works with NCCL (GPU tensors) and with gloo (records staged
+    through the host, used by the single-GPU tests)."""
+    import numpy as np
+
+    from .coordinate_model import assemble_frames
+    from .synthetic import objects_to_arrays
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    e = path.engine
+    F_r = heatmaps_local.shape[0]
+    # per-rank frame counts and the clip-wide maximum object count (host-side, tiny)
+    local_meta = (F_r, max([1] + [sum(len(v) for v in o.values()) for o in objects_local]))
+    metas = [None] * world
+    if world > 1:
+        dist.all_gather_object(metas, local_meta, group=group)
+    else:
+        metas = [local_meta]
+    counts = [m[0] for m in metas]
+    P = max(m[1] for m in metas)
+    kp = e.decode(heatmaps_local, width, height, path.keypoint_conf)
+    if path.synthesis:
+        e.synthesize(kp)
+    fit = e.fit(kp, mode=path.fit_mode, K=path.max_iters, thr=path.thr)
+    foot_h, cnt_h = objects_to_arrays(list(objects_local), P)
+    foot = torch.from_numpy(foot_h).to(e.device); cnt = torch.from_numpy(cnt_h).to(e.device)
+    like = [kp.xy, kp.order, kp.count, fit.H, fit.used_mask, fit.inlier_mask, fit.status, foot, cnt]
+    rec = pack_results(like)
+    backend = dist.get_backend(group) if (dist.is_initialized() and world > 1) else None
+    if backend == "gloo":
+        rec = rec.cpu()
+    all_rec = gather_to_rank0(rec, counts, group) if world > 1 else rec
+    objs_all = [None] * world
+    if world > 1:
+        dist.gather_object(list(objects_local), objs_all if rank == 0 else None, dst=0, group=group)
+    else:
+        objs_all = [list(objects_local)]
+    if rank != 0:
+        return None
+    all_rec = all_rec.to(e.device)
+    xy, order, count, H, used, inl, status, foot_a, cnt_a = unpack_results(all_rec, like)
+    h_index, attempted = e.select(status.contiguous(), homography_interval)
+    proj = e.project(H.contiguous(), foot_a.contiguous(), cnt_a.contiguous(), width, height, h_index=h_index)
+    objects_per_frame = [o for part in objs_all for o in part]
+    c = lambda t: t.cpu().numpy()
+    return assemble_frames(objects_per_frame, fps, 0, c(xy), c(order), c(count), c(used), c(inl), c(status), c(attempted),
+                           c(h_index), c(proj.coords_i), c(proj.in_bounds), c(proj.bounds))

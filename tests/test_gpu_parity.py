@@ -378,3 +378,43 @@ np.save(sys.argv[1], np.concatenate([fit.H.cpu().numpy().ravel(), fit.inlier_mas
     assert np.array_equal(a[-12:], b[-12:])                      # masks
     # H: the LM minimum is flat to ~1e-8 (cost changes < 1e-15 there), so two summation orders agree to that
     assert np.max(np.abs(a[:-12] - b[:-12]) / np.abs(a[:-12])) < 1e-6
+
+
+def _sharded_worker(rank, world, port, golden_path, out_q):
+    import torch.distributed as dist
+    from eagle_b200 import synthetic
+    from eagle_b200.coordinate_model import GeometryPath
+    from eagle_b200.sharding import frame_range, run_sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = np.load(golden_path)
+    n, w, h = int(g["n_frames"]), int(g["width"]), int(g["height"])
+    clip = synthetic.make_clip(n, w, h, seed=int(g["seed"]), ghost_prob=0.05)
+    lo, hi = frame_range(n, rank, world)
+    path = GeometryPath("cuda:0")
+    res = run_sharded(path, torch.from_numpy(clip["heatmaps"][lo:hi]).cuda(), clip["objects"][lo:hi], w, h, fps=int(g["fps"]),
+                      homography_interval=5)
+    if rank == 0:
+        out_q.put(json.dumps(res, default=float, sort_keys=True) == str(g["result_json"]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_clip_equals_reference_dict(golden_dir, world):
+    """Frame-range sharding (here: ranks share cuda:0 and gather over gloo; NCCL on a multi-GPU box):
+    the shard boundaries (17 frames over 2 / 3 ranks) do not align with the homography interval (5), so
+    the cadence state has to be carried across shards on rank 0 -- the result must still be the dict the
+    unmodified reference produced for the whole clip."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, os.path.join(golden_dir, "ref_cadence_720p.npz"), q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
