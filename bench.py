@@ -31,6 +31,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_OUT = sys.stdout
 
 W, H = 1920, 1080
 FRAMES_PER_GPU = 2250
@@ -156,7 +157,7 @@ def run_reference_arm(args, rank):
                                        "cv2.resize+normalise, np.argmax decode, cv2.findHomography cascade, cv2.perspectiveTransform)"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -186,6 +187,12 @@ def build_inputs(torch, dev, n_frames, seed):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 from C (NCCL prints its version
+    # banner there) are redirected to stderr, and the line is printed through a private copy of fd 1.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -395,7 +402,7 @@ def main():
             "preprocess_roofline": {"bound": "hbm", "achieved": F * (H * W * 3 + 3 * 540 * 960 * 4) / (k1_ms * 1e-3) / 1e9, "unit": "GB/s",
                                     "frac": F * (H * W * 3 + 3 * 540 * 960 * 4) / (k1_ms * 1e-3) / 1e9 / peak},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
