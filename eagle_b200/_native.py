@@ -32,15 +32,16 @@ lib.egl_last_error.restype = C.c_char_p
 lib.egl_sm_count.restype = _i
 lib.egl_preprocess_u8.argtypes = [_vp, _i, _i, _i, _sz, _sz, _vp, _vp]
 lib.egl_decode_heatmaps.argtypes = [_vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]
+lib.egl_decode_logits.argtypes = [_vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]
 lib.egl_synthesize_keypoints.argtypes = [_vp, _vp, _vp, _i, _i, _vp]
 lib.egl_fit_homography.argtypes = [_vp, _vp, _vp, _i, _i, _i, _vp, _u64, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp]
 lib.egl_select_homography.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp]
 lib.egl_project_points.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
-for _name in ("egl_preprocess_u8", "egl_decode_heatmaps", "egl_synthesize_keypoints", "egl_fit_homography",
+for _name in ("egl_preprocess_u8", "egl_decode_heatmaps", "egl_decode_logits", "egl_synthesize_keypoints", "egl_fit_homography",
               "egl_select_homography", "egl_project_points"):
     getattr(lib, _name).restype = _i
 
-EXPORTS = ("egl_version", "egl_last_error", "egl_sm_count", "egl_preprocess_u8", "egl_decode_heatmaps",
+EXPORTS = ("egl_version", "egl_last_error", "egl_sm_count", "egl_preprocess_u8", "egl_decode_heatmaps", "egl_decode_logits",
            "egl_synthesize_keypoints", "egl_fit_homography", "egl_select_homography", "egl_project_points")
 
 if lib.egl_version() != ABI_VERSION:

@@ -241,6 +241,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) argmax_warp_ring_kernel(Decode
 
 // Alternative without the TMA ring (kept for A/B measurements, EGL_DECODE_VARIANT=ldg): one CTA per
 // map, 256 threads, 8 independent 128-bit streaming loads in flight per thread.
+// torch.sigmoid for float on CUDA is 1 / (1 + expf(-x)) with the full-precision expf and an IEEE divide
+// (ATen sigmoid_kernel_cuda); evaluated the same way here so that arg-max over sigmoid(logits) -- with
+// its ties where the float sigmoid saturates or plateaus -- is bit-identical to sigmoid-then-decode.
+__device__ __forceinline__ float sigmoid_like_torch(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
+
+template <bool kSigmoid>
 __global__ void __launch_bounds__(256) argmax_ldg_kernel(DecodeArgs a) {
     __shared__ float s_val[8];
     __shared__ int s_idx[8];
@@ -257,6 +263,15 @@ __global__ void __launch_bounds__(256) argmax_ldg_kernel(DecodeArgs a) {
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * 256;
             v[u] = i < n ? __ldcs(src + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+        if (kSigmoid) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (i0 + u * 256 < n) {
+                    v[u].x = sigmoid_like_torch(v[u].x); v[u].y = sigmoid_like_torch(v[u].y);
+                    v[u].z = sigmoid_like_torch(v[u].z); v[u].w = sigmoid_like_torch(v[u].w);
+                }
+            }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -386,9 +401,9 @@ __global__ void __launch_bounds__(kPostWarps * 32) postprocess_kernel(const int3
 
 using namespace egl;
 
-extern "C" int egl_decode_heatmaps(const float* hm, int F, int hm_h, int hm_w, int img_w, int img_h, double keypoint_conf,
-                                   int32_t* kp_flat, float* kp_score, int32_t* kp_xy, uint8_t* kp_order, int32_t* kp_count,
-                                   void* stream) {
+static int decode_impl(const float* hm, int F, int hm_h, int hm_w, int img_w, int img_h, double keypoint_conf,
+                       int32_t* kp_flat, float* kp_score, int32_t* kp_xy, uint8_t* kp_order, int32_t* kp_count, void* stream,
+                       bool from_logits) {
     EGL_REQUIRE(hm && kp_flat && kp_score && kp_xy && kp_order && kp_count, EGL_ERR_NULL, "egl_decode_heatmaps: null pointer");
     EGL_REQUIRE(F >= 0 && hm_h > 0 && hm_w > 0 && img_w > 0 && img_h > 0, EGL_ERR_SHAPE, "egl_decode_heatmaps: bad shape");
     EGL_REQUIRE(((long long)hm_h * hm_w) % 4 == 0, EGL_ERR_SHAPE,
@@ -409,7 +424,7 @@ extern "C" int egl_decode_heatmaps(const float* hm, int F, int hm_h, int hm_w, i
     if (sms <= 0) return -1;
     // Launch variants (EGL_DECODE_VARIANT, measurement switch; default 4 = register-streaming kernel).
     static const char* variant_env = getenv("EGL_DECODE_VARIANT");
-    const int variant = variant_env ? atoi(variant_env) : 4;
+    const int variant = (variant_env && !from_logits) ? atoi(variant_env) : 4;  // the ring variants take heatmaps only
     int rc = 0;
     auto launch_ring = [&](auto kernel, int stages, int threads, int ctas_per_sm, int chunk_div) -> int {
         DecodeArgs b = a;
@@ -450,7 +465,10 @@ extern "C" int egl_decode_heatmaps(const float* hm, int F, int hm_h, int hm_w, i
         case 10: rc = launch_ring(argmax_kernel<2, 256, 3>, 2, 256, 3, 1); break;         // 3 CTAs/SM, 2 x 32 KB each
         case 11: rc = launch_ring(argmax_kernel<3, 128, 4>, 3, 128, 4, 2); break;         // 4 CTAs/SM, 3 x 16 KB each
         case 0: rc = launch_ring(argmax_kernel<6, 512, 1>, 6, 512, 1, 1); break;    // 6 x 32 KB, 1 CTA/SM
-        default: argmax_ldg_kernel<<<(unsigned)a.total_maps, 256, 0, s>>>(a); break;  // register streaming
+        default:  // register streaming
+            if (from_logits) argmax_ldg_kernel<true><<<(unsigned)a.total_maps, 256, 0, s>>>(a);
+            else argmax_ldg_kernel<false><<<(unsigned)a.total_maps, 256, 0, s>>>(a);
+            break;
     }
     if (rc) return rc;
     rc = cuda_status(cudaGetLastError(), "egl_decode_heatmaps: argmax kernel launch");
@@ -458,4 +476,16 @@ extern "C" int egl_decode_heatmaps(const float* hm, int F, int hm_h, int hm_w, i
     postprocess_kernel<<<(F + kPostWarps - 1) / kPostWarps, kPostWarps * 32, 0, s>>>(kp_flat, kp_score, F, hm_h, hm_w, img_w, img_h, keypoint_conf, kp_xy,
                                                     kp_order, kp_count);
     return cuda_status(cudaGetLastError(), "egl_decode_heatmaps: postprocess kernel launch");
+}
+
+extern "C" int egl_decode_heatmaps(const float* hm, int F, int hm_h, int hm_w, int img_w, int img_h, double keypoint_conf,
+                                   int32_t* kp_flat, float* kp_score, int32_t* kp_xy, uint8_t* kp_order, int32_t* kp_count,
+                                   void* stream) {
+    return decode_impl(hm, F, hm_h, hm_w, img_w, img_h, keypoint_conf, kp_flat, kp_score, kp_xy, kp_order, kp_count, stream, false);
+}
+
+extern "C" int egl_decode_logits(const float* logits, int F, int hm_h, int hm_w, int img_w, int img_h, double keypoint_conf,
+                                 int32_t* kp_flat, float* kp_score, int32_t* kp_xy, uint8_t* kp_order, int32_t* kp_count,
+                                 void* stream) {
+    return decode_impl(logits, F, hm_h, hm_w, img_w, img_h, keypoint_conf, kp_flat, kp_score, kp_xy, kp_order, kp_count, stream, true);
 }

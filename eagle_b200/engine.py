@@ -84,16 +84,17 @@ class GeometryEngine:
                            torch.empty((F, 2), dtype=torch.int32, device=dev))
 
     def decode(self, heatmaps: torch.Tensor, img_w: int, img_h: int, keypoint_conf: float = 0.3,
-               out: KeypointSet | None = None) -> KeypointSet:
-        """heatmaps (F, 57, h, w) float32 contiguous on the device."""
+               out: KeypointSet | None = None, from_logits: bool = False) -> KeypointSet:
+        """heatmaps (F, 57, h, w) float32 contiguous on the device; from_logits=True takes the network's
+        pre-sigmoid output and fuses the sigmoid into the arg-max kernel."""
         assert heatmaps.dtype == torch.float32 and heatmaps.is_cuda and heatmaps.is_contiguous()
         F, C, h, w = heatmaps.shape
         assert C == NUM_LANDMARKS
         kp = out if out is not None else self.alloc_keypoints(F)
         with torch.cuda.device(heatmaps.device):
-            N.check(N.lib.egl_decode_heatmaps(_ptr(heatmaps), F, h, w, img_w, img_h, float(keypoint_conf), _ptr(kp.flat),
-                                              _ptr(kp.score), _ptr(kp.xy), _ptr(kp.order), _ptr(kp.count), _stream()),
-                    "egl_decode_heatmaps")
+            fn = N.lib.egl_decode_logits if from_logits else N.lib.egl_decode_heatmaps
+            N.check(fn(_ptr(heatmaps), F, h, w, img_w, img_h, float(keypoint_conf), _ptr(kp.flat), _ptr(kp.score), _ptr(kp.xy),
+                       _ptr(kp.order), _ptr(kp.count), _stream()), "egl_decode_logits" if from_logits else "egl_decode_heatmaps")
         return kp
 
     # -- F1 ---------------------------------------------------------------------------------

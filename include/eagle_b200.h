@@ -83,6 +83,17 @@ int egl_decode_heatmaps(const float *hm, int F, int hm_h, int hm_w, int img_w, i
                         void *stream);
 
 /*
+ * F3  same as egl_decode_heatmaps, but reads the network's LOGITS (KeypointModel.forward_unnormalized,
+ * keypoint_hrnet.py:572-573) and applies the sigmoid of KeypointModel.forward (:565-570) inside the
+ * arg-max kernel: one pass over HBM instead of sigmoid (read + write) followed by decode (read).
+ * kp_score holds sigmoid(logit); ties of the float sigmoid (saturation at 1.0, plateaus) resolve to the
+ * first index exactly as sigmoid-then-np.argmax does.
+ */
+int egl_decode_logits(const float *logits, int F, int hm_h, int hm_w, int img_w, int img_h, double keypoint_conf,
+                      int32_t *kp_flat, float *kp_score, int32_t *kp_xy, uint8_t *kp_order, int32_t *kp_count,
+                      void *stream);
+
+/*
  * F1  line-intersection keypoint synthesis, appended to kp_order / kp_xy in place.
  * Replaces CoordinateModel._synthesize_keypoints_with_line_intersections
  * (coordinate_model.py:140-186, with :76-138): per world-y and world-x line family with >= 2

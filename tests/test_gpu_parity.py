@@ -418,3 +418,24 @@ def test_sharded_clip_equals_reference_dict(golden_dir, world):
         p.join(300)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_decode_from_logits_equals_sigmoid_then_decode(engine):
+    """F3: the fused sigmoid + arg-max over LOGITS gives bit-identical (index, score) to torch.sigmoid
+    followed by the heatmap decode -- including where the float sigmoid saturates to 1.0 or plateaus, so
+    that several positions tie and the first one must win."""
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    F = 6
+    logits = torch.randn((F, 57, 135, 240), generator=g, device="cuda") * 3.0 - 4.0
+    logits[0, :, 50:60, 100:110] += 25.0            # saturated plateau: sigmoid == 1.0 on many pixels
+    logits[1, :, 10, 20] = 12.0; logits[1, :, 90, 200] = 12.0000001   # distinct logits, same float sigmoid? (tie or not, must agree)
+    logits[2] = logits[2].clamp(max=-6.0)           # everything below the 0.01 score cut
+    logits[3, 5] = 40.0                             # whole map saturated -> index 0
+    logits[4, :, 134, 239] = 9.0
+    hm = torch.sigmoid(logits)
+    a = engine.decode(hm, 1920, 1080)
+    b = engine.decode(logits, 1920, 1080, from_logits=True)
+    assert torch.equal(a.flat, b.flat)
+    assert torch.equal(a.score, b.score)
+    assert torch.equal(a.order, b.order) and torch.equal(a.count, b.count) and torch.equal(a.xy, b.xy)
+    assert int(a.flat[3, 5]) == 0 and float(a.score[3, 5]) == 1.0

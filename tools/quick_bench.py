@@ -39,6 +39,12 @@ def main():
     t = timeit(lambda: eng.decode(hm, 1920, 1080, out=kp))
     gb = F * 57 * 135 * 240 * 4 / 1e9
     print(f"decode   F={F}: {t:.3f} ms  {gb / t * 1e3:.0f} GB/s  {F / t * 1e3:.0f} frames/s")
+    logits = torch.logit(hm.clamp(1e-6, 1 - 1e-6))
+    t2 = timeit(lambda: eng.decode(logits, 1920, 1080, out=kp, from_logits=True))
+    t3 = timeit(lambda: eng.decode(torch.sigmoid(logits), 1920, 1080, out=kp))
+    print(f"decode from logits (fused sigmoid) F={F}: {t2:.3f} ms  {gb / t2 * 1e3:.0f} GB/s   vs torch.sigmoid + decode: {t3:.3f} ms")
+    del logits
+    eng.decode(hm, 1920, 1080, out=kp)
     # F1 + K3 + select + K4
     eng.synthesize(kp)
     fit = eng.alloc_fit(F)
