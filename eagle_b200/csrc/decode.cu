@@ -241,58 +241,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) argmax_warp_ring_kernel(Decode
 
 // Alternative without the TMA ring (kept for A/B measurements, EGL_DECODE_VARIANT=ldg): one CTA per
 // map, 256 threads, 8 independent 128-bit streaming loads in flight per thread.
-// torch.sigmoid for float on CUDA is 1 / (1 + expf(-x)) with the full-precision expf and an IEEE divide
-// (ATen sigmoid_kernel_cuda); evaluated the same way here so that arg-max over sigmoid(logits) -- with
-// its ties where the float sigmoid saturates or plateaus -- is bit-identical to sigmoid-then-decode.
-__device__ __forceinline__ float sigmoid_like_torch(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
-
-template <bool kSigmoid>
-__global__ void __launch_bounds__(256) argmax_ldg_kernel(DecodeArgs a) {
-    __shared__ float s_val[8];
-    __shared__ int s_idx[8];
+// Finish of a per-map arg-max: combine the per-thread (value, first index) pairs of a 256-thread CTA.
+__device__ __forceinline__ void block_argmax_store(float bv, int bi, DecodeArgs& a, long long map, float* s_val, int* s_idx) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long map = blockIdx.x;
-    const float4* src = a.hm + map * a.map_f4;
-    const int n = a.map_f4;
-    float bv = -INFINITY;
-    int bi = tid < n ? tid * 4 : 0x7fffffff;
-    bool bnan = false;
-    for (int i0 = tid; i0 < n; i0 += 256 * 8) {
-        float4 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + u * 256;
-            v[u] = i < n ? __ldcs(src + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        }
-        if (kSigmoid) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (i0 + u * 256 < n) {
-                    v[u].x = sigmoid_like_torch(v[u].x); v[u].y = sigmoid_like_torch(v[u].y);
-                    v[u].z = sigmoid_like_torch(v[u].z); v[u].w = sigmoid_like_torch(v[u].w);
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int base = (i0 + u * 256) * 4;
-            const float m = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
-            const float sum = (v[u].x + v[u].y) + (v[u].z + v[u].w);
-            if (sum != sum) {
-                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool take = !bnan && (e[j] > bv || e[j] != e[j]);
-                    if (take) { bv = e[j]; bi = base + j; bnan = e[j] != e[j]; }
-                }
-            } else {
-                const int j = v[u].x == m ? 0 : (v[u].y == m ? 1 : (v[u].z == m ? 2 : 3));
-                const bool upd = !bnan && m > bv;
-                bv = upd ? m : bv;
-                bi = upd ? base + j : bi;
-            }
-        }
-    }
     float v = bv;
     int ix = bi;
 #pragma unroll
@@ -314,6 +265,118 @@ __global__ void __launch_bounds__(256) argmax_ldg_kernel(DecodeArgs a) {
         }
         if (lane == 0) { a.kp_flat[map] = ix; a.kp_score[map] = v; }
     }
+}
+
+__global__ void __launch_bounds__(256) argmax_ldg_kernel(DecodeArgs a) {
+    __shared__ float s_val[8];
+    __shared__ int s_idx[8];
+    const int tid = threadIdx.x;
+    const long long map = blockIdx.x;
+    const float4* src = a.hm + map * a.map_f4;
+    const int n = a.map_f4;
+    float bv = -INFINITY;
+    int bi = tid < n ? tid * 4 : 0x7fffffff;
+    bool bnan = false;
+    for (int i0 = tid; i0 < n; i0 += 256 * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 256;
+            v[u] = i < n ? __ldcs(src + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int base = (i0 + u * 256) * 4;
+            const float m = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
+            const float sum = (v[u].x + v[u].y) + (v[u].z + v[u].w);
+            if (sum != sum) {
+                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool take = !bnan && (e[j] > bv || e[j] != e[j]);
+                    if (take) { bv = e[j]; bi = base + j; bnan = e[j] != e[j]; }
+                }
+            } else {
+                const int j = v[u].x == m ? 0 : (v[u].y == m ? 1 : (v[u].z == m ? 2 : 3));
+                const bool upd = !bnan && m > bv;
+                bv = upd ? m : bv;
+                bi = upd ? base + j : bi;
+            }
+        }
+    }
+    block_argmax_store(bv, bi, a, map, s_val, s_idx);
+}
+
+// torch.sigmoid for float on CUDA is 1 / (1 + expf(-x)) with the full-precision expf and an IEEE divide
+// (ATen sigmoid_kernel_cuda); evaluated the same way here so that arg-max over sigmoid(logits) -- with
+// its ties where the float sigmoid saturates or plateaus -- is bit-identical to sigmoid-then-decode.
+__device__ __forceinline__ float sigmoid_like_torch(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
+
+// Gate for the fused sigmoid arg-max: the largest logit g such that every logit below g has a float
+// sigmoid STRICTLY smaller than sigmoid(M), so that it cannot be the arg-max, not even as a tie.
+//   * the sigmoid is monotone; two logits share a float sigmoid only when they are closer than about one
+//     float spacing of the result mapped back through the derivative, 1.2e-7 * (1 + e^M) per ulp.  The
+//     margin used is 32 ulps of that (expf is good to 2 ulps, so computed values keep the strict order),
+//     and never less than a few ulps of M itself;
+//   * from logit ~16.6 upwards the float sigmoid is exactly 1.0 (everything up there ties), so the gate
+//     never rises above 16;
+//   * below logit -80 the sigmoid is denormal (coarser spacing, wider ties): no gating there.
+__device__ __forceinline__ float sigmoid_gate(float M) {
+    const float Mc = fminf(M, 80.f);
+    if (!(Mc > -80.f)) return -INFINITY;
+    const float margin = fmaxf(4e-6f * (1.f + expf(Mc)), 4e-7f * fabsf(Mc));
+    return fminf(Mc - margin, 16.f);
+}
+
+// F3: arg-max over sigmoid(logits) without evaluating the sigmoid everywhere.  A logit below
+// sigmoid_gate(largest logit seen so far by any lane of the warp) cannot reach the maximum sigmoid, not
+// even as a tie, so it is skipped after one compare; only logits at or near a new
+// maximum -- O(log n) events per map -- pay for expf and the divide.  Result is exactly
+// arg-max(torch.sigmoid(logits)) with first-index ties.
+__global__ void __launch_bounds__(256) argmax_logits_kernel(DecodeArgs a) {
+    __shared__ float s_val[8];
+    __shared__ int s_idx[8];
+    const int tid = threadIdx.x;
+    const long long map = blockIdx.x;
+    const float4* src = a.hm + map * a.map_f4;
+    const int n = a.map_f4;
+    float bv = -INFINITY;                    // best sigmoid value of this thread
+    int bi = tid < n ? tid * 4 : 0x7fffffff;
+    bool bnan = false;
+    float known = -INFINITY;                 // largest logit known to this warp
+    float gate = -INFINITY;                  // sigmoid_gate(known): logits below it are skipped
+    for (int i0 = tid; i0 < n; i0 += 256 * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 256;
+            v[u] = i < n ? __ldcs(src + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int base = (i0 + u * 256) * 4;
+            const float m = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
+            const float sum = (v[u].x + v[u].y) + (v[u].z + v[u].w);
+            if (m >= gate || sum != sum) {     // rare after the first few float4s
+                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (e[j] >= gate || e[j] != e[j]) {
+                        const float sg = sigmoid_like_torch(e[j]);
+                        const bool take = !bnan && (sg > bv || sg != sg);
+                        if (take) { bv = sg; bi = base + j; bnan = sg != sg; }
+                    }
+                }
+                if (m > known) { known = m; gate = sigmoid_gate(m); }
+            }
+        }
+        // share the largest logit across the warp so that every lane gates on it
+        float wk = known;
+#pragma unroll
+        for (int mm = 16; mm > 0; mm >>= 1) wk = fmaxf(wk, __shfl_xor_sync(kFull, wk, mm));
+        if (wk > known) { known = wk; gate = sigmoid_gate(wk); }
+    }
+    block_argmax_store(bv, bi, a, map, s_val, s_idx);
 }
 
 // Keypoint post-processing, one warp per frame (the sequential statement of the same rules is
@@ -466,8 +529,8 @@ static int decode_impl(const float* hm, int F, int hm_h, int hm_w, int img_w, in
         case 11: rc = launch_ring(argmax_kernel<3, 128, 4>, 3, 128, 4, 2); break;         // 4 CTAs/SM, 3 x 16 KB each
         case 0: rc = launch_ring(argmax_kernel<6, 512, 1>, 6, 512, 1, 1); break;    // 6 x 32 KB, 1 CTA/SM
         default:  // register streaming
-            if (from_logits) argmax_ldg_kernel<true><<<(unsigned)a.total_maps, 256, 0, s>>>(a);
-            else argmax_ldg_kernel<false><<<(unsigned)a.total_maps, 256, 0, s>>>(a);
+            if (from_logits) argmax_logits_kernel<<<(unsigned)a.total_maps, 256, 0, s>>>(a);
+            else argmax_ldg_kernel<<<(unsigned)a.total_maps, 256, 0, s>>>(a);
             break;
     }
     if (rc) return rc;

@@ -432,6 +432,13 @@ def test_decode_from_logits_equals_sigmoid_then_decode(engine):
     logits[2] = logits[2].clamp(max=-6.0)           # everything below the 0.01 score cut
     logits[3, 5] = 40.0                             # whole map saturated -> index 0
     logits[4, :, 134, 239] = 9.0
+    logits[5, 0] = -95.0; logits[5, 0, 70, 70] = -94.99999       # denormal sigmoid range: wide ties
+    logits[5, 1] = -200.0                                         # sigmoid underflows to 0 everywhere -> index 0
+    logits[5, 2, 100, 5] = 30.0; logits[5, 2, 120, 7] = float("inf")   # saturated finite logit BEFORE a +inf: first one wins
+    logits[5, 3, 3, 3] = float("inf"); logits[5, 3, 100, 100] = 20.0   # +inf first
+    logits[5, 4] = float("-inf")                                  # all -inf
+    logits[5, 5, 60:70, 60:70] = 10.0 + torch.arange(100, device="cuda").view(10, 10) * 1e-5   # dense near-ties around logit 10
+    logits[5, 6, 20, 20] = float("nan"); logits[5, 6, 90, 90] = 50.0   # NaN beats everything (np.argmax rule)
     hm = torch.sigmoid(logits)
     a = engine.decode(hm, 1920, 1080)
     b = engine.decode(logits, 1920, 1080, from_logits=True)
