@@ -436,47 +436,49 @@ constexpr int kRefitWarps = 4;
 struct RefitShared {
     PointList pl;
     double A[81];
-    double aug[10 * 11];
+    double aug[9 * 10];
     double vec[12];
+    double xs[9], rs[9], ds[9];  // parameter vector / right-hand side / LM scaling staged for lane-indexed access
 };
 
-// Row-parallel Gaussian elimination with partial pivoting on the augmented n x (n+1) system in
-// shared memory (row stride S); lanes 0..n-1 own rows.  Result x[0..n) in shared memory.  All 32
-// lanes must call.  Returns false on a zero / non-finite pivot (uniform across the warp).
-template <int n, int S>
-__device__ bool warp_gauss_solve(double* aug, double* x) {
+// Gauss-Jordan elimination of a symmetric POSITIVE DEFINITE 9x9 system held as an augmented 9x10 array
+// in shared memory, all 32 lanes working: lane l owns elements l, l+32, l+64 of the 90; step k scales by
+// the k-th pivot and clears column k in every other row.  No pivoting is needed for SPD matrices, so
+// there is no search and no row swap; one warp synchronisation per step.  Every system of the refit is
+// SPD: the shifted normal matrix of the inverse iteration, the damped LM matrix A + lambda*diag(A), and
+// the undamped, gauge-singular LM matrix made definite by the rank-one term c * xhat xhat^T (x = the
+// current parameter vector is exactly the null vector of A, so (A + c xhat xhat^T)^-1 v = A^+ v for the
+// v orthogonal to x that occur here -- the same minimum-norm step cv2's eigen back-substitution takes).
+// Returns false (uniformly) if a pivot is not positive and finite.  x[0..9) in shared memory.
+__device__ bool warp_spd_solve9(double* aug, double* x) {
+    constexpr int n = 9, S = 10;
     const int lane = threadIdx.x & 31;
-    for (int k = 0; k < n; ++k) {
-        // pivot: largest |aug[r][k]|, r >= k, lowest row on ties
-        double best = (lane >= k && lane < n) ? fabs(aug[lane * S + k]) : -1.0;
-        int piv = lane;
+    int er[3], ej[3];
 #pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-            const double ob = shfl_xor_f64(best, m);
-            const int op = __shfl_xor_sync(kFull, piv, m);
-            if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
-        }
-        if (!(best > 0.0) || !isfinite(best)) return false;
-        if (piv != k && lane <= n) {  // lanes are columns for the swap
-            const double t = aug[k * S + lane];
-            aug[k * S + lane] = aug[piv * S + lane];
-            aug[piv * S + lane] = t;
+    for (int q = 0; q < 3; ++q) {
+        const int e = lane + 32 * q;
+        er[q] = e < n * S ? e / S : -1;
+        ej[q] = e % S;
+    }
+    for (int k = 0; k < n; ++k) {
+        const double piv = aug[k * S + k];
+        if (!(piv > 0.0) || !isfinite(piv)) return false;
+        const double inv = 1.0 / piv;
+        double nv[3];
+        bool upd[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            upd[q] = er[q] >= 0 && er[q] != k && ej[q] > k;
+            if (upd[q]) nv[q] = aug[er[q] * S + ej[q]] - (aug[er[q] * S + k] * inv) * aug[k * S + ej[q]];
         }
         __syncwarp();
-        if (lane > k && lane < n) {
-            const double m = aug[lane * S + k] * (1.0 / aug[k * S + k]);
-            if (m != 0.0)
-                for (int j = k + 1; j <= n; ++j) aug[lane * S + j] -= m * aug[k * S + j];
-        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (upd[q]) aug[er[q] * S + ej[q]] = nv[q];
         __syncwarp();
     }
-    for (int i = n - 1; i >= 0; --i) {  // column-oriented back substitution
-        const double xi = aug[i * S + n] / aug[i * S + i];
-        __syncwarp();
-        if (lane < i) aug[lane * S + n] -= aug[lane * S + i] * xi;
-        if (lane == 0) x[i] = xi;
-        __syncwarp();
-    }
+    if (lane < n) x[lane] = aug[lane * S + n] / aug[lane * S + lane];
+    __syncwarp();
     return true;
 }
 
@@ -582,7 +584,7 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
                 }
                 if (lane < 9) sh.aug[lane * 10 + 9] = y_l;
                 __syncwarp();
-                if (!warp_gauss_solve<9, 10>(sh.aug, sh.vec)) { have_ls = false; break; }
+                if (!warp_spd_solve9(sh.aug, sh.vec)) { have_ls = false; break; }
                 double z = lane < 9 ? sh.vec[lane] : 0.0;
                 const double nrm = warp_sum_f64(z * z);
                 // sign: component of largest magnitude positive (lowest index on ties)
@@ -664,39 +666,48 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
                 }
             return warp_sum_f64(s);
         };
-        // gauge-fixed solve A d = rhs with null vector x (bordered 10x10), result in sh.vec
+        // stage a 9-vector held (replicated) in registers into shared memory; static register indices only
+        auto stage = [&](double* dst, const double* src) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i)
+                if (lane == i) dst[i] = src[i];
+            __syncwarp();
+        };
+        // gauge-fixed solve A d = rhs (A singular along x): (A + c xhat xhat^T) d = rhs, result in sh.vec
         auto solve_gauge = [&](const double* rhs) -> bool {
             double xn = 0, dmx = 0;
 #pragma unroll
             for (int i = 0; i < 9; ++i) { xn += x[i] * x[i]; dmx = fmax(dmx, fabs(sh.A[i * 9 + i])); }
             if (!(xn > 0.0) || !(dmx > 0.0)) return false;
-            const double sc = dmx / sqrt(xn);
-            for (int t = lane; t < 81; t += 32) sh.aug[(t / 9) * 11 + (t % 9)] = sh.A[t];
-            if (lane < 9) {
-                sh.aug[lane * 11 + 9] = sc * x[lane];
-                sh.aug[lane * 11 + 10] = rhs[lane];
-                sh.aug[9 * 11 + lane] = sc * x[lane];
+            const double cc = dmx / xn;  // c / |x|^2
+            stage(sh.xs, x);
+            stage(sh.rs, rhs);
+            for (int t = lane; t < 81; t += 32) {
+                const int r = t / 9, c = t % 9;
+                sh.aug[r * 10 + c] = sh.A[t] + cc * sh.xs[r] * sh.xs[c];
             }
-            if (lane == 0) { sh.aug[9 * 11 + 9] = 0.0; sh.aug[9 * 11 + 10] = 0.0; }
+            if (lane < 9) sh.aug[lane * 10 + 9] = sh.rs[lane];
             __syncwarp();
-            return warp_gauss_solve<10, 11>(sh.aug, sh.vec);
+            return warp_spd_solve9(sh.aug, sh.vec);
         };
         linearise(x);
 #pragma unroll
         for (int i = 0; i < 9; ++i) D[i] = sh.A[i * 9 + i];
+        stage(sh.ds, D);
         const double Rlo = 0.25, Rhi = 0.75;
         double lambda = 1, lc = 0.75;
         int iter = 0;
         for (;;) {
             bool ok;
             if (lambda > 0) {
+                stage(sh.rs, v);
                 for (int t = lane; t < 81; t += 32) {
                     const int r = t / 9, c = t % 9;
-                    sh.aug[r * 10 + c] = sh.A[t] + (r == c ? lambda * D[r] : 0.0);
+                    sh.aug[r * 10 + c] = sh.A[t] + (r == c ? lambda * sh.ds[r] : 0.0);
                 }
-                if (lane < 9) sh.aug[lane * 10 + 9] = v[lane];
+                if (lane < 9) sh.aug[lane * 10 + 9] = sh.rs[lane];
                 __syncwarp();
-                ok = warp_gauss_solve<9, 10>(sh.aug, sh.vec);
+                ok = warp_spd_solve9(sh.aug, sh.vec);
             } else {
                 ok = solve_gauge(v);
             }
@@ -764,7 +775,9 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
             pm |= (uint64_t)__ballot_sync(kFull, in) << (32 * pass);
         }
         count = __popcll(pm);
-        if (lane < 9) a.H[(size_t)f * 9 + lane] = H[lane < 9 ? lane : 0];
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            if (lane == i) a.H[(size_t)f * 9 + i] = H[i];
     }
     // position bits -> channel bits
     uint64_t cm = 0;
