@@ -447,3 +447,31 @@ def test_decode_from_logits_equals_sigmoid_then_decode(engine):
     assert torch.equal(a.order, b.order) and torch.equal(a.count, b.count) and torch.equal(a.xy, b.xy)
     assert int(a.flat[3, 5]) == 0 and float(a.score[3, 5]) == 1.0
     assert int(b.flat[5, 2]) == 100 * 240 + 5 and int(b.flat[5, 6]) == 20 * 240 + 20 and int(b.flat[5, 4]) == 0
+
+
+def test_empty_and_ragged_inputs(engine):
+    """F = 0 everywhere; frames with zero objects, one class missing, and more objects than usual."""
+    from eagle_b200.coordinate_model import CoordinateModel, GeometryPath
+    from eagle_b200 import synthetic
+    from oracle import pipeline
+    # F = 0 through every entry point
+    kp = engine.decode(torch.empty((0, 57, 135, 240), device="cuda"), 1920, 1080)
+    assert kp.n_frames == 0
+    engine.synthesize(kp)
+    fit = engine.fit(kp)
+    assert fit.H.shape == (0, 9)
+    pr = engine.project(fit.H, torch.empty((0, 1, 2), device="cuda"), torch.empty(0, dtype=torch.int32, device="cuda"), 1920, 1080)
+    assert pr.coords.shape == (0, 1, 2)
+    assert engine.preprocess(torch.empty((0, 720, 1280, 3), dtype=torch.uint8, device="cuda")).shape == (0, 3, 540, 960)
+    assert CoordinateModel(keypoint_model=lambda x: x, detect_objects=lambda f: {}).get_coordinates([], fps=25) == {}
+    # ragged object lists
+    clip = synthetic.make_clip(5, 1280, 720, seed=13, ghost_prob=0.05)
+    objs = clip["objects"]
+    objs[0] = {"Player": {}, "Goalkeeper": {}}                              # nothing detected
+    objs[1] = {"Player": objs[1]["Player"], "Goalkeeper": {}}               # no goalkeeper, no "Ball" key
+    extra = {100 + k: {"BBox": [10 * k, 20, 10 * k + 30, 200 + k], "Confidence": 0.5, "Bottom_center": [10 * k + 15, 200 + k]}
+             for k in range(30)}
+    objs[2] = {"Player": {**objs[2]["Player"], **extra}, "Goalkeeper": objs[2]["Goalkeeper"], "Ball": {}}   # 50+ objects, empty Ball dict
+    want = pipeline.get_coordinates(clip["heatmaps"], objs, 1280, 720)
+    got = GeometryPath("cuda:0").run(torch.from_numpy(clip["heatmaps"]).cuda(), objs, 1280, 720, fps=1)
+    assert json.dumps(got, default=float, sort_keys=True) == json.dumps(want, default=float, sort_keys=True)
