@@ -467,6 +467,7 @@ using namespace egl;
 static int decode_impl(const float* hm, int F, int hm_h, int hm_w, int img_w, int img_h, double keypoint_conf,
                        int32_t* kp_flat, float* kp_score, int32_t* kp_xy, uint8_t* kp_order, int32_t* kp_count, void* stream,
                        bool from_logits) {
+    if (F == 0) return 0;  // empty batch: nothing to enqueue, pointers may be null
     EGL_REQUIRE(hm && kp_flat && kp_score && kp_xy && kp_order && kp_count, EGL_ERR_NULL, "egl_decode_heatmaps: null pointer");
     EGL_REQUIRE(F >= 0 && hm_h > 0 && hm_w > 0 && img_w > 0 && img_h > 0, EGL_ERR_SHAPE, "egl_decode_heatmaps: bad shape");
     EGL_REQUIRE(((long long)hm_h * hm_w) % 4 == 0, EGL_ERR_SHAPE,

@@ -800,6 +800,7 @@ extern "C" int egl_fit_homography(const int32_t* kp_xy, const uint8_t* kp_order,
                                   int K, const uint8_t* hyp, uint64_t seed, double thr, double confidence, double* H,
                                   uint64_t* used_mask, uint64_t* inlier_mask, int32_t* status, int32_t* info,
                                   void* stream) {
+    if (F == 0) return 0;  // empty batch: nothing to enqueue, pointers may be null
     EGL_REQUIRE(kp_xy && kp_order && kp_count && H && used_mask && inlier_mask && status && info, EGL_ERR_NULL,
                 "egl_fit_homography: null pointer");
     EGL_REQUIRE(F >= 0 && K >= 1, EGL_ERR_SHAPE, "egl_fit_homography: need F >= 0 and K >= 1 (F=%d K=%d)", F, K);

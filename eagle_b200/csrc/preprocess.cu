@@ -139,6 +139,7 @@ using namespace egl;
 
 extern "C" int egl_preprocess_u8(const uint8_t* frames, int F, int H, int W, size_t row_stride, size_t frame_stride,
                                  float* out, void* stream) {
+    if (F == 0) return 0;  // empty batch: nothing to enqueue, pointers may be null
     EGL_REQUIRE(frames && out, EGL_ERR_NULL, "egl_preprocess_u8: null pointer");
     EGL_REQUIRE(F >= 0 && H >= 2 && W >= 2, EGL_ERR_SHAPE, "egl_preprocess_u8: bad shape %dx%d", H, W);
     EGL_REQUIRE(row_stride >= (size_t)3 * W && frame_stride >= row_stride * (size_t)H, EGL_ERR_SHAPE,

@@ -120,6 +120,7 @@ using namespace egl;
 
 extern "C" int egl_select_homography(const int32_t* status, int F, int interval, int carry_in, int32_t* h_index,
                                      uint8_t* attempted, void* stream) {
+    if (F == 0) return 0;  // empty batch: nothing to enqueue, pointers may be null
     EGL_REQUIRE(status && h_index && attempted, EGL_ERR_NULL, "egl_select_homography: null pointer");
     EGL_REQUIRE(F >= 0 && interval >= 1, EGL_ERR_SHAPE, "egl_select_homography: bad arguments");
     if (F == 0) return 0;
@@ -130,6 +131,7 @@ extern "C" int egl_select_homography(const int32_t* status, int F, int interval,
 extern "C" int egl_project_points(const double* H, const int32_t* h_index, const float* pts, const int32_t* npts, int F, int P,
                                   int img_w, int img_h, float* out_f, int64_t* out_i, uint8_t* inb, double* bounds,
                                   void* stream) {
+    if (F == 0) return 0;  // empty batch: nothing to enqueue, pointers may be null
     EGL_REQUIRE(H && pts && npts && out_f && out_i && inb && bounds, EGL_ERR_NULL, "egl_project_points: null pointer");
     EGL_REQUIRE(F >= 0 && P >= 0 && img_w > 0 && img_h > 0, EGL_ERR_SHAPE, "egl_project_points: bad shape");
     if (F == 0) return 0;

@@ -38,6 +38,7 @@ using namespace egl;
 
 extern "C" int egl_synthesize_keypoints(int32_t* kp_xy, uint8_t* kp_order, int32_t* kp_count, int F, int max_new,
                                         void* stream) {
+    if (F == 0) return 0;  // empty batch: nothing to enqueue, pointers may be null
     EGL_REQUIRE(kp_xy && kp_order && kp_count, EGL_ERR_NULL, "egl_synthesize_keypoints: null pointer");
     EGL_REQUIRE(F >= 0 && max_new >= 0, EGL_ERR_SHAPE, "egl_synthesize_keypoints: bad arguments");
     if (F == 0 || max_new == 0) return 0;
