@@ -168,6 +168,8 @@ class CoordinateModel:
     def get_coordinates(self, frames, fps: int, num_homography: int = 1, num_keypoint_detection: int = 1,
                         verbose: bool = True, calibration: bool = False) -> dict:
         """coordinate_model.py:188-417."""
+        if len(frames) == 0:
+            return {}
         homography_interval = max(1, int(fps / max(1, num_homography)))
         keypoint_interval = max(1, int(fps / max(1, num_keypoint_detection)))
         if keypoint_interval != 1:
@@ -175,9 +177,6 @@ class CoordinateModel:
                                       "(coordinate_model.py:419-478), which is outside the accelerated path")
         if calibration:
             raise NotImplementedError("brightness calibration (coordinate_model.py:520-555) is outside the accelerated path")
-        res = {}
-        if len(frames) == 0:
-            return res
         height, width = frames[0].shape[:2]
         # cadence state crosses chunk boundaries through carry_in; chunks keep memory bounded
         all_obj = [self.detect_objects(f) for f in frames]
