@@ -45,7 +45,13 @@ __device__ __forceinline__ void axis_tap(int d, double scale, int* ofs, int* c0,
 // mbarrier, one bulk copy per distinct row: when the vertical scale is < 2 neighbouring output rows
 // share a source row, which is then fetched once and aliased), so a CTA keeps up to 2R rows in
 // flight and the per-CTA fixed costs (launch, barrier set-up, tap arithmetic) are amortised R-fold.
-template <int R>
+//
+// kMean4: when the frame is an even integer multiple s of 960x540 (1080p: s = 2, 4K: s = 4) both taps of
+// both passes weigh exactly 1024/2048, the fixed-point recipe collapses to the rounded mean of four source
+// pixels, (S[y0][x0] + S[y0][x0+1] + S[y0+1][x0] + S[y0+1][x0+1] + 2) >> 2 with x0 = (s/2)(2dx+1) - 1 (the same
+// value, bit for bit -- it is also OpenCV's own INTER_AREA shortcut at s = 2), at a third of the
+// integer instructions; `half_scale` = s/2 is passed in scale_x's place.
+template <int R, bool kMean4>
 __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* __restrict__ frames, int H, int W,
                                                                  size_t row_stride, size_t frame_stride, double scale_x,
                                                                  double scale_y, int use_bulk, float* __restrict__ out) {
@@ -65,7 +71,12 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* 
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         int sy;
-        axis_tap(dy0 + r, scale_y, &sy, &b0[r], &b1[r]);
+        if (kMean4) {
+            sy = (int)scale_y * (2 * (dy0 + r) + 1) - 1;
+            b0[r] = b1[r] = 1024;
+        } else {
+            axis_tap(dy0 + r, scale_y, &sy, &b0[r], &b1[r]);
+        }
         ysrc[2 * r] = min(max(sy, 0), H - 1);  // rows clamp, weights do not
         ysrc[2 * r + 1] = min(max(sy + 1, 0), H - 1);
     }
@@ -100,7 +111,12 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         int s, c0, c1;
-        axis_tap(tid + kPreThreads * k, scale_x, &s, &c0, &c1);
+        if (kMean4) {
+            s = (int)scale_x * (2 * (tid + kPreThreads * k) + 1) - 1;
+            c0 = c1 = 1024;
+        } else {
+            axis_tap(tid + kPreThreads * k, scale_x, &s, &c0, &c1);
+        }
         if (s < 0) { s = 0; c0 = 2048; c1 = 0; }
         if (s >= W - 1) { s = W - 1; c0 = 2048; c1 = 0; }
         xo[k] = 3 * s;
@@ -122,10 +138,15 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* 
         for (int k = 0; k < 4; ++k) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {  // c indexes the SOURCE byte (B,G,R); plane = 2 - c (RGB)
-                const int top = (int)r0[xo[k] + c] * a0[k] + (int)r0[xo1[k] + c] * a1[k];
-                const int bot = (int)r1[xo[k] + c] * a0[k] + (int)r1[xo1[k] + c] * a1[k];
-                int v = (((b0[r] * (top >> 4)) >> 16) + ((b1[r] * (bot >> 4)) >> 16) + 2) >> 2;
-                v = min(max(v, 0), 255);
+                int v;
+                if (kMean4) {
+                    v = ((int)r0[xo[k] + c] + (int)r0[xo[k] + 3 + c] + (int)r1[xo[k] + c] + (int)r1[xo[k] + 3 + c] + 2) >> 2;
+                } else {
+                    const int top = (int)r0[xo[k] + c] * a0[k] + (int)r0[xo1[k] + c] * a1[k];
+                    const int bot = (int)r1[xo[k] + c] * a0[k] + (int)r1[xo1[k] + c] * a1[k];
+                    v = (((b0[r] * (top >> 4)) >> 16) + ((b1[r] * (bot >> 4)) >> 16) + 2) >> 2;
+                    v = min(max(v, 0), 255);
+                }
                 const int plane = 2 - c;
                 __stcs(dst + (size_t)plane * kOutH * kOutW + kPreThreads * k, __fmul_rn(__fsub_rn((float)v, mean[plane]), den[plane]));
             }
@@ -155,10 +176,17 @@ extern "C" int egl_preprocess_u8(const uint8_t* frames, int F, int H, int W, siz
     // OpenCV: inv_scale = dsize/ssize (double); scale = 1./inv_scale
     const double scale_x = 1. / ((double)kOutW / (double)W);
     const double scale_y = 1. / ((double)kOutH / (double)H);
-    // output rows per CTA: as many as keep >= 2 CTAs' worth of row slots within shared memory
+    // even integer multiple of the output size -> rounded mean of four (see kMean4)
+    static const char* mean4_env = getenv("EGL_PREPROCESS_MEAN4");  // measurement switch: 0 forces the general recipe
+    const bool mean4 = (W % kOutW == 0) && (H % kOutH == 0) && (W / kOutW == H / kOutH) && ((W / kOutW) % 2 == 0) &&
+                       !(mean4_env && atoi(mean4_env) == 0);
+    const double arg_x = mean4 ? (double)(W / kOutW / 2) : scale_x, arg_y = mean4 ? (double)(H / kOutH / 2) : scale_y;
+    // output rows per CTA: 4 unless the row slots of a CTA would exceed ~100 KB of shared memory
     static const char* rows_env = getenv("EGL_PREPROCESS_ROWS");
     int R = rows_env ? atoi(rows_env) : 4;
-    while (R > 1 && (size_t)2 * R * row_pad > 100 * 1024) R >>= 1;
+    if (R != 1 && R != 2 && R != 3 && R != 4 && R != 6) R = 4;
+    if (mean4 && R == 3) R = 2;
+    while (R > 1 && (size_t)2 * R * row_pad > 100 * 1024) R = (R == 6) ? 4 : (R == 3 ? 2 : R / 2);
     const size_t smem = (size_t)2 * R * row_pad;
     EGL_REQUIRE(smem <= 200 * 1024, EGL_ERR_SHAPE, "egl_preprocess_u8: frame too wide (%d px)", W);
     cudaStream_t st = (cudaStream_t)stream;
@@ -168,18 +196,26 @@ extern "C" int egl_preprocess_u8(const uint8_t* frames, int F, int H, int W, siz
                                  "egl_preprocess_u8: cudaFuncSetAttribute");
             if (rc) return rc;
         }
-        kernel<<<(unsigned)(F * (kOutH / rows)), kPreThreads, smem, st>>>(frames, H, W, row_stride, frame_stride, scale_x, scale_y,
+        kernel<<<(unsigned)(F * (kOutH / rows)), kPreThreads, smem, st>>>(frames, H, W, row_stride, frame_stride, arg_x, arg_y,
                                                                          use_bulk, out);
         return 0;
     };
     int rc;
-    switch (R) {
-        case 1: rc = launch(preprocess_kernel<1>, 1); break;
-        case 2: rc = launch(preprocess_kernel<2>, 2); break;
-        case 3: rc = launch(preprocess_kernel<3>, 3); break;
-        case 4: rc = launch(preprocess_kernel<4>, 4); break;
-        case 6: rc = launch(preprocess_kernel<6>, 6); break;
-        default: rc = launch(preprocess_kernel<2>, 2); break;
+    if (mean4) {
+        switch (R) {
+            case 1: rc = launch(preprocess_kernel<1, true>, 1); break;
+            case 2: rc = launch(preprocess_kernel<2, true>, 2); break;
+            case 6: rc = launch(preprocess_kernel<6, true>, 6); break;
+            default: rc = launch(preprocess_kernel<4, true>, 4); break;
+        }
+    } else {
+        switch (R) {
+            case 1: rc = launch(preprocess_kernel<1, false>, 1); break;
+            case 2: rc = launch(preprocess_kernel<2, false>, 2); break;
+            case 3: rc = launch(preprocess_kernel<3, false>, 3); break;
+            case 6: rc = launch(preprocess_kernel<6, false>, 6); break;
+            default: rc = launch(preprocess_kernel<4, false>, 4); break;
+        }
     }
     if (rc) return rc;
     return cuda_status(cudaGetLastError(), "egl_preprocess_u8: kernel launch");

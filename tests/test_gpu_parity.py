@@ -241,7 +241,7 @@ def test_empty_and_degenerate_frames(engine):
 # ------------------------------------------------------------------------------------------------
 # K1 preprocess
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("w,h", [(1280, 720), (1920, 1080), (3840, 2160), (854, 480), (1366, 768)])
+@pytest.mark.parametrize("w,h", [(1280, 720), (1920, 1080), (3840, 2160), (854, 480), (1366, 768), (2880, 1620), (5760, 3240), (960, 540)])
 def test_preprocess_matches_reference_calls(engine, w, h):
     from oracle import preprocess
     fr = np.random.default_rng(w).integers(0, 256, (2, h, w, 3), dtype=np.uint8)
