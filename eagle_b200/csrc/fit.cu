@@ -144,38 +144,68 @@ __global__ void __launch_bounds__(kCv2Warps * 32) ransac_cv2_kernel(FitArgs a) {
 
     CvRng rng{~0ull};
     int niters = max(a.K, 1), iter = 0, best = 0, best_idx = -1;
+    int rejected = 0;  // consecutive rejected samples: OpenCV's getSubset gives up after 10000 per iteration
     bool exhausted = false;
     while (iter < niters && !exhausted) {
-        // every lane replays the same RNG walk; lane b keeps the b-th accepted sample
-        int B = min(32, niters - iter);
+        // ---- fill up to 32 hypothesis slots (lane s = slot s) with the next accepted samples --------
+        // The RNG stream fixes the sequence of candidate samples; whether a candidate passes checkSubset
+        // does not feed back into the stream.  So every lane replays the (cheap) RNG walk for a group of
+        // 32 candidates, lane j keeps candidate j and tests it -- the expensive part, now in parallel --
+        // and a ballot compacts the accepted ones, in stream order, into the slots.  The stream is then
+        // rewound to just after the last candidate actually consumed.
+        const int B = min(32, niters - iter);
+        int filled = 0;
         int my[4] = {0, 0, 0, 0};
-        for (int b = 0; b < B; ++b) {
-            int idx[4];
-            bool found = false;
-            for (int attempt = 0; attempt < 10000 && !found; ++attempt) {
+        while (filled < B && !exhausted) {
+            int cand[4] = {0, 0, 0, 0};
+            uint64_t st_after = 0;
+            for (int j = 0; j < 32; ++j) {
+                int idx[4];
                 draw_subset(rng, N, idx);
-                float qx[4], qy[4], rx[4], ry[4];
+                if (lane == j) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    qx[k] = pl.sx[idx[k]]; qy[k] = pl.sy[idx[k]];
-                    rx[k] = pl.dx[idx[k]]; ry[k] = pl.dy[idx[k]];
+                    for (int k = 0; k < 4; ++k) cand[k] = idx[k];
+                    st_after = rng.state;
                 }
-                found = check_subset(qx, qy, rx, ry);
             }
-            if (!found) {  // getSubset failed: iter 0 -> no model at all, otherwise stop here
-                B = b;
-                exhausted = true;
-                break;
-            }
-            if (lane == b) {
+            float qx[4], qy[4], rx[4], ry[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) my[k] = idx[k];
+            for (int k = 0; k < 4; ++k) {
+                qx[k] = pl.sx[cand[k]]; qy[k] = pl.sy[cand[k]];
+                rx[k] = pl.dx[cand[k]]; ry[k] = pl.dy[cand[k]];
+            }
+            unsigned bal = __ballot_sync(kFull, check_subset(qx, qy, rx, ry));
+            const int legit = min(32, 10000 - rejected);       // attempts OpenCV would still make
+            if (legit < 32) bal &= (1u << legit) - 1u;
+            const int acc = __popc(bal);
+            const int take = min(acc, B - filled);
+            // slot (filled + r) <- the r-th accepted candidate of this group
+            const int r = lane - filled;
+            const int src = (r >= 0 && r < take) ? (int)__fns(bal, 0, r + 1) : lane;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int v = __shfl_sync(kFull, cand[k], src);
+                if (r >= 0 && r < take) my[k] = v;
+            }
+            filled += take;
+            int last = 31;                                      // last candidate examined
+            if (filled == B && take > 0) last = (int)__fns(bal, 0, take);
+            else if (acc == 0 && legit < 32) last = legit - 1;
+            rng.state = (uint64_t)__shfl_sync(kFull, (unsigned)(st_after >> 32), last) << 32 |
+                        (uint64_t)__shfl_sync(kFull, (unsigned)st_after, last);
+            if (acc == 0) {
+                rejected += legit;
+                if (rejected >= 10000) exhausted = true;        // getSubset failed for iteration iter + filled
+            } else {
+                // rejected samples after the last accepted one examined so far
+                rejected = last - (31 - __clz(bal & (last == 31 ? 0xffffffffu : ((2u << last) - 1u))));
             }
         }
-        // one hypothesis per lane
+        const int Bf = filled;  // hypotheses actually available (== B unless the sampler gave up)
+        // ---- one hypothesis per lane -------------------------------------------------------------------
         int cnt = 0;
         double Hm[9];
-        if (lane < B) {
+        if (lane < Bf) {
             float qx[4], qy[4], rx[4], ry[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -192,7 +222,7 @@ __global__ void __launch_bounds__(kCv2Warps * 32) ransac_cv2_kernel(FitArgs a) {
         // OpenCV's sequential rule over the batch: accept iff strictly better (and >= 4 inliers),
         // then shrink niters; hypotheses at or beyond the new niters were never evaluated by cv2.
         int winner = -1, done = 0;
-        for (int b = 0; b < B; ++b) {
+        for (int b = 0; b < Bf; ++b) {
             if (iter + b >= niters) break;
             const int c = __shfl_sync(kFull, cnt, b);
             ++done;
@@ -208,7 +238,7 @@ __global__ void __launch_bounds__(kCv2Warps * 32) ransac_cv2_kernel(FitArgs a) {
             for (int k = 0; k < 9; ++k) H[k] = shfl_f64(Hm[k], winner);
         }
         iter += done;
-        if (done < B) break;
+        if (done < Bf) break;
     }
     if (lane == 0) {
         if (best == 0) {

@@ -316,14 +316,21 @@ EGL_HD_NOINLINE bool run_kernel_ls(const float* sx, const float* sy, const float
 }
 
 // Minimal 4-point solve in double (the model cv2 evaluates per RANSAC iteration).  Same
-// normalisation as runKernel, but the 8x8 system with h33 = 1 in normalised coordinates is solved
-// by elimination instead of a 9x9 eigen-decomposition: identical up to ~1e-13 relative, far below
-// the float cast OpenCV applies before scoring.
-EGL_HD_NOINLINE bool dlt4_f64(const float* sx, const float* sy, const float* dx, const float* dy, double* H) {
+// normalisation as runKernel; the 8x8 system with h33 = 1 in normalised coordinates is solved by
+// block elimination in registers (left null vector of [X Y 1] -> 2x2 system for h31, h32 -> Cramer
+// for the rest) instead of cv2's 9x9 eigen-decomposition: identical up to ~1e-13 relative, far
+// below the float cast OpenCV applies before scoring.
+EGL_HD double det3_f64(double Xa, double Ya, double Xb, double Yb, double Xc, double Yc) {
+    return Xa * (Yb - Yc) - Ya * (Xb - Xc) + (Xb * Yc - Xc * Yb);
+}
+
+EGL_HD bool dlt4_f64(const float* sx, const float* sy, const float* dx, const float* dy, double* H) {
     double cMx = 0, cMy = 0, cmx = 0, cmy = 0;
+EGL_UNROLL
     for (int i = 0; i < 4; ++i) { cmx += dx[i]; cmy += dy[i]; cMx += sx[i]; cMy += sy[i]; }
     cmx /= 4; cmy /= 4; cMx /= 4; cMy /= 4;
     double smx = 0, smy = 0, sMx = 0, sMy = 0;
+EGL_UNROLL
     for (int i = 0; i < 4; ++i) {
         smx += fabs(dx[i] - cmx); smy += fabs(dy[i] - cmy);
         sMx += fabs(sx[i] - cMx); sMy += fabs(sy[i] - cMy);
@@ -331,23 +338,60 @@ EGL_HD_NOINLINE bool dlt4_f64(const float* sx, const float* sy, const float* dx,
     if (fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON)
         return false;
     smx = 4 / smx; smy = 4 / smy; sMx = 4 / sMx; sMy = 4 / sMy;
-    double a[8 * 9];
+    double X[4], Y[4], x[4], y[4];
+EGL_UNROLL
     for (int i = 0; i < 4; ++i) {
-        const double x = (dx[i] - cmx) * smx, y = (dy[i] - cmy) * smy;
-        const double X = (sx[i] - cMx) * sMx, Y = (sy[i] - cMy) * sMy;
-        double* r0 = a + (2 * i) * 9;
-        double* r1 = a + (2 * i + 1) * 9;
-        r0[0] = X; r0[1] = Y; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0; r0[6] = -x * X; r0[7] = -x * Y; r0[8] = x;
-        r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = X; r1[4] = Y; r1[5] = 1; r1[6] = -y * X; r1[7] = -y * Y; r1[8] = y;
+        x[i] = (dx[i] - cmx) * smx; y[i] = (dy[i] - cmy) * smy;
+        X[i] = (sx[i] - cMx) * sMx; Y[i] = (sy[i] - cMy) * sMy;
     }
+    double n[4] = {det3_f64(X[1], Y[1], X[2], Y[2], X[3], Y[3]), -det3_f64(X[0], Y[0], X[2], Y[2], X[3], Y[3]),
+                   det3_f64(X[0], Y[0], X[1], Y[1], X[3], Y[3]), -det3_f64(X[0], Y[0], X[1], Y[1], X[2], Y[2])};
+EGL_UNROLL
+    for (int k = 0; k < 3; ++k) {  // the row with the largest |n| goes to slot 3: rows 0..2 then have the largest 3x3 determinant
+        const bool sw = fabs(n[k]) > fabs(n[3]);
+        double t;
+        t = n[3]; n[3] = sw ? n[k] : t; n[k] = sw ? t : n[k];
+        t = X[3]; X[3] = sw ? X[k] : t; X[k] = sw ? t : X[k];
+        t = Y[3]; Y[3] = sw ? Y[k] : t; Y[k] = sw ? t : Y[k];
+        t = x[3]; x[3] = sw ? x[k] : t; x[k] = sw ? t : x[k];
+        t = y[3]; y[3] = sw ? y[k] : t; y[k] = sw ? t : y[k];
+    }
+    double a11 = 0, a12 = 0, a21 = 0, a22 = 0, b1 = 0, b2 = 0;
+EGL_UNROLL
+    for (int k = 0; k < 4; ++k) {
+        const double nx = n[k] * x[k], ny = n[k] * y[k];
+        a11 -= nx * X[k]; a12 -= nx * Y[k]; b1 += nx;
+        a21 -= ny * X[k]; a22 -= ny * Y[k]; b2 += ny;
+    }
+    const double Dt = a11 * a22 - a12 * a21;
+    const double dP = det3_f64(X[0], Y[0], X[1], Y[1], X[2], Y[2]);
+    if (Dt == 0.0 || dP == 0.0) return false;
+    const double rD = 1.0 / Dt, rP = 1.0 / dP;
     double h0[9];
-    if (!gauss_solve<8>(a, h0)) return false;
+    h0[6] = (b1 * a22 - a12 * b2) * rD;
+    h0[7] = (a11 * b2 - b1 * a21) * rD;
     h0[8] = 1.0;
+    double u[3], v[3];
+EGL_UNROLL
+    for (int k = 0; k < 3; ++k) {
+        const double w = h0[6] * X[k] + h0[7] * Y[k] + 1.0;
+        u[k] = x[k] * w; v[k] = y[k] * w;
+    }
+    const double c0 = Y[1] - Y[2], c1 = Y[2] - Y[0], c2 = Y[0] - Y[1];
+    const double d0 = X[2] - X[1], d1 = X[0] - X[2], d2 = X[1] - X[0];
+    const double e0 = X[1] * Y[2] - X[2] * Y[1], e1 = X[2] * Y[0] - X[0] * Y[2], e2 = X[0] * Y[1] - X[1] * Y[0];
+    h0[0] = (u[0] * c0 + u[1] * c1 + u[2] * c2) * rP;
+    h0[1] = (u[0] * d0 + u[1] * d1 + u[2] * d2) * rP;
+    h0[2] = (u[0] * e0 + u[1] * e1 + u[2] * e2) * rP;
+    h0[3] = (v[0] * c0 + v[1] * c1 + v[2] * c2) * rP;
+    h0[4] = (v[0] * d0 + v[1] * d1 + v[2] * d2) * rP;
+    h0[5] = (v[0] * e0 + v[1] * e1 + v[2] * e2) * rP;
     const double norm[8] = {cMx, cMy, cmx, cmy, sMx, sMy, smx, smy};
     dlt_denormalise(h0, norm, H);
-    for (int i = 0; i < 9; ++i)
-        if (!isfinite(H[i])) return false;
-    return true;
+    bool fin = true;
+EGL_UNROLL
+    for (int i = 0; i < 9; ++i) fin = fin && isfinite(H[i]);
+    return fin;
 }
 
 // ---- HomographyRefineCallback + LMSolverImpl::run (9 parameters, <= 10 iterations) ------------
