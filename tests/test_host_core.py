@@ -122,3 +122,21 @@ def test_fixed_k_core_equals_independent_c_mirror():
         Hr, fm, n = hostcore.refit(Hb, img, wor, m)
         assert np.array_equal(mask.ravel(), fm) and np.max(np.abs(H - Hr) / np.abs(Hr)) < 1e-6
         assert not any(fm[k] for k, c in enumerate(ON) if flags[f, c])
+
+
+def test_postprocess_randomised_collisions_and_ties():
+    """Many channels landing on few pixels with scores from a small discrete set: exercises the duplicate
+    arbitration (best score wins; exact ties -> later label, earlier dict slot) against the oracle."""
+    rng = np.random.default_rng(4)
+    h, w = 12, 20
+    vals = np.array([0.009, 0.01, 0.0100001, 0.2, 0.29999998, 0.3, 0.30000001, 0.5, 0.5, 0.9, 1.0], np.float32)
+    for t in range(300):
+        pix = rng.choice(h * w, size=rng.integers(1, 6), replace=False)
+        flat = rng.choice(pix, size=57)
+        score = rng.choice(vals, size=57)
+        W, H = [(1280, 720), (1920, 1080), (3840, 2160), (854, 480)][t % 4]
+        kps = [(i, (flat[i] % w) / (w - 1), (flat[i] // w) / (h - 1), float(score[i])) for i in range(57) if float(score[i]) > 0.01]
+        want = decode.postprocess(kps, W, H, 0.3)
+        xy, order = hostcore.postprocess(flat, score, h, w, W, H)
+        got = {landmarks.INDEX_TO_NAME[int(c)]: (int(xy[c, 0]), int(xy[c, 1])) for c in order}
+        assert list(got) == list(want) and got == {k: tuple(v) for k, v in want.items()}, t
