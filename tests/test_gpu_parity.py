@@ -498,3 +498,38 @@ def test_decode_randomised_collisions_and_ties(engine):
             want = decode.decode_frame(hm[f], W, H)
             got = {LANDMARK_NAMES[int(c)]: (int(xy[f, c, 0]), int(xy[f, c, 1])) for c in order[f, :count[f, 0]]}
             assert list(got) == list(want) and got == {k: tuple(v) for k, v in want.items()}, f
+
+
+def test_rejection_heavy_sampling_matches_cv2(engine):
+    """Point sets where almost every 4-point sample fails OpenCV's checkSubset (most points on one line,
+    a handful off it): the sampler has to walk hundreds of rejected candidates per accepted one, across
+    many 32-candidate groups.  Status and inlier masks must still equal live cv2.findHomography's."""
+    import cv2
+    from eagle_b200.engine import KeypointSet
+    from eagle_b200.pitch import WORLD_XY_F32
+    rng = np.random.default_rng(12)
+    on = [i for i in range(57) if i not in (0, 1, 24, 25)]
+    cases = []
+    for t in range(48):
+        n = int(rng.integers(8, 30)); k = int(rng.integers(1, 5))
+        sel = np.sort(rng.choice(on, n, replace=False))
+        img = np.c_[np.arange(n) * 9 + 5, np.arange(n) * 4 + 11].astype(np.float32)    # collinear
+        off = rng.choice(n, k, replace=False)
+        img[off] += rng.integers(-200, 200, (k, 2)).astype(np.float32)                  # k points off the line
+        cases.append((sel, img))
+    T = len(cases)
+    xy = np.zeros((T, 57, 2), np.int32); order = np.full((T, 64), 255, np.uint8); count = np.zeros((T, 2), np.int32)
+    for i, (sel, img) in enumerate(cases):
+        xy[i, sel] = img.astype(np.int32); order[i, :len(sel)] = sel; count[i] = len(sel)
+    kp = KeypointSet(torch.zeros((T, 57), dtype=torch.int32).cuda(), torch.zeros((T, 57)).cuda(), torch.from_numpy(xy).cuda(),
+                     torch.from_numpy(order).cuda(), torch.from_numpy(count).cuda())
+    fit = engine.fit(kp)
+    status = fit.status.cpu().numpy(); inl = fit.inlier_mask.cpu().numpy(); info = fit.info.cpu().numpy()
+    n_model = 0
+    for i, (sel, img) in enumerate(cases):
+        Hc, mc = cv2.findHomography(img, WORLD_XY_F32[sel], cv2.RANSAC, 5.0)
+        assert (Hc is None) == (status[i] != 0), (i, status[i], info[i].tolist())
+        if Hc is not None:
+            n_model += 1
+            assert int(inl[i]) == sum(1 << int(c) for c, m in zip(sel, mc.ravel()) if m), (i, info[i].tolist())
+    assert 5 < n_model < T
