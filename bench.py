@@ -385,7 +385,7 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        n_cpu = 256
+        n_cpu = 2048  # ~15 s of single-thread CPU work
         v, dt = cpu_path_fps(n_cpu, 1)
         cpu = {"value": v, "unit": "frames/s", "cores": 1, "kind": "port",
                "sample": f"{n_cpu} frames of the same 1080p workload, 1 process / 1 thread: oracle port of the reference path "
