@@ -466,44 +466,54 @@ constexpr int kRefitWarps = 4;
 struct RefitShared {
     PointList pl;
     double A[81];
-    double aug[9 * 10];
+    double aug[10 * 11];
     double vec[12];
     double xs[9], rs[9], ds[9];  // parameter vector / right-hand side / LM scaling staged for lane-indexed access
 };
 
-// Gauss-Jordan elimination of a symmetric POSITIVE DEFINITE 9x9 system held as an augmented 9x10 array
-// in shared memory, all 32 lanes working: lane l owns elements l, l+32, l+64 of the 90; step k scales by
-// the k-th pivot and clears column k in every other row.  No pivoting is needed for SPD matrices, so
-// there is no search and no row swap; one warp synchronisation per step.  Every system of the refit is
-// SPD: the shifted normal matrix of the inverse iteration, the damped LM matrix A + lambda*diag(A), and
-// the undamped, gauge-singular LM matrix made definite by the rank-one term c * xhat xhat^T (x = the
-// current parameter vector is exactly the null vector of A, so (A + c xhat xhat^T)^-1 v = A^+ v for the
-// v orthogonal to x that occur here -- the same minimum-norm step cv2's eigen back-substitution takes).
-// Returns false (uniformly) if a pivot is not positive and finite.  x[0..9) in shared memory.
-__device__ bool warp_spd_solve9(double* aug, double* x) {
-    constexpr int n = 9, S = 10;
+// Gauss-Jordan elimination with partial pivoting of an n x n system held as an augmented n x (n+1)
+// array (row stride S = n+1) in shared memory, all 32 lanes working: lane l owns elements l, l+32, ...;
+// step k picks the largest remaining entry of column k (every lane scans the <= 10 candidates itself, so
+// the choice is uniform without shuffles; lowest row on ties, like the scalar gauss_solve), swaps rows,
+// and clears column k in every other row.  Same pivot order as the one-thread-per-frame code, which is
+// what keeps the two kernels -- and cv2 -- together on poorly conditioned fits.  x[0..n) in shared
+// memory.  Returns false (uniformly) on a zero / non-finite pivot.
+template <int n>
+__device__ bool warp_pivot_solve(double* aug, double* x) {
+    constexpr int S = n + 1, E = n * S, Q = (E + 31) / 32;
     const int lane = threadIdx.x & 31;
-    int er[3], ej[3];
+    int er[Q], ej[Q];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < Q; ++q) {
         const int e = lane + 32 * q;
-        er[q] = e < n * S ? e / S : -1;
+        er[q] = e < E ? e / S : -1;
         ej[q] = e % S;
     }
     for (int k = 0; k < n; ++k) {
-        const double piv = aug[k * S + k];
-        if (!(piv > 0.0) || !isfinite(piv)) return false;
-        const double inv = 1.0 / piv;
-        double nv[3];
-        bool upd[3];
+        int piv = k;
+        double best = fabs(aug[k * S + k]);
+        for (int r = k + 1; r < n; ++r) {
+            const double v = fabs(aug[r * S + k]);
+            if (v > best) { best = v; piv = r; }
+        }
+        if (!(best > 0.0) || !isfinite(best)) return false;
+        __syncwarp();
+        if (piv != k && lane < S) {  // lanes are columns for the swap
+            const double t = aug[k * S + lane];
+            aug[k * S + lane] = aug[piv * S + lane];
+            aug[piv * S + lane] = t;
+        }
+        __syncwarp();
+        const double inv = 1.0 / aug[k * S + k];
+        double nv[Q];
+        bool upd[Q];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < Q; ++q) {
             upd[q] = er[q] >= 0 && er[q] != k && ej[q] > k;
             if (upd[q]) nv[q] = aug[er[q] * S + ej[q]] - (aug[er[q] * S + k] * inv) * aug[k * S + ej[q]];
         }
-        __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
+        for (int q = 0; q < Q; ++q)
             if (upd[q]) aug[er[q] * S + ej[q]] = nv[q];
         __syncwarp();
     }
@@ -614,7 +624,7 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
                 }
                 if (lane < 9) sh.aug[lane * 10 + 9] = y_l;
                 __syncwarp();
-                if (!warp_spd_solve9(sh.aug, sh.vec)) { have_ls = false; break; }
+                if (!warp_pivot_solve<9>(sh.aug, sh.vec)) { have_ls = false; break; }
                 double z = lane < 9 ? sh.vec[lane] : 0.0;
                 const double nrm = warp_sum_f64(z * z);
                 // sign: component of largest magnitude positive (lowest index on ties)
@@ -703,22 +713,25 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
                 if (lane == i) dst[i] = src[i];
             __syncwarp();
         };
-        // gauge-fixed solve A d = rhs (A singular along x): (A + c xhat xhat^T) d = rhs, result in sh.vec
+        // gauge-fixed solve A d = rhs (A singular along x): bordered system [[A, s x],[s x^T, 0]] [d; mu] = [rhs; 0]
+        // (solve_gauge_fixed9 of geometry_core.cuh, parallelised), result in sh.vec[0..9)
         auto solve_gauge = [&](const double* rhs) -> bool {
             double xn = 0, dmx = 0;
 #pragma unroll
             for (int i = 0; i < 9; ++i) { xn += x[i] * x[i]; dmx = fmax(dmx, fabs(sh.A[i * 9 + i])); }
             if (!(xn > 0.0) || !(dmx > 0.0)) return false;
-            const double cc = dmx / xn;  // c / |x|^2
+            const double sc = dmx / sqrt(xn);
             stage(sh.xs, x);
             stage(sh.rs, rhs);
-            for (int t = lane; t < 81; t += 32) {
-                const int r = t / 9, c = t % 9;
-                sh.aug[r * 10 + c] = sh.A[t] + cc * sh.xs[r] * sh.xs[c];
+            for (int t = lane; t < 81; t += 32) sh.aug[(t / 9) * 11 + (t % 9)] = sh.A[t];
+            if (lane < 9) {
+                sh.aug[lane * 11 + 9] = sc * sh.xs[lane];
+                sh.aug[lane * 11 + 10] = sh.rs[lane];
+                sh.aug[9 * 11 + lane] = sc * sh.xs[lane];
             }
-            if (lane < 9) sh.aug[lane * 10 + 9] = sh.rs[lane];
+            if (lane == 0) { sh.aug[9 * 11 + 9] = 0.0; sh.aug[9 * 11 + 10] = 0.0; }
             __syncwarp();
-            return warp_spd_solve9(sh.aug, sh.vec);
+            return warp_pivot_solve<10>(sh.aug, sh.vec);
         };
         linearise(x);
 #pragma unroll
@@ -737,7 +750,7 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
                 }
                 if (lane < 9) sh.aug[lane * 10 + 9] = sh.rs[lane];
                 __syncwarp();
-                ok = warp_spd_solve9(sh.aug, sh.vec);
+                ok = warp_pivot_solve<9>(sh.aug, sh.vec);
             } else {
                 ok = solve_gauge(v);
             }
@@ -847,8 +860,7 @@ extern "C" int egl_fit_homography(const int32_t* kp_xy, const uint8_t* kp_order,
     }
     int rc = cuda_status(cudaGetLastError(), "egl_fit_homography: hypothesis kernel launch");
     if (rc) return rc;
-    // refit_warp_kernel is the product kernel (faster at every batch size measured: 0.18 ms for 2250
-    // frames, 2.6 ms for 50 k); EGL_REFIT_VARIANT=1 runs the one-thread-per-frame kernel, i.e. the
+    // refit_warp_kernel is the product kernel (0.28 ms for 2250 frames); EGL_REFIT_VARIANT=1 runs the one-thread-per-frame kernel, i.e. the
     // host-checkable scalar code of geometry_core.cuh, for cross-checking.
     static const char* refit_env = getenv("EGL_REFIT_VARIANT");
     if (refit_env && atoi(refit_env) == 1)
