@@ -42,45 +42,62 @@ def frame_time(i: int, fps: int) -> str:
     return f"{i // fps // 60:02d}:{i // fps % 60:02d}"
 
 
+def _bbox_list(bbox):
+    """``np.array(obj["BBox"], dtype=np.uint16).tolist()`` (coordinate_model.py:373) without the numpy round trip
+    when the box already is a list of in-range Python ints (the detector clips person boxes to the frame)."""
+    if type(bbox) is list and len(bbox) == 4:
+        a, b, c, d = bbox
+        if type(a) is int and type(b) is int and type(c) is int and type(d) is int and 0 <= a <= 65535 and 0 <= b <= 65535 \
+                and 0 <= c <= 65535 and 0 <= d <= 65535:
+            return [a, b, c, d]
+    return np.array(bbox, dtype=np.uint16).tolist()
+
+
 def assemble_frames(objects_per_frame, fps: int, first_index: int, kp_xy, kp_order, kp_count, used_mask, inlier_mask,
                     status, attempted, h_index, coords_i, in_bounds, bounds) -> dict:
     """Host-side dict assembly (coordinate_model.py:359-362, 369-392, 405-415) from the arrays the
-    kernels produced (all numpy, already on the host)."""
+    kernels produced (all numpy, already on the host).  The arrays are turned into plain Python lists
+    once, so the per-frame loop only touches native ints and floats (this loop is the serial part of the
+    drop-in API: ~0.1 ms per frame)."""
     res = {}
     off = set(OFF_PLANE)
+    names = LANDMARK_NAMES
+    xy_l = np.asarray(kp_xy).tolist(); order_l = np.asarray(kp_order).tolist(); n_l = np.asarray(kp_count)[:, 0].tolist()
+    inl_l = np.asarray(inlier_mask).tolist(); st_l = np.asarray(status).tolist(); att_l = np.asarray(attempted).tolist()
+    hi_l = np.asarray(h_index).tolist(); ci_l = np.asarray(coords_i).tolist(); ib_l = np.asarray(in_bounds).tolist()
+    bd_l = np.asarray(bounds, dtype=np.float64).tolist()
     for k, objects in enumerate(objects_per_frame):
         i = first_index + k
         # --- "Keypoints": inliers as float lists when this frame's fit was used, else all keypoints
-        n = int(kp_count[k, 0])
-        chans = [int(c) for c in kp_order[k, :n]]
-        if attempted[k] and status[k] == N.FIT_OK:
-            inl = int(inlier_mask[k])
-            keypoints = {LANDMARK_NAMES[c]: [float(kp_xy[k, c, 0]), float(kp_xy[k, c, 1])]
-                         for c in chans if c not in off and (inl >> c) & 1}
+        chans = order_l[k][:n_l[k]]
+        xy = xy_l[k]
+        if att_l[k] and st_l[k] == N.FIT_OK:
+            inl = inl_l[k]
+            keypoints = {names[c]: [float(xy[c][0]), float(xy[c][1])] for c in chans if c not in off and (inl >> c) & 1}
         else:
-            keypoints = {LANDMARK_NAMES[c]: (int(kp_xy[k, c, 0]), int(kp_xy[k, c, 1])) for c in chans}
+            keypoints = {names[c]: (xy[c][0], xy[c][1]) for c in chans}
         # --- "Coordinates"
-        have_h = h_index[k] >= 0
+        have_h = hi_l[k] >= 0
         indiv = {}
         p = 0
+        ci = ci_l[k]; ib = ib_l[k]
         for class_name, class_dict in objects.items():
             for obj_id, obj in class_dict.items():
-                bbox = np.array(obj["BBox"], dtype=np.uint16).tolist()
-                if have_h and in_bounds[k, p]:
-                    curr = {int(obj_id): {"BBox": bbox, "Confidence": obj["Confidence"],
-                                          "Transformed_Coordinates": [int(coords_i[k, p, 0]), int(coords_i[k, p, 1])]}}
+                if have_h and ib[p]:
+                    curr = {int(obj_id): {"BBox": _bbox_list(obj["BBox"]), "Confidence": obj["Confidence"],
+                                          "Transformed_Coordinates": ci[p]}}
                 else:
-                    curr = {int(obj_id): {"BBox": bbox, "Confidence": obj["Confidence"], "Transformed_Coordinates": None,
-                                          "Image_Bottom_center": obj["Bottom_center"]}}
+                    curr = {int(obj_id): {"BBox": _bbox_list(obj["BBox"]), "Confidence": obj["Confidence"],
+                                          "Transformed_Coordinates": None, "Image_Bottom_center": obj["Bottom_center"]}}
                 p += 1
                 if class_name not in indiv:
                     indiv[class_name] = curr
                 else:
                     indiv[class_name].update(curr)
         # --- "Boundaries"
-        b = bounds[k]
-        if have_h and not np.isnan(b[0]):
-            boundaries = [(float(b[0]), 0), (float(b[1]), PITCH_WIDTH_M), (float(b[2]), PITCH_WIDTH_M), (float(b[3]), 0)]
+        b = bd_l[k]
+        if have_h and b[0] == b[0]:
+            boundaries = [(b[0], 0), (b[1], PITCH_WIDTH_M), (b[2], PITCH_WIDTH_M), (b[3], 0)]
         else:
             boundaries = [None, None, None, None]
         res[i] = {"Coordinates": indiv, "Time": frame_time(i, fps), "Keypoints": keypoints, "Boundaries": boundaries}
