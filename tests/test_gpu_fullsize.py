@@ -106,3 +106,28 @@ def test_ransac_stress_recovers_planted_inliers(engine):
     want = np.array([sum(1 << c for c in on if not flags[f, c]) for f in range(F)], dtype=np.int64)
     assert np.array_equal(fit.inlier_mask.cpu().numpy(), want)
     assert int(fit.info[:, 1].min()) == 32 and int(fit.info[:, 1].max()) == 32
+
+
+def test_cadence_selection_full_match_length(engine):
+    """configs[2] length: 135,000 frames (90 min at 25 fps) through the cadence kernel, intervals 1 and 25,
+    with bursts of failed fits; against the reference's sequential state machine evaluated on the host."""
+    F = 135000
+    rng = np.random.default_rng(8)
+    status = (rng.uniform(size=F) < 0.03).astype(np.int32)             # isolated failures
+    for s in rng.integers(0, F - 400, 40):
+        status[s:s + int(rng.integers(1, 300))] = 1                     # bursts (camera cut-aways)
+    status[:7] = 2                                                      # no model at the very start
+    for interval in (1, 25):
+        h, att = engine.select(torch.from_numpy(status).cuda(), interval)
+        h = h.cpu().numpy(); att = att.cpu().numpy()
+        want_h = np.empty(F, np.int32); want_a = np.empty(F, np.uint8)
+        cur, flag = -1, False
+        for i in range(F):
+            a = (i % interval == 0) or flag
+            if a:
+                if status[i] == 0:
+                    cur = i; flag = False
+                else:
+                    flag = True
+            want_h[i] = cur; want_a[i] = a
+        assert np.array_equal(h, want_h) and np.array_equal(att, want_a), interval
