@@ -649,25 +649,26 @@ EGL_HD_NOINLINE int postprocess_keypoints(const int32_t* flat, const float* scor
 }
 
 // ---- fixed-K mode: sample generator and the FP32 minimal solve ------------------------------
-// counter-based sample generator: SplitMix64 keyed by (seed, frame, hypothesis); 4 distinct indices
-EGL_HD uint32_t splitmix_next(uint64_t& s) {
-    s += 0x9E3779B97F4A7C15ull;
-    uint64_t z = s;
+// counter-based sample generator: ONE SplitMix64 output keyed by (seed, frame, hypothesis) gives four
+// 16-bit fields, each scaled to [0, N); a repeated index is bumped to the next free one (mod N).  Cheap
+// (a dozen integer instructions) and reproducible anywhere -- oracle/ransac_f32.c restates it.
+EGL_HD uint64_t splitmix_mix(uint64_t s) {
+    uint64_t z = s + 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (uint32_t)(z >> 32);
+    return z ^ (z >> 31);
 }
 EGL_HD void seeded_subset(uint64_t seed, uint64_t frame, uint64_t K, uint64_t h, int N, int idx[4]) {
-    uint64_t s = seed ^ (0xD1B54A32D192ED03ull * (frame * K + h + 1));
+    const uint64_t z = splitmix_mix(seed ^ (0xD1B54A32D192ED03ull * (frame * K + h + 1)));
+EGL_UNROLL
     for (int i = 0; i < 4; ++i) {
-        int v;
-        bool dup;
-        do {
-            v = (int)(((uint64_t)splitmix_next(s) * (uint64_t)N) >> 32);
-            dup = false;
+        int v = (int)((((uint32_t)(z >> (16 * i)) & 0xFFFFu) * (uint32_t)N) >> 16);
+        for (int guard = 0; guard < 4; ++guard) {  // at most 3 earlier indices to step over
+            bool dup = false;
             for (int k = 0; k < i; ++k) dup |= (idx[k] == v);
-        } while (dup);
+            if (!dup) break;
+            v = v + 1 == N ? 0 : v + 1;
+        }
         idx[i] = v;
     }
 }

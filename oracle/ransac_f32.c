@@ -145,26 +145,25 @@ int orc_fixedk_frame(const float *X, const float *Y, const float *x, const float
     return 0;
 }
 
-/* the kernel's counter-based sample generator (SplitMix64), restated */
+/* the kernel's counter-based sample generator, restated: one SplitMix64 output per hypothesis, four 16-bit
+ * fields scaled to [0, n), repeated indices bumped to the next free index modulo n */
 void orc_seeded_table(uint64_t seed, uint64_t frame, int K, int n, uint8_t *table)
 {
-    int hh, i, k;
+    int hh, i, k, g;
     for (hh = 0; hh < K; hh++) {
-        uint64_t s = seed ^ (0xD1B54A32D192ED03ull * (frame * (uint64_t)K + (uint64_t)hh + 1));
+        uint64_t z = (seed ^ (0xD1B54A32D192ED03ull * (frame * (uint64_t)K + (uint64_t)hh + 1))) + 0x9E3779B97F4A7C15ull;
         int idx[4];
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
         for (i = 0; i < 4; i++) {
-            int v, dup;
-            do {
-                uint64_t z;
-                s += 0x9E3779B97F4A7C15ull;
-                z = s;
-                z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-                z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-                z ^= z >> 31;
-                v = (int)(((uint64_t)(uint32_t)(z >> 32) * (uint64_t)n) >> 32);
-                dup = 0;
+            int v = (int)(((uint32_t)((z >> (16 * i)) & 0xFFFFu) * (uint32_t)n) >> 16);
+            for (g = 0; g < 4; g++) {
+                int dup = 0;
                 for (k = 0; k < i; k++) dup |= (idx[k] == v);
-            } while (dup);
+                if (!dup) break;
+                v = (v + 1 == n) ? 0 : v + 1;
+            }
             idx[i] = v;
         }
         for (i = 0; i < 4; i++) table[4 * hh + i] = (uint8_t)idx[i];
