@@ -860,10 +860,14 @@ extern "C" int egl_fit_homography(const int32_t* kp_xy, const uint8_t* kp_order,
     }
     int rc = cuda_status(cudaGetLastError(), "egl_fit_homography: hypothesis kernel launch");
     if (rc) return rc;
-    // refit_warp_kernel is the product kernel (0.28 ms for 2250 frames); EGL_REFIT_VARIANT=1 runs the one-thread-per-frame kernel, i.e. the
-    // host-checkable scalar code of geometry_core.cuh, for cross-checking.
+    // Same algorithm, two parallelisations: one warp per frame has the lower latency (0.28 ms for a
+    // 2250-frame clip, a single wave), one thread per frame -- the host-checkable scalar code of
+    // geometry_core.cuh -- the higher throughput once there are more frames than resident warps
+    // (measured cross-over ~10-12 k frames: 50 k frames 2.2 ms vs 3.9 ms).  EGL_REFIT_VARIANT = 1 / 2
+    // forces the thread / warp kernel (used by the cross-check test).
     static const char* refit_env = getenv("EGL_REFIT_VARIANT");
-    if (refit_env && atoi(refit_env) == 1)
+    const int refit_variant = refit_env ? atoi(refit_env) : 0;
+    if (refit_variant == 1 || (refit_variant == 0 && F > 12288))
         refit_kernel<<<(F + kRefitThreads - 1) / kRefitThreads, kRefitThreads, 0, s>>>(a);
     else
         refit_warp_kernel<<<(F + kRefitWarps - 1) / kRefitWarps, kRefitWarps * 32, 0, s>>>(a);
