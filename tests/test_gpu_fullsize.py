@@ -131,3 +131,22 @@ def test_cadence_selection_full_match_length(engine):
                     flag = True
             want_h[i] = cur; want_a[i] = a
         assert np.array_equal(h, want_h) and np.array_equal(att, want_a), interval
+
+
+def test_config0_200_frames_720p_dict_equals_oracle():
+    """BASELINE.json configs[0]: the reference's own CPU-runnable case -- a synthetic 200-frame 1280x720
+    clip, 22 players + ball per frame -- through the CUDA path and through the oracle (the reference's
+    cv2/numpy statements): the two result dicts must be JSON-identical, frame for frame."""
+    import json
+    from eagle_b200 import synthetic
+    from eagle_b200.coordinate_model import GeometryPath
+    from oracle import pipeline
+    clip = synthetic.make_clip(200, 1280, 720, seed=2024, ghost_prob=0.05)
+    assert all(sum(len(v) for v in o.values()) == 23 for o in clip["objects"])
+    want = pipeline.get_coordinates(clip["heatmaps"], clip["objects"], 1280, 720, fps=25, num_homography=25)
+    got = GeometryPath("cuda:0").run(torch.from_numpy(clip["heatmaps"]).cuda(), clip["objects"], 1280, 720, fps=25)
+    assert json.dumps(got, default=float, sort_keys=True) == json.dumps(want, default=float, sort_keys=True)
+    # and with the reference's default homography cadence (once per second)
+    want = pipeline.get_coordinates(clip["heatmaps"], clip["objects"], 1280, 720, fps=25, num_homography=1)
+    got = GeometryPath("cuda:0").run(torch.from_numpy(clip["heatmaps"]).cuda(), clip["objects"], 1280, 720, fps=25, homography_interval=25)
+    assert json.dumps(got, default=float, sort_keys=True) == json.dumps(want, default=float, sort_keys=True)
