@@ -22,6 +22,12 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _require(cond: bool, msg: str) -> None:
+    """Argument checks of the host wrapper (kept as real exceptions: asserts vanish under -O)."""
+    if not cond:
+        raise ValueError(msg)
+
+
 @dataclass
 class KeypointSet:
     """Per-frame landmark detections in HBM (what K2 writes and F1 / K3 read)."""
@@ -64,8 +70,9 @@ class GeometryEngine:
     # -- K1 ---------------------------------------------------------------------------------
     def preprocess(self, frames: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """frames (F, H, W, 3) uint8 BGR on the device -> (F, 3, 540, 960) float32."""
-        assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3 and frames.is_cuda
-        assert frames.stride(3) == 1 and frames.stride(2) == 3
+        _require(frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3 and frames.is_cuda,
+                 "preprocess: frames must be a CUDA uint8 tensor of shape (F, H, W, 3)")
+        _require(frames.stride(3) == 1 and frames.stride(2) == 3, "preprocess: pixels must be packed B,G,R bytes (strides 3, 1)")
         F, H, W, _ = frames.shape
         if out is None:
             out = torch.empty((F, 3, N.MODEL_H, N.MODEL_W), dtype=torch.float32, device=frames.device)
@@ -87,9 +94,10 @@ class GeometryEngine:
                out: KeypointSet | None = None, from_logits: bool = False) -> KeypointSet:
         """heatmaps (F, 57, h, w) float32 contiguous on the device; from_logits=True takes the network's
         pre-sigmoid output and fuses the sigmoid into the arg-max kernel."""
-        assert heatmaps.dtype == torch.float32 and heatmaps.is_cuda and heatmaps.is_contiguous()
+        _require(heatmaps.dtype == torch.float32 and heatmaps.is_cuda and heatmaps.is_contiguous() and heatmaps.dim() == 4,
+                 "decode: heatmaps must be a contiguous CUDA float32 tensor of shape (F, 57, h, w)")
         F, C, h, w = heatmaps.shape
-        assert C == NUM_LANDMARKS
+        _require(C == NUM_LANDMARKS, f"decode: expected {NUM_LANDMARKS} heatmap channels, got {C}")
         kp = out if out is not None else self.alloc_keypoints(F)
         with torch.cuda.device(heatmaps.device):
             fn = N.lib.egl_decode_logits if from_logits else N.lib.egl_decode_heatmaps
@@ -116,7 +124,8 @@ class GeometryEngine:
         F = kp.n_frames
         r = out if out is not None else self.alloc_fit(F)
         if hyp is not None:
-            assert hyp.dtype == torch.uint8 and hyp.is_cuda and hyp.is_contiguous() and tuple(hyp.shape) == (F, K, 4)
+            _require(hyp.dtype == torch.uint8 and hyp.is_cuda and hyp.is_contiguous() and tuple(hyp.shape) == (F, K, 4),
+                     "fit: hyp must be a contiguous CUDA uint8 tensor of shape (F, K, 4)")
         with torch.cuda.device(kp.xy.device):
             N.check(N.lib.egl_fit_homography(_ptr(kp.xy), _ptr(kp.order), _ptr(kp.count), F, mode, K, _ptr(hyp), seed, float(thr),
                                              float(confidence), _ptr(r.H), _ptr(r.used_mask), _ptr(r.inlier_mask), _ptr(r.status),
@@ -143,12 +152,13 @@ class GeometryEngine:
     def project(self, H: torch.Tensor, foot: torch.Tensor, count: torch.Tensor, img_w: int, img_h: int,
                 h_index: torch.Tensor | None = None, out: Projection | None = None) -> Projection:
         """foot (F, P, 2) float32, count (F,) int32, H (*, 9) float64; h_index (F,) int32 or None."""
-        assert foot.dtype == torch.float32 and count.dtype == torch.int32 and H.dtype == torch.float64
-        assert foot.is_contiguous() and H.is_contiguous()
+        _require(foot.dtype == torch.float32 and count.dtype == torch.int32 and H.dtype == torch.float64,
+                 "project: dtypes must be foot float32, count int32, H float64")
+        _require(foot.is_contiguous() and H.is_contiguous() and foot.dim() == 3, "project: foot (F, P, 2) and H must be contiguous")
         F, P, _ = foot.shape
         pr = out if out is not None else self.alloc_projection(F, P)
         if h_index is not None:
-            assert h_index.dtype == torch.int32 and h_index.numel() == F
+            _require(h_index.dtype == torch.int32 and h_index.numel() == F, "project: h_index must be int32 with one entry per frame")
         with torch.cuda.device(foot.device):
             N.check(N.lib.egl_project_points(_ptr(H), _ptr(h_index), _ptr(foot), _ptr(count), F, P, img_w, img_h, _ptr(pr.coords),
                                              _ptr(pr.coords_i), _ptr(pr.in_bounds), _ptr(pr.bounds), _stream()),
