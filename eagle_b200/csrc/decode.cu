@@ -70,11 +70,12 @@ __global__ void __launch_bounds__(kDecThreads, kMinBlocks) argmax_kernel(DecodeA
     // producer state (thread 0 only): next chunk to request
     const float4* issue_src = a.hm + m0 * map_f4;  // advances chunk by chunk; maps are contiguous
     int issue_k = 0, issue_stage = 0, issued = 0;
+    const uint64_t policy = l2_evict_first_policy();
     auto issue = [&]() {
         const int off = issue_k * chunk_f4;
         const int n = min(chunk_f4, map_f4 - off);
         mbar_expect_tx(&full[issue_stage], (uint32_t)n * 16u);
-        bulk_g2s(ring + (size_t)issue_stage * chunk_f4, issue_src, (uint32_t)n * 16u, &full[issue_stage]);
+        bulk_g2s_hint(ring + (size_t)issue_stage * chunk_f4, issue_src, (uint32_t)n * 16u, &full[issue_stage], policy);
         issue_src += n;
         if (++issue_k == cpm) issue_k = 0;
         if (++issue_stage == kStages) issue_stage = 0;
