@@ -32,7 +32,7 @@ import torch
 from . import _native as N
 from .engine import GeometryEngine
 from .pitch import LANDMARK_NAMES, OFF_PLANE, PITCH_LENGTH_M, PITCH_WIDTH_M
-from .synthetic import objects_to_arrays
+from .boxes import objects_to_arrays
 
 BATCH = 4  # reference's HRNet batch (coordinate_model.py:20); only the chunking of the network calls
 

@@ -78,7 +78,7 @@ def run_sharded(path, heatmaps_local: torch.Tensor, objects_local: Sequence[dict
     import numpy as np
 
     from .coordinate_model import assemble_frames
-    from .synthetic import objects_to_arrays
+    from .boxes import objects_to_arrays
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
