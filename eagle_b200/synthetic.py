@@ -4,8 +4,8 @@ There are no datasets or checkpoints offline, so every test and benchmark runs o
 of the reference's shapes: a broadcast-like camera homography per frame,
 Gaussian landmark peaks rendered into (57, 135, 240) float32 heatmaps at the positions
 ``KeypointModel`` would emit them (keypoint_hrnet.py:590-591: x/(W-1), y/(H-1) normalisation), and
-detector-shaped boxes whose foot points fall on the pitch.  CPU (numpy) generation serves the
-tests and the CPU baseline; ``*_device`` variants generate directly in HBM for the benchmark.
+detector-shaped boxes whose foot points fall on the pitch.  Generation is numpy on the host (tests,
+CPU baseline, the benchmark's pool of landmark layouts); bench.py adds per-frame noise on the device.
 """
 from __future__ import annotations
 
