@@ -168,3 +168,95 @@ def stress_point_sets(n_frames: int, width: int, height: int, seed: int = 0, out
         kp[f] = np.rint(px).astype(np.int32)
     valid = np.full(n_frames, sum(1 << int(i) for i in on), np.uint64)
     return kp, valid, flags, cams
+
+
+# --------------------------------------------------------------------------------------------------
+# rendered clips: smooth camera motion + pitch markings, for the keypoint-propagation (optical flow) path
+# --------------------------------------------------------------------------------------------------
+def camera_path(n: int, width: int, height: int, rng: np.random.Generator, pan_px: float = 3.0, zoom_rate: float = 0.002) -> np.ndarray:
+    """(n, 3, 3) pitch->image homographies of one camera panning / zooming smoothly (a few px per frame)."""
+    base = np.linalg.inv(_BASE_IMG_TO_PITCH_720P)
+    S = np.diag([width / 1280.0, height / 720.0, 1.0])
+    x0 = rng.uniform(-150.0, 150.0); y0 = rng.uniform(-20.0, 30.0); z0 = rng.uniform(0.95, 1.2)
+    vx = rng.uniform(-pan_px, pan_px); vy = rng.uniform(-0.3, 0.3) * pan_px; vz = rng.uniform(-zoom_rate, zoom_rate)
+    out = np.empty((n, 3, 3))
+    for i in range(n):
+        # slow sinusoidal variation of the pan speed so that the motion is not exactly uniform
+        px = x0 + vx * i + 4.0 * np.sin(0.21 * i); py = y0 + vy * i + 1.5 * np.sin(0.13 * i + 1.0)
+        z = z0 + vz * i
+        pan = np.eye(3); pan[0, 2] = px; pan[1, 2] = py
+        zoom = np.array([[z, 0, 640.0 * (1 - z)], [0, z, 360.0 * (1 - z)], [0, 0, 1.0]])
+        H = S @ zoom @ pan @ base
+        out[i] = H / H[2, 2]
+    return out
+
+
+def _marking_distance(wx: np.ndarray, wy: np.ndarray) -> np.ndarray:
+    """Distance in metres from pitch points to the nearest marking of a standard 105 x 68 pitch."""
+    L, Wd = float(PITCH_LENGTH_M), float(PITCH_WIDTH_M)
+    d = np.full(wx.shape, 1e9)
+
+    def vseg(x, y0, y1):
+        nonlocal d
+        dy = np.maximum(np.maximum(y0 - wy, wy - y1), 0.0)
+        d = np.minimum(d, np.hypot(wx - x, dy))
+
+    def hseg(y, x0, x1):
+        nonlocal d
+        dx = np.maximum(np.maximum(x0 - wx, wx - x1), 0.0)
+        d = np.minimum(d, np.hypot(dx, wy - y))
+
+    vseg(0.0, 0.0, Wd); vseg(L, 0.0, Wd); vseg(L / 2, 0.0, Wd); hseg(0.0, 0.0, L); hseg(Wd, 0.0, L)
+    for x_goal, sgn in ((0.0, 1.0), (L, -1.0)):
+        for depth, half in ((16.5, 20.16), (5.5, 9.16)):
+            xe = x_goal + sgn * depth
+            vseg(xe, Wd / 2 - half, Wd / 2 + half)
+            hseg(Wd / 2 - half, min(x_goal, xe), max(x_goal, xe)); hseg(Wd / 2 + half, min(x_goal, xe), max(x_goal, xe))
+        # penalty arc (outside the box only) and spot
+        sx = x_goal + sgn * 11.0
+        r = np.hypot(wx - sx, wy - Wd / 2)
+        outside = (sgn * (wx - x_goal)) > 16.5
+        d = np.minimum(d, np.where(outside, np.abs(r - 9.15), 1e9))
+        d = np.minimum(d, np.maximum(r - 0.15, 0.0))
+    d = np.minimum(d, np.abs(np.hypot(wx - L / 2, wy - Wd / 2) - 9.15))
+    return d
+
+
+def render_pitch_frame(cam: np.ndarray, width: int, height: int, rng: np.random.Generator | None = None, noise: float = 1.5) -> np.ndarray:
+    """(height, width, 3) uint8 BGR picture of the pitch seen through ``cam``: mown grass with a texture
+    that is fixed in pitch coordinates (so it moves with the camera), white markings, grey surroundings."""
+    inv = np.linalg.inv(cam)
+    ys, xs = np.mgrid[0:height, 0:width].astype(np.float64)
+    den = inv[2, 0] * xs + inv[2, 1] * ys + inv[2, 2]
+    wx = (inv[0, 0] * xs + inv[0, 1] * ys + inv[0, 2]) / den
+    wy = (inv[1, 0] * xs + inv[1, 1] * ys + inv[1, 2]) / den
+    tex = 7.0 * np.sin(1.31 * wx + 0.73 * wy) + 5.0 * np.sin(2.9 * wy - 1.1 * wx + 0.4) + 4.0 * np.sin(0.47 * wx * wy * 0.05 + 1.7)
+    stripe = np.where((np.floor(wx / 5.25).astype(np.int64) & 1) == 0, 10.0, -10.0)
+    inside = (wx >= -2.0) & (wx <= PITCH_LENGTH_M + 2.0) & (wy >= -2.0) & (wy <= PITCH_WIDTH_M + 2.0) & (den > 0)
+    img = np.empty((height, width, 3), np.float64)
+    img[..., 0] = np.where(inside, 45.0 + 0.6 * tex, 95.0 + tex)                 # B
+    img[..., 1] = np.where(inside, 125.0 + stripe + tex, 100.0 + 1.2 * tex)      # G
+    img[..., 2] = np.where(inside, 50.0 + 0.8 * tex, 105.0 + 0.9 * tex)          # R
+    d = _marking_distance(wx, wy)
+    line = np.clip(1.5 - d / 0.12, 0.0, 1.0) * inside  # ~0.3 m wide, soft edge
+    img += (235.0 - img) * line[..., None]
+    if rng is not None and noise > 0:
+        img += rng.normal(0.0, noise, img.shape)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def make_flow_clip(n_frames: int, width: int, height: int, seed: int = 0, hide_prob: float = 0.1, pan_px: float = 3.0):
+    """Like make_clip, but with one smoothly moving camera and rendered frames that show the markings
+    the heatmaps point at -- what the Lucas-Kanade propagation needs."""
+    rng = np.random.default_rng(seed)
+    cams = camera_path(n_frames, width, height, rng, pan_px=pan_px)
+    heat = np.empty((n_frames, NUM_LANDMARKS, HM_H, HM_W), np.float32)
+    frames = np.empty((n_frames, height, width, 3), np.uint8)
+    objs = []
+    for i in range(n_frames):
+        px, vis = landmark_pixels(cams[i], width, height)
+        vis = vis & (rng.uniform(size=NUM_LANDMARKS) >= hide_prob)
+        heat[i] = render_heatmaps(px, vis, width, height, rng)
+        objs.append(sample_objects(cams[i], width, height, rng))
+        frames[i] = render_pitch_frame(cams[i], width, height, rng)
+    return {"cameras": cams, "heatmaps": heat, "objects": objs, "frames": frames, "width": width, "height": height}

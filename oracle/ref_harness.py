@@ -92,8 +92,30 @@ class Recorder:
         return False
 
 
+def stamp_frames(frames):
+    """Copies of the frames with the frame index written into pixel (0,0) (see run_reference)."""
+    stamped = []
+    for i, fr in enumerate(frames):
+        fr = np.array(fr, copy=True)
+        fr[0, 0] = (i & 255, (i >> 8) & 255, (i >> 16) & 255)  # BGR
+        stamped.append(fr)
+    return stamped
+
+
+def bare_reference_model(keypoint_conf: float = 0.3):
+    """A reference CoordinateModel without networks: enough for calculate_optical_flow (:419-478),
+    calibrate_keypoints (:520-555) and _synthesize_keypoints_with_line_intersections (:76-186)."""
+    import cv2
+    cm = load_reference()
+    model = cm.CoordinateModel.__new__(cm.CoordinateModel)
+    model.keypoint_conf = keypoint_conf
+    model.detector_conf = 0.35
+    model.lk_params = dict(winSize=(15, 15), maxLevel=2, criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 10, 0.03))
+    return model
+
+
 def run_reference(frames, heatmaps, objects_per_frame, fps: int = 1, num_homography: int = 1,
-                  num_keypoint_detection: int = 1, keypoint_conf: float = 0.3):
+                  num_keypoint_detection: int = 1, keypoint_conf: float = 0.3, calibration: bool = False):
     """Call the real get_coordinates.  frames: sequence of (H,W,3) uint8; heatmaps (F,57,h,w) f32.
 
     With the default fps=1 both cadence intervals are 1 (coordinate_model.py:205-206): every frame
@@ -142,12 +164,8 @@ def run_reference(frames, heatmaps, objects_per_frame, fps: int = 1, num_homogra
     it = iter(objects_per_frame)
     model.detect_objects = lambda frame: next(it)
 
-    stamped = []
-    for i, fr in enumerate(frames):
-        fr = np.array(fr, copy=True)
-        fr[0, 0] = (i & 255, (i >> 8) & 255, (i >> 16) & 255)  # BGR
-        stamped.append(fr)
+    stamped = stamp_frames(frames)
     with Recorder() as rec:
         res = model.get_coordinates(stamped, fps=fps, num_homography=num_homography,
-                                    num_keypoint_detection=num_keypoint_detection, verbose=False)
+                                    num_keypoint_detection=num_keypoint_detection, verbose=False, calibration=calibration)
     return res, rec
