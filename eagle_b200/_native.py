@@ -9,7 +9,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libeagle_b200.so")
 
 ABI_VERSION = 1
-FIT_OK, FIT_FEW_POINTS, FIT_NO_MODEL = 0, 1, 2
+FIT_OK, FIT_FEW_POINTS, FIT_NO_MODEL, FIT_SKIPPED = 0, 1, 2, 3
+KP_PY_INT, KP_NUMPY_INT, KP_FLOAT = 0, 1, 2
 FIT_FIXED_K, FIT_CV2_COMPAT = 0, 1
 NUM_LANDMARKS, ORDER_STRIDE, MODEL_H, MODEL_W = 57, 64, 540, 960
 
@@ -37,12 +38,26 @@ lib.egl_synthesize_keypoints.argtypes = [_vp, _vp, _vp, _i, _i, _vp]
 lib.egl_fit_homography.argtypes = [_vp, _vp, _vp, _i, _i, _i, _vp, _u64, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp]
 lib.egl_select_homography.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp]
 lib.egl_project_points.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
+lib.egl_pyramid_bytes.argtypes = [_i, _i, _i]
+lib.egl_pyramid_bytes.restype = C.c_int64
+lib.egl_gray_pyramid.argtypes = [_vp, _i, _i, _i, _sz, _sz, _i, _vp, _vp]
+lib.egl_track_keypoints.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp]
+lib.egl_filter_flow.argtypes = [_vp, _i, _i, _sz, _sz, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]
+lib.egl_merge_keypoints.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]
+lib.egl_calibrate_keypoints.argtypes = [_vp, _i, _i, _sz, _sz, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
+lib.egl_fit_homography_masked.argtypes = [_vp, _vp, _vp, _i, _i, _i, _vp, _u64, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+lib.egl_commit_fit.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]
+for _name in ("egl_gray_pyramid", "egl_track_keypoints", "egl_filter_flow", "egl_merge_keypoints", "egl_calibrate_keypoints",
+              "egl_fit_homography_masked", "egl_commit_fit"):
+    getattr(lib, _name).restype = _i
 for _name in ("egl_preprocess_u8", "egl_decode_heatmaps", "egl_decode_logits", "egl_synthesize_keypoints", "egl_fit_homography",
               "egl_select_homography", "egl_project_points"):
     getattr(lib, _name).restype = _i
 
 EXPORTS = ("egl_version", "egl_last_error", "egl_sm_count", "egl_preprocess_u8", "egl_decode_heatmaps", "egl_decode_logits",
-           "egl_synthesize_keypoints", "egl_fit_homography", "egl_select_homography", "egl_project_points")
+           "egl_synthesize_keypoints", "egl_fit_homography", "egl_select_homography", "egl_project_points", "egl_pyramid_bytes",
+           "egl_gray_pyramid", "egl_track_keypoints", "egl_filter_flow", "egl_merge_keypoints", "egl_calibrate_keypoints",
+           "egl_fit_homography_masked", "egl_commit_fit")
 
 if lib.egl_version() != ABI_VERSION:
     raise NativeError(f"libeagle_b200.so has ABI {lib.egl_version()}, this package expects {ABI_VERSION}; rebuild")

@@ -13,7 +13,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libeagle_b200.so")
-SOURCES = ["common.cu", "preprocess.cu", "decode.cu", "synthesize.cu", "fit.cu", "project.cu"]
+SOURCES = ["common.cu", "preprocess.cu", "decode.cu", "synthesize.cu", "fit.cu", "project.cu", "flow.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -18,9 +18,11 @@ What runs where
   * this module only moves data and assembles Python dicts.
 
 Cadence: the homography cadence (``num_homography``, retry after a failed fit, reuse of the
-previous H) is reproduced exactly.  Keypoint cadence other than "every frame" needs Lucas-Kanade
-optical-flow propagation between network frames (coordinate_model.py:419-478), which is outside
-this path; ``num_keypoint_detection`` must therefore give a keypoint interval of 1.
+previous H) is reproduced exactly.  With a keypoint interval of 1 and every frame decoding >= 4
+landmarks the frames are independent and go through GeometryPath in one batch; any other case
+(sparse keypoint cadence, brightness calibration, a frame with < 4 landmarks that the reference
+rescues by optical flow) goes through eagle_b200.propagation.PropagatedPath, which reproduces the
+reference's Lucas-Kanade propagation (coordinate_model.py:277-330, 419-478, 520-555) on the GPU.
 """
 from __future__ import annotations
 
@@ -54,24 +56,39 @@ def _bbox_list(bbox):
 
 
 def assemble_frames(objects_per_frame, fps: int, first_index: int, kp_xy, kp_order, kp_count, used_mask, inlier_mask,
-                    status, attempted, h_index, coords_i, in_bounds, bounds) -> dict:
+                    status, attempted, h_index, coords_i, in_bounds, bounds, kp_src=None) -> dict:
     """Host-side dict assembly (coordinate_model.py:359-362, 369-392, 405-415) from the arrays the
     kernels produced (all numpy, already on the host).  The arrays are turned into plain Python lists
     once, so the per-frame loop only touches native ints and floats (this loop is the serial part of the
-    drop-in API: ~0.1 ms per frame)."""
+    drop-in API: ~0.1 ms per frame).
+
+    With ``kp_src`` (keypoint propagation) the keypoint sets are already what the reference holds in
+    ``prev_keypoints`` at the end of each frame -- the inlier commit ran on the device -- and kp_src says
+    which Python type each value has there (EGL_KP_*), so that json.dump(default=float) prints the same."""
     res = {}
     off = set(OFF_PLANE)
     names = LANDMARK_NAMES
     xy_l = np.asarray(kp_xy).tolist(); order_l = np.asarray(kp_order).tolist(); n_l = np.asarray(kp_count)[:, 0].tolist()
-    inl_l = np.asarray(inlier_mask).tolist(); st_l = np.asarray(status).tolist(); att_l = np.asarray(attempted).tolist()
     hi_l = np.asarray(h_index).tolist(); ci_l = np.asarray(coords_i).tolist(); ib_l = np.asarray(in_bounds).tolist()
     bd_l = np.asarray(bounds, dtype=np.float64).tolist()
+    if kp_src is None:
+        inl_l = np.asarray(inlier_mask).tolist(); st_l = np.asarray(status).tolist(); att_l = np.asarray(attempted).tolist()
+    else:
+        src_l = np.asarray(kp_src).tolist()
+        i64 = np.int64
     for k, objects in enumerate(objects_per_frame):
         i = first_index + k
         # --- "Keypoints": inliers as float lists when this frame's fit was used, else all keypoints
         chans = order_l[k][:n_l[k]]
         xy = xy_l[k]
-        if att_l[k] and st_l[k] == N.FIT_OK:
+        if kp_src is not None:
+            src = src_l[k]
+            keypoints = {}
+            for c in chans:
+                t = src[c]
+                x, y = xy[c]
+                keypoints[names[c]] = (x, y) if t == N.KP_PY_INT else ([float(x), float(y)] if t == N.KP_FLOAT else (i64(x), i64(y)))
+        elif att_l[k] and st_l[k] == N.FIT_OK:
             inl = inl_l[k]
             keypoints = {names[c]: [float(xy[c][0]), float(xy[c][1])] for c in chans if c not in off and (inl >> c) & 1}
         else:
@@ -156,6 +173,8 @@ class CoordinateModel:
         self._detect_objects = detect_objects
         self.chunk = chunk
         self.path = GeometryPath(device, keypoint_conf)
+        self.always_propagate = False  # route every clip through PropagatedPath (tests)
+        self.last_stats = {}
 
     def detect_objects(self, frame: np.ndarray) -> dict:
         if self._detect_objects is None:
@@ -163,14 +182,18 @@ class CoordinateModel:
         return self._detect_objects(frame)
 
     @torch.no_grad()
-    def _heatmaps(self, frames: Sequence[np.ndarray]) -> torch.Tensor:
+    def _heatmaps_dev(self, dev_frames: torch.Tensor) -> torch.Tensor:
+        """K1 + the attached network on frames that already are in HBM ((n, H, W, 3) uint8)."""
         if self.keypoint_model is None:
             raise RuntimeError("no keypoint network attached: pass keypoint_model=<callable tensor -> heatmaps>")
-        host = torch.from_numpy(np.ascontiguousarray(np.stack(frames)))
-        dev_frames = host.pin_memory().to(self.device, non_blocking=True)
-        x = self.path.engine.preprocess(dev_frames)
+        x = self.path.engine.preprocess(dev_frames.contiguous())
         outs = [self.keypoint_model(x[i:i + BATCH]) for i in range(0, x.shape[0], BATCH)]
         return torch.cat(outs).to(torch.float32).contiguous()
+
+    @torch.no_grad()
+    def _heatmaps(self, frames: Sequence[np.ndarray]) -> torch.Tensor:
+        host = torch.from_numpy(np.ascontiguousarray(np.stack(frames)))
+        return self._heatmaps_dev(host.pin_memory().to(self.device, non_blocking=True))
 
     @torch.no_grad()
     def detect_keypoints(self, frame: np.ndarray) -> dict:
@@ -189,11 +212,8 @@ class CoordinateModel:
             return {}
         homography_interval = max(1, int(fps / max(1, num_homography)))
         keypoint_interval = max(1, int(fps / max(1, num_keypoint_detection)))
-        if keypoint_interval != 1:
-            raise NotImplementedError("keypoint cadence other than every frame needs optical-flow propagation "
-                                      "(coordinate_model.py:419-478), which is outside the accelerated path")
-        if calibration:
-            raise NotImplementedError("brightness calibration (coordinate_model.py:520-555) is outside the accelerated path")
+        if keypoint_interval != 1 or calibration or self.always_propagate:
+            return self._get_coordinates_propagated(frames, fps, homography_interval, keypoint_interval, calibration)
         height, width = frames[0].shape[:2]
         # cadence state crosses chunk boundaries through carry_in; chunks keep memory bounded
         all_obj = [self.detect_objects(f) for f in frames]
@@ -207,6 +227,9 @@ class CoordinateModel:
             kps.append(kp)
             fits.append(e.fit(kp))
         cat = lambda xs: torch.cat(xs) if len(xs) > 1 else xs[0]
+        if int(torch.stack([(k.count[:, 1] < 4).any() for k in kps]).any().item()):
+            # a frame decoded < 4 landmarks: the reference brings optical flow in (:287-311)
+            return self._get_coordinates_propagated(frames, fps, homography_interval, keypoint_interval, calibration, all_obj)
         status = cat([f.status for f in fits]); Hs = cat([f.H for f in fits])
         h_index, attempted = e.select(status, homography_interval)
         max_pts = max(1, max(sum(len(v) for v in o.values()) for o in all_obj))
@@ -218,3 +241,26 @@ class CoordinateModel:
                                c(cat([k.count for k in kps])), c(cat([f.used_mask for f in fits])),
                                c(cat([f.inlier_mask for f in fits])), c(status), c(attempted), c(h_index), c(proj.coords_i),
                                c(proj.in_bounds), c(proj.bounds))
+
+    def _get_coordinates_propagated(self, frames, fps: int, homography_interval: int, keypoint_interval: int, calibration: bool,
+                                    all_obj=None) -> dict:
+        """Any cadence: frames to HBM, network on the chain heads, PropagatedPath, projection, dict assembly."""
+        from .propagation import PropagatedPath
+        e = self.path.engine
+        height, width = frames[0].shape[:2]
+        if all_obj is None:
+            all_obj = [self.detect_objects(f) for f in frames]
+        host = torch.from_numpy(np.ascontiguousarray(np.stack(frames)))
+        dev_frames = host.pin_memory().to(self.device, non_blocking=True)
+        heads = list(range(0, len(frames), keypoint_interval))
+        hm = torch.cat([self._heatmaps_dev(dev_frames[heads[s:s + self.chunk]]) for s in range(0, len(heads), self.chunk)])
+        prop = PropagatedPath(e, self.keypoint_conf)
+        out = prop.run(dev_frames, hm, lambda i: self._heatmaps_dev(dev_frames[i:i + 1]), keypoint_interval, homography_interval, calibration)
+        self.last_stats = dict(prop.stats)
+        max_pts = max(1, max(sum(len(v) for v in o.values()) for o in all_obj))
+        foot_h, count_h = objects_to_arrays(all_obj, max_pts)
+        proj = e.project(out["H"], torch.from_numpy(foot_h).to(self.device), torch.from_numpy(count_h).to(self.device), width, height,
+                         h_index=out["h_index"])
+        c = lambda t: t.cpu().numpy()
+        return assemble_frames(all_obj, fps, 0, c(out["xy"]), c(out["order"]), c(out["count"]), None, None, None, None, c(out["h_index"]),
+                               c(proj.coords_i), c(proj.in_bounds), c(proj.bounds), kp_src=c(out["src"]))

@@ -43,7 +43,21 @@ struct FitArgs {
     uint64_t* inlier_mask;
     int32_t* status;
     int32_t* info;
+    const uint8_t* sched;  // optional: fit frame f only where sched[f] | retry[f] (cadence of coordinate_model.py:333)
+    const uint8_t* retry;
 };
+
+// Frames the cadence does not fit this step: status EGL_FIT_SKIPPED, nothing else touched but the masks.
+__device__ __forceinline__ bool fit_skipped(const FitArgs& a, int f) {
+    return a.sched && !(a.sched[f] | (a.retry ? a.retry[f] : (uint8_t)0));
+}
+__device__ __forceinline__ void park_skipped(const FitArgs& a, int f) {
+    a.status[f] = EGL_FIT_SKIPPED;
+    a.used_mask[f] = 0;
+    a.inlier_mask[f] = 0;
+    a.info[4 * f + 0] = a.info[4 * f + 1] = a.info[4 * f + 3] = 0;
+    a.info[4 * f + 2] = -1;
+}
 
 struct PointList {  // one frame's correspondences, float as cv2 receives them (:348-349)
     float sx[kMaxPts], sy[kMaxPts], dx[kMaxPts], dy[kMaxPts];
@@ -125,6 +139,10 @@ __global__ void __launch_bounds__(kCv2Warps * 32) ransac_cv2_kernel(FitArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.x * kCv2Warps + warp;
     if (f >= a.F) return;
+    if (fit_skipped(a, f)) {
+        if (lane == 0) park_skipped(a, f);
+        return;
+    }
     PointList& pl = s_pl[warp];
     uint64_t used;
     const int N = gather_points_warp(a, f, pl, &used);
@@ -268,6 +286,10 @@ __global__ void __launch_bounds__(kFixedThreads) ransac_fixedk_kernel(FitArgs a,
     __shared__ unsigned long long s_used;
     const int f = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (fit_skipped(a, f)) {
+        if (tid == 0) park_skipped(a, f);
+        return;
+    }
     if (warp == 0) {
         uint64_t used;
         const int n = gather_points_warp(a, f, s_pl, &used);
@@ -839,19 +861,17 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
 
 using namespace egl;
 
-extern "C" int egl_fit_homography(const int32_t* kp_xy, const uint8_t* kp_order, const int32_t* kp_count, int F, int mode,
-                                  int K, const uint8_t* hyp, uint64_t seed, double thr, double confidence, double* H,
-                                  uint64_t* used_mask, uint64_t* inlier_mask, int32_t* status, int32_t* info,
-                                  void* stream) {
+static int fit_impl(const char* who, const int32_t* kp_xy, const uint8_t* kp_order, const int32_t* kp_count, int F, int mode, int K,
+                    const uint8_t* hyp, uint64_t seed, double thr, double confidence, double* H, uint64_t* used_mask,
+                    uint64_t* inlier_mask, int32_t* status, int32_t* info, const uint8_t* sched, const uint8_t* retry, void* stream) {
     if (F == 0) return 0;  // empty batch: nothing to enqueue, pointers may be null
-    EGL_REQUIRE(kp_xy && kp_order && kp_count && H && used_mask && inlier_mask && status && info, EGL_ERR_NULL,
-                "egl_fit_homography: null pointer");
-    EGL_REQUIRE(F >= 0 && K >= 1, EGL_ERR_SHAPE, "egl_fit_homography: need F >= 0 and K >= 1 (F=%d K=%d)", F, K);
-    EGL_REQUIRE(mode == EGL_FIT_CV2_COMPAT || mode == EGL_FIT_FIXED_K, EGL_ERR_MODE, "egl_fit_homography: unknown mode %d", mode);
-    EGL_REQUIRE(confidence > 0 && confidence < 1, EGL_ERR_SHAPE, "egl_fit_homography: confidence must be in (0,1)");
-    if (F == 0) return 0;
+    EGL_REQUIRE(kp_xy && kp_order && kp_count && H && used_mask && inlier_mask && status && info, EGL_ERR_NULL, "%s: null pointer", who);
+    EGL_REQUIRE(F >= 0 && K >= 1, EGL_ERR_SHAPE, "%s: need F >= 0 and K >= 1 (F=%d K=%d)", who, F, K);
+    EGL_REQUIRE(mode == EGL_FIT_CV2_COMPAT || mode == EGL_FIT_FIXED_K, EGL_ERR_MODE, "%s: unknown mode %d", who, mode);
+    EGL_REQUIRE(confidence > 0 && confidence < 1, EGL_ERR_SHAPE, "%s: confidence must be in (0,1)", who);
     if (!(thr > 0)) thr = 3.0;  // findHomography: ransacReprojThreshold <= 0 -> 3
-    FitArgs a{kp_xy, kp_order, kp_count, F, K, hyp, seed, (float)(thr * thr), confidence, H, used_mask, inlier_mask, status, info};
+    FitArgs a{kp_xy, kp_order, kp_count, F, K, hyp, seed, (float)(thr * thr), confidence, H, used_mask, inlier_mask, status, info,
+              sched, retry};
     cudaStream_t s = (cudaStream_t)stream;
     if (mode == EGL_FIT_CV2_COMPAT) {
         ransac_cv2_kernel<<<(F + kCv2Warps - 1) / kCv2Warps, kCv2Warps * 32, 0, s>>>(a);
@@ -872,4 +892,21 @@ extern "C" int egl_fit_homography(const int32_t* kp_xy, const uint8_t* kp_order,
     else
         refit_warp_kernel<<<(F + kRefitWarps - 1) / kRefitWarps, kRefitWarps * 32, 0, s>>>(a);
     return cuda_status(cudaGetLastError(), "egl_fit_homography: refit kernel launch");
+}
+
+extern "C" int egl_fit_homography(const int32_t* kp_xy, const uint8_t* kp_order, const int32_t* kp_count, int F, int mode,
+                                  int K, const uint8_t* hyp, uint64_t seed, double thr, double confidence, double* H,
+                                  uint64_t* used_mask, uint64_t* inlier_mask, int32_t* status, int32_t* info,
+                                  void* stream) {
+    return fit_impl("egl_fit_homography", kp_xy, kp_order, kp_count, F, mode, K, hyp, seed, thr, confidence, H, used_mask, inlier_mask,
+                    status, info, nullptr, nullptr, stream);
+}
+
+extern "C" int egl_fit_homography_masked(const int32_t* kp_xy, const uint8_t* kp_order, const int32_t* kp_count, int F, int mode,
+                                         int K, const uint8_t* hyp, uint64_t seed, double thr, double confidence, double* H,
+                                         uint64_t* used_mask, uint64_t* inlier_mask, int32_t* status, int32_t* info,
+                                         const uint8_t* sched, const uint8_t* retry, void* stream) {
+    if (F > 0) EGL_REQUIRE(sched, EGL_ERR_NULL, "egl_fit_homography_masked: sched is null");
+    return fit_impl("egl_fit_homography_masked", kp_xy, kp_order, kp_count, F, mode, K, hyp, seed, thr, confidence, H, used_mask,
+                    inlier_mask, status, info, sched, retry, stream);
 }

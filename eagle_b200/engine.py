@@ -36,10 +36,11 @@ class KeypointSet:
     xy: torch.Tensor      # (F, 57, 2) int32 image pixel per channel
     order: torch.Tensor   # (F, 64) uint8   channels kept, in the reference's dict order
     count: torch.Tensor   # (F, 2) int32    {entries in order, of which decoded from heatmaps}
+    src: torch.Tensor | None = None  # (F, 64) uint8 KP_* type tag per channel (keypoint propagation only)
 
     @property
     def n_frames(self) -> int:
-        return self.flat.shape[0]
+        return self.xy.shape[0]
 
 
 @dataclass
@@ -120,17 +121,96 @@ class GeometryEngine:
                          torch.zeros((F, 4), dtype=torch.int32, device=dev))
 
     def fit(self, kp: KeypointSet, mode: int = N.FIT_CV2_COMPAT, K: int = 2000, hyp: torch.Tensor | None = None,
-            seed: int = 0, thr: float = 5.0, confidence: float = 0.995, out: FitResult | None = None) -> FitResult:
+            seed: int = 0, thr: float = 5.0, confidence: float = 0.995, out: FitResult | None = None,
+            sched: torch.Tensor | None = None, retry: torch.Tensor | None = None) -> FitResult:
+        """sched / retry (F,) uint8: fit only the frames with sched | retry (the reference's cadence test, :333)."""
         F = kp.n_frames
         r = out if out is not None else self.alloc_fit(F)
         if hyp is not None:
             _require(hyp.dtype == torch.uint8 and hyp.is_cuda and hyp.is_contiguous() and tuple(hyp.shape) == (F, K, 4),
                      "fit: hyp must be a contiguous CUDA uint8 tensor of shape (F, K, 4)")
         with torch.cuda.device(kp.xy.device):
-            N.check(N.lib.egl_fit_homography(_ptr(kp.xy), _ptr(kp.order), _ptr(kp.count), F, mode, K, _ptr(hyp), seed, float(thr),
-                                             float(confidence), _ptr(r.H), _ptr(r.used_mask), _ptr(r.inlier_mask), _ptr(r.status),
-                                             _ptr(r.info), _stream()), "egl_fit_homography")
+            if sched is None:
+                N.check(N.lib.egl_fit_homography(_ptr(kp.xy), _ptr(kp.order), _ptr(kp.count), F, mode, K, _ptr(hyp), seed, float(thr),
+                                                 float(confidence), _ptr(r.H), _ptr(r.used_mask), _ptr(r.inlier_mask), _ptr(r.status),
+                                                 _ptr(r.info), _stream()), "egl_fit_homography")
+            else:
+                _require(sched.dtype == torch.uint8 and sched.numel() == F and sched.is_contiguous(), "fit: sched must be (F,) uint8")
+                _require(retry is None or (retry.dtype == torch.uint8 and retry.numel() == F and retry.is_contiguous()),
+                         "fit: retry must be (F,) uint8")
+                N.check(N.lib.egl_fit_homography_masked(_ptr(kp.xy), _ptr(kp.order), _ptr(kp.count), F, mode, K, _ptr(hyp), seed,
+                                                        float(thr), float(confidence), _ptr(r.H), _ptr(r.used_mask),
+                                                        _ptr(r.inlier_mask), _ptr(r.status), _ptr(r.info), _ptr(sched), _ptr(retry),
+                                                        _stream()), "egl_fit_homography_masked")
         return r
+
+    # -- F4: keypoint propagation ----------------------------------------------------------
+    def gray_pyramid(self, frames: torch.Tensor, max_level: int = 2, out: torch.Tensor | None = None) -> torch.Tensor:
+        """frames (F, H, W, 3) uint8 BGR on the device -> (F, egl_pyramid_bytes) uint8 gray pyramids."""
+        _require(frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3 and frames.is_cuda,
+                 "gray_pyramid: frames must be a CUDA uint8 tensor of shape (F, H, W, 3)")
+        _require(frames.stride(3) == 1 and frames.stride(2) == 3, "gray_pyramid: pixels must be packed B,G,R bytes")
+        F, H, W, _ = frames.shape
+        nbytes = int(N.lib.egl_pyramid_bytes(H, W, max_level))
+        _require(nbytes > 0, "gray_pyramid: bad frame size / max_level")
+        if out is None:
+            out = torch.empty((F, nbytes), dtype=torch.uint8, device=frames.device)
+        with torch.cuda.device(frames.device):
+            N.check(N.lib.egl_gray_pyramid(_ptr(frames), F, H, W, frames.stride(1), frames.stride(0) if F > 1 else H * frames.stride(1),
+                                           max_level, _ptr(out), _stream()), "egl_gray_pyramid")
+        return out
+
+    def track(self, pyr: torch.Tensor, height: int, width: int, prev: KeypointSet, prev0: int, next0: int, frame_step: int,
+              max_level: int = 2, max_count: int = 10, eps: float = 0.03):
+        """cv2.calcOpticalFlowPyrLK for n = prev.n_frames frame pairs (prev0 + p*step -> next0 + p*step).
+        Returns (new_pts (n, 64, 2) float32, status (n, 64) uint8)."""
+        n = prev.n_frames
+        new_pts = torch.empty((n, N.ORDER_STRIDE, 2), dtype=torch.float32, device=pyr.device)
+        status = torch.empty((n, N.ORDER_STRIDE), dtype=torch.uint8, device=pyr.device)
+        _require(pyr.dtype == torch.uint8 and pyr.is_contiguous() and pyr.dim() == 2
+                 and pyr.shape[1] == int(N.lib.egl_pyramid_bytes(height, width, max_level)), "track: pyr does not match the frame size")
+        last = max(prev0, next0) + (n - 1) * frame_step
+        _require(0 <= min(prev0, next0) and last < pyr.shape[0], "track: frame index out of range")
+        with torch.cuda.device(pyr.device):
+            N.check(N.lib.egl_track_keypoints(_ptr(pyr), height, width, max_level, _ptr(prev.xy), _ptr(prev.order), _ptr(prev.count), n,
+                                              prev0, next0, frame_step, max_count, float(eps), _ptr(new_pts), _ptr(status), _stream()),
+                    "egl_track_keypoints")
+        return new_pts, status
+
+    def filter_flow(self, frames: torch.Tensor, hue0: int, frame_step: int, prev: KeypointSet, new_pts: torch.Tensor,
+                    status: torch.Tensor, out: KeypointSet) -> KeypointSet:
+        n = prev.n_frames
+        F, H, W, _ = frames.shape
+        _require(0 <= hue0 and hue0 + (n - 1) * frame_step < F, "filter_flow: frame index out of range")
+        with torch.cuda.device(frames.device):
+            N.check(N.lib.egl_filter_flow(_ptr(frames), H, W, frames.stride(1), frames.stride(0) if F > 1 else H * frames.stride(1), hue0,
+                                          frame_step, _ptr(prev.xy), _ptr(prev.order), _ptr(prev.count), _ptr(new_pts), _ptr(status), n,
+                                          _ptr(out.xy), _ptr(out.order), _ptr(out.count), _ptr(out.src), _stream()), "egl_filter_flow")
+        return out
+
+    def merge(self, a: KeypointSet, b: KeypointSet, apply: torch.Tensor | None = None) -> KeypointSet:
+        """a = {**a, **b} per frame, in place."""
+        with torch.cuda.device(a.xy.device):
+            N.check(N.lib.egl_merge_keypoints(_ptr(a.xy), _ptr(a.order), _ptr(a.count), _ptr(a.src), _ptr(b.xy), _ptr(b.order),
+                                              _ptr(b.count), _ptr(b.src), _ptr(apply), a.n_frames, _stream()), "egl_merge_keypoints")
+        return a
+
+    def calibrate(self, frames: torch.Tensor, frame0: int, frame_step: int, kp: KeypointSet, err: torch.Tensor) -> KeypointSet:
+        F, H, W, _ = frames.shape
+        n = kp.n_frames
+        _require(0 <= frame0 and frame0 + (n - 1) * frame_step < F, "calibrate: frame index out of range")
+        _require(err.dtype == torch.int32 and err.numel() == n, "calibrate: err must be (n,) int32")
+        with torch.cuda.device(frames.device):
+            N.check(N.lib.egl_calibrate_keypoints(_ptr(frames), H, W, frames.stride(1), frames.stride(0) if F > 1 else H * frames.stride(1),
+                                                  frame0, frame_step, _ptr(kp.xy), _ptr(kp.order), _ptr(kp.count), _ptr(kp.src), _ptr(err),
+                                                  n, _stream()), "egl_calibrate_keypoints")
+        return kp
+
+    def commit(self, kp: KeypointSet, fit: FitResult, sched: torch.Tensor | None, retry: torch.Tensor | None,
+               fit_ok: torch.Tensor | None) -> None:
+        with torch.cuda.device(kp.xy.device):
+            N.check(N.lib.egl_commit_fit(_ptr(kp.order), _ptr(kp.count), _ptr(kp.src), _ptr(fit.status), _ptr(fit.inlier_mask),
+                                         _ptr(sched), _ptr(retry), _ptr(fit_ok), kp.n_frames, _stream()), "egl_commit_fit")
 
     # -- cadence ----------------------------------------------------------------------------
     def select(self, status: torch.Tensor, interval: int = 1, carry_in: int = -1):

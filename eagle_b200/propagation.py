@@ -1,0 +1,273 @@
+"""Sparse keypoint cadence on the GPU: network keypoints every ``keypoint_interval`` frames, Lucas-Kanade
+propagation in between (coordinate_model.py:206, 277-367, 419-478, 520-555).
+
+How the reference's frame loop is laid out here
+  * A *chain* is one network frame (the "head", i % keypoint_interval == 0) plus the frames up to the
+    next head.  Inside a chain every frame depends on the one before (flow from its final keypoints);
+    chains are independent of each other unless a head decodes fewer than four landmarks (:287-311)
+    or a failed fit leaves the retry flag set across the chain boundary (:333,:350-367).
+  * All per-frame state lives in HBM as (step, chain, ...) arrays, so "advance every chain by one
+    frame" is one launch of each kernel over a contiguous slice: track -> filter -> synthesise ->
+    [calibrate] -> fit (only where the cadence asks) -> commit.  A clip needs keypoint_interval such
+    rounds, whatever its length.
+  * That parallel pass speculates "heads are independent, no retry flag crosses a boundary".  The few
+    chains for which that turns out wrong are re-run one by one, in order, with the same kernels on
+    single-chain slices -- the reference's sequential semantics, exactly.
+  * The host sees one small D2H per round (the keypoint counts: a frame whose flow kept fewer than
+    four points asks the network for that frame, :316-320).
+
+Nothing here computes on the CPU; the arithmetic is in csrc/flow.cu, fit.cu, synthesize.cu.
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .engine import FitResult, GeometryEngine, KeypointSet
+from .pitch import NUM_LANDMARKS
+
+LK_MAX_LEVEL, LK_MAX_COUNT, LK_EPS = 2, 10, 0.03  # lk_params, coordinate_model.py:65
+
+
+class _Sets:
+    """(step, chain) arrays of keypoint sets and fit results."""
+
+    def __init__(self, k: int, nc: int, dev):
+        z = lambda *shape, dtype: torch.zeros(shape, dtype=dtype, device=dev)
+        self.xy = z(k, nc, NUM_LANDMARKS, 2, dtype=torch.int32)
+        self.order = z(k, nc, N.ORDER_STRIDE, dtype=torch.uint8)
+        self.count = z(k, nc, 2, dtype=torch.int32)
+        self.src = z(k, nc, N.ORDER_STRIDE, dtype=torch.uint8)
+        self.H = z(k, nc, 9, dtype=torch.float64)
+        self.used = z(k, nc, dtype=torch.int64)
+        self.inl = z(k, nc, dtype=torch.int64)
+        self.status = torch.full((k, nc), N.FIT_SKIPPED, dtype=torch.int32, device=dev)
+        self.info = z(k, nc, 4, dtype=torch.int32)
+        self.fit_ok = z(k, nc, dtype=torch.uint8)
+        self.cal_err = z(k, nc, dtype=torch.int32)
+        self.retry = z(nc, dtype=torch.uint8)
+
+    def kp(self, s: int, c0: int, c1: int) -> KeypointSet:
+        return KeypointSet(None, None, self.xy[s, c0:c1], self.order[s, c0:c1], self.count[s, c0:c1], self.src[s, c0:c1])
+
+    def fit(self, s: int, c0: int, c1: int) -> FitResult:
+        return FitResult(self.H[s, c0:c1], self.used[s, c0:c1], self.inl[s, c0:c1], self.status[s, c0:c1], self.info[s, c0:c1])
+
+
+def _new_set(n: int, dev) -> KeypointSet:
+    return KeypointSet(torch.empty((n, NUM_LANDMARKS), dtype=torch.int32, device=dev), torch.empty((n, NUM_LANDMARKS), dtype=torch.float32, device=dev),
+                       torch.zeros((n, NUM_LANDMARKS, 2), dtype=torch.int32, device=dev), torch.zeros((n, N.ORDER_STRIDE), dtype=torch.uint8, device=dev),
+                       torch.zeros((n, 2), dtype=torch.int32, device=dev), torch.zeros((n, N.ORDER_STRIDE), dtype=torch.uint8, device=dev))
+
+
+def _clone(a: KeypointSet) -> KeypointSet:
+    return KeypointSet(None, None, a.xy.clone(), a.order.clone(), a.count.clone(), a.src.clone())
+
+
+def _assign(dst: KeypointSet, src: KeypointSet) -> None:
+    dst.xy.copy_(src.xy); dst.order.copy_(src.order); dst.count.copy_(src.count); dst.src.copy_(src.src)
+
+
+class PropagatedPath:
+    """The frame loop of get_coordinates for any keypoint / homography cadence, frames resident in HBM."""
+
+    def __init__(self, engine: GeometryEngine, keypoint_conf: float = 0.3, fit_mode: int = N.FIT_CV2_COMPAT, max_iters: int = 2000,
+                 thr: float = 5.0):
+        self.e = engine
+        self.keypoint_conf = keypoint_conf
+        self.fit_mode, self.max_iters, self.thr = fit_mode, max_iters, thr
+        self.stats = {}
+
+    # ---------------------------------------------------------------------------------------------
+    def run(self, frames: torch.Tensor, head_heatmaps: torch.Tensor, detect: Callable[[int], torch.Tensor] | None,
+            keypoint_interval: int, homography_interval: int, calibration: bool = False) -> dict:
+        """frames (F, H, W, 3) uint8 BGR CUDA; head_heatmaps (ceil(F/k), 57, h, w) float32 CUDA = the network's
+        output for frames 0, k, 2k, ...; detect(i) -> (1, 57, h, w) heatmaps of frame i on demand.
+
+        Returns device tensors in frame order: xy, order, count, src (the "Keypoints" of every frame),
+        H (F, 9), fit_ok (F,), h_index (F,) and host-side counters in ``self.stats``."""
+        e = self.e
+        F, Himg, Wimg, _ = frames.shape
+        k = int(keypoint_interval)
+        nc = (F + k - 1) // k
+        dev = frames.device
+        assert head_heatmaps.shape[0] == nc, "one heatmap stack per chain head"
+        self.frames, self.k, self.F, self.Himg, self.Wimg = frames, k, F, Himg, Wimg
+        self.calibration = calibration
+        self.detect = detect
+        self.pyr = e.gray_pyramid(frames, LK_MAX_LEVEL)
+        st = self.st = _Sets(k, nc, dev)
+        idx = np.arange(k)[:, None] + np.arange(nc)[None, :] * k
+        self.sched_h = ((idx % homography_interval) == 0) & (idx < F)
+        self.sched = torch.from_numpy(self.sched_h.astype(np.uint8)).to(dev)
+        self.extra_mem: dict[int, KeypointSet] = {}     # entries the first-frame rescue wrote into the reference's `mem`
+        self.detected: dict[int, KeypointSet] = {}      # cache of on-demand detections (not semantic: `mem[i]` is only read at frame i)
+        self.stats = {"fallback_frames": 0, "repaired_chains": 0, "first_frame_rescue": False}
+
+        # heads: decode straight into step 0 of the state, keep a pristine copy (the reference's `mem`)
+        tmp = _new_set(nc, dev)
+        e.decode(head_heatmaps, Wimg, Himg, self.keypoint_conf, out=KeypointSet(tmp.flat, tmp.score, st.xy[0], st.order[0], st.count[0]))
+        self.heads = _clone(st.kp(0, 0, nc))
+        head_cnt = self.heads.count[:, 0].cpu().numpy()
+
+        # ---- parallel pass: every chain advances one frame per round
+        for s in range(k):
+            n_s = (F - s + k - 1) // k
+            if n_s <= 0:
+                break
+            if s > 0:
+                self._flow(s, 0, n_s)
+                cnt = st.count[s, :n_s, 0].cpu().numpy()
+                for c in np.nonzero(cnt < 4)[0]:
+                    self._fallback(s, int(c))
+            self._finish(s, 0, n_s)
+
+        # ---- repairs, in frame order
+        rerun_upto = -1
+        if head_cnt[0] < 4 and F > 1:
+            rerun_upto = self._rescue_first_frame()
+        retry_final = st.retry.cpu().numpy().copy()
+        for c in range(nc):
+            incoming = int(retry_final[c - 1]) if c > 0 else 0
+            head = self.extra_mem.get(c * k)
+            cnt_c = int(head.count[0, 0]) if head is not None else int(head_cnt[c])
+            need = c <= rerun_upto or (c > 0 and (cnt_c < 4 or (incoming and not self.sched_h[0, c])))
+            if need:
+                self._run_chain(c, incoming)
+                retry_final[c] = int(st.retry[c].item())
+                self.stats["repaired_chains"] += 1
+
+        # ---- back to frame order (chain-major == frame order), cadence lookup of the H each frame uses
+        fo = lambda t: t.transpose(0, 1).reshape((nc * k,) + tuple(t.shape[2:]))[:F].contiguous()
+        if calibration:
+            bad = torch.nonzero(fo(st.cal_err))
+            if bad.numel() > 0:
+                # coordinate_model.py:548 -- grid_hsv[OFFSET, OFFSET] on a block clipped at the top / left edge
+                raise IndexError(f"index 3 is out of bounds for axis 0 with size 3 (calibrate_keypoints, frame {int(bad[0, 0])})")
+        out = {"xy": fo(st.xy), "order": fo(st.order), "count": fo(st.count), "src": fo(st.src), "H": fo(st.H), "fit_ok": fo(st.fit_ok),
+               "status": fo(st.status), "inlier_mask": fo(st.inl)}
+        sel_status = torch.where(out["fit_ok"] != 0, torch.full_like(out["status"], N.FIT_OK), torch.full_like(out["status"], N.FIT_NO_MODEL))
+        out["h_index"], _ = e.select(sel_status, 1)
+        return out
+
+    # ---------------------------------------------------------------------------------------------
+    def _flow(self, s: int, c0: int, c1: int) -> None:
+        """calculate_optical_flow(frame_i, gray_{i-1}, keypoints_{i-1}, gray_i) for the frames i = c*k + s (:315)."""
+        e, st, k = self.e, self.st, self.k
+        prev = st.kp(s - 1, c0, c1)
+        p0, n0 = c0 * k + s - 1, c0 * k + s
+        pts, status = e.track(self.pyr, self.Himg, self.Wimg, prev, p0, n0, k, LK_MAX_LEVEL, LK_MAX_COUNT, LK_EPS)
+        e.filter_flow(self.frames, n0, k, prev, pts, status, st.kp(s, c0, c1))
+
+    def _flow_single(self, prev: KeypointSet, prev_frame: int, next_frame: int, hue_frame: int) -> KeypointSet:
+        e = self.e
+        out = _new_set(1, self.frames.device)
+        pts, status = e.track(self.pyr, self.Himg, self.Wimg, prev, prev_frame, next_frame, 1, LK_MAX_LEVEL, LK_MAX_COUNT, LK_EPS)
+        e.filter_flow(self.frames, hue_frame, 1, prev, pts, status, out)
+        return out
+
+    def _detect_set(self, i: int) -> KeypointSet:
+        """mem.get(i, self.detect_keypoints(frame)) (:318): the network on one frame, decoded."""
+        if i in self.extra_mem:
+            return self.extra_mem[i]
+        if i in self.detected:
+            return self.detected[i]
+        if i % self.k == 0:
+            c = i // self.k
+            return KeypointSet(None, None, self.heads.xy[c:c + 1], self.heads.order[c:c + 1], self.heads.count[c:c + 1], self.heads.src[c:c + 1])
+        if self.detect is None:
+            raise RuntimeError(f"frame {i}: optical flow kept fewer than 4 keypoints and no keypoint network is attached for the "
+                               "fallback detection (coordinate_model.py:316-320)")
+        hm = self.detect(i)
+        d = _new_set(1, self.frames.device)
+        self.e.decode(hm, self.Wimg, self.Himg, self.keypoint_conf, out=d)
+        self.detected[i] = d
+        self.stats["fallback_frames"] += 1
+        return d
+
+    def _fallback(self, s: int, c: int) -> None:
+        """:316-320,324: keypoints = {**detected, **flowed}, then {**keypoints, **detected}."""
+        e, st = self.e, self.st
+        d = self._detect_set(c * self.k + s)
+        a = _clone(d)
+        cur = st.kp(s, c, c + 1)
+        e.merge(a, cur)
+        e.merge(a, d)
+        _assign(cur, a)
+
+    def _finish(self, s: int, c0: int, c1: int) -> None:
+        """:326-367 for frames i = c*k + s: synthesis, calibration, fit where the cadence asks, inlier commit."""
+        e, st, k = self.e, self.st, self.k
+        kp = st.kp(s, c0, c1)
+        e.synthesize(kp)
+        if self.calibration:
+            st.cal_err[s, c0:c1].zero_()
+            e.calibrate(self.frames, c0 * k + s, k, kp, st.cal_err[s, c0:c1])
+        fit = st.fit(s, c0, c1)
+        sched, retry = self.sched[s, c0:c1], st.retry[c0:c1]
+        e.fit(kp, mode=self.fit_mode, K=self.max_iters, thr=self.thr, out=fit, sched=sched, retry=retry)
+        e.commit(kp, fit, sched, retry, st.fit_ok[s, c0:c1])
+
+    def _run_chain(self, c: int, incoming_retry: int) -> None:
+        """One chain, frame after frame, with the true predecessor state (the reference's loop, literally)."""
+        e, st, k, F = self.e, self.st, self.k, self.F
+        st.retry[c] = incoming_retry
+        i = c * k
+        cur = st.kp(0, c, c + 1)
+        head = KeypointSet(None, None, self.heads.xy[c:c + 1], self.heads.order[c:c + 1], self.heads.count[c:c + 1], self.heads.src[c:c + 1])
+        if c == 0:
+            _assign(cur, head)                      # :285 keypoints = decoded; the rescue only rewrote mem
+            if 0 in self.extra_mem:
+                e.merge(cur, self.extra_mem[0])     # :324
+        else:
+            m = self.extra_mem.get(i, head)         # :285 mem.get(i)
+            _assign(cur, m)
+            if int(m.count[0, 0]) < 4:              # :308-311
+                flowed = self._flow_single(st.kp(k - 1, c - 1, c), i - 1, i, i)
+                e.merge(cur, flowed)
+                e.merge(cur, m)                     # :324
+        self._finish(0, c, c + 1)
+        for s in range(1, k):
+            i = c * k + s
+            if i >= F:
+                break
+            self._flow(s, c, c + 1)
+            if int(st.count[s, c, 0].item()) < 4:
+                self._fallback(s, c)
+            elif i in self.extra_mem:
+                e.merge(st.kp(s, c, c + 1), self.extra_mem[i])  # :322,:324
+            self._finish(s, c, c + 1)
+
+    def _rescue_first_frame(self) -> int:
+        """:288-307: frame 0 decoded < 4 landmarks -- find the first later frame with >= 4, flow its keypoints
+        backwards to frame 0 and merge them into ``mem``.  Returns the last chain that has to be re-run."""
+        F, k = self.F, self.k
+        self.stats["first_frame_rescue"] = True
+        prev = None
+        j = 0
+        for j in range(1, F):
+            d = self._detect_set(j)
+            self.extra_mem.setdefault(j, d)
+            if int(d.count[0, 0]) >= 4:
+                prev = d
+                break
+        if prev is None:
+            return -1
+        next_idx = j
+        for jj in range(j - 1, -1, -1):
+            flowed = self._flow_single(prev, jj, next_idx, jj)  # (prev_frame, prev_gray) = frame jj, curr_gray = frame jj+1 (:303)
+            if int(flowed.count[0, 0]) > 0:
+                prev = flowed
+            base = _clone(prev)
+            existing = self.extra_mem.get(jj)
+            if existing is None and jj % k == 0:
+                c = jj // k
+                existing = KeypointSet(None, None, self.heads.xy[c:c + 1], self.heads.order[c:c + 1], self.heads.count[c:c + 1], self.heads.src[c:c + 1])
+            if existing is not None:
+                self.e.merge(base, existing)
+            self.extra_mem[jj] = base
+            next_idx = jj
+        return j // k

@@ -43,6 +43,12 @@ extern "C" {
 #define EGL_FIT_OK 0         /* H, masks valid */
 #define EGL_FIT_FEW_POINTS 1 /* < 4 on-plane landmarks: reference sets compute_homography=True (:350-352) */
 #define EGL_FIT_NO_MODEL 2   /* RANSAC found no model (cv2.findHomography returned None, :363-367) */
+#define EGL_FIT_SKIPPED 3    /* egl_fit_homography_masked: the cadence did not ask for a fit on this frame */
+
+/* kp_src[] values: which Python type the reference holds a keypoint value in (it reaches the JSON) */
+#define EGL_KP_PY_INT 0    /* tuple of int: decoded (:248) or synthesised (:179) */
+#define EGL_KP_NUMPY_INT 1 /* tuple of numpy int64: optical flow (:476) or calibration (:553) */
+#define EGL_KP_FLOAT 2     /* list of float: inlier of a successful fit (:361) */
 
 /* fit modes */
 #define EGL_FIT_CV2_COMPAT 1 /* OpenCV's RNG, sampling, adaptive stopping: picks the model cv2 picks */
@@ -149,6 +155,77 @@ int egl_select_homography(const int32_t *status, int F, int interval, int carry_
 int egl_project_points(const double *H, const int32_t *h_index, const float *pts, const int32_t *npts, int F, int P,
                        int img_w, int img_h, float *out_f, int64_t *out_i, uint8_t *inb, double *bounds,
                        void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * F4  keypoint propagation between network frames (the sparse keypoint cadence, coordinate_model.py:206).
+ *
+ * A "keypoint set" is the per-frame dict the reference carries: kp_xy [n][57][2] int32 (by channel),
+ * kp_order [n][64] uint8 (insertion order), kp_count [n][2] int32 ({entries, -}), kp_src [n][64] uint8
+ * (EGL_KP_* by channel).  Frames are addressed as  index0 + p * frame_step  (p = 0..n-1) inside a
+ * device array of frames / pyramids, so that one call advances every chain of a clip by one frame.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Bytes per frame of the gray pyramid egl_gray_pyramid writes (levels stop before one is <= 15 px). */
+int64_t egl_pyramid_bytes(int H, int W, int max_level);
+
+/*
+ * cv2.cvtColor(frame, COLOR_BGR2GRAY) (coordinate_model.py:281) + the image pyramid
+ * cv2.calcOpticalFlowPyrLK builds from it (cv2.pyrDown per level), bit-exact.
+ *   pyr  [F][egl_pyramid_bytes] uint8: level 0 (H x W), level 1 ((H+1)/2 x (W+1)/2), ... each 16-byte aligned
+ */
+int egl_gray_pyramid(const uint8_t *frames, int F, int H, int W, size_t row_stride, size_t frame_stride, int max_level,
+                     uint8_t *pyr, void *stream);
+
+/*
+ * cv2.calcOpticalFlowPyrLK(prev_gray, curr_gray, prev_points, None, winSize=(15,15), maxLevel,
+ * criteria=(EPS|COUNT, max_count, eps)) (coordinate_model.py:431-435, lk_params :65), bit-exact with
+ * OpenCV's SSE build (see oracle/optflow.py).  The points of pair p are the entries of keypoint set p.
+ *   new_pts [n][64][2] float32, status [n][64] uint8 (1 = found)
+ */
+int egl_track_keypoints(const uint8_t *pyr, int H, int W, int max_level, const int32_t *kp_xy, const uint8_t *kp_order,
+                        const int32_t *kp_count, int n, int prev0, int next0, int frame_step, int max_count, double eps,
+                        float *new_pts, uint8_t *status, void *stream);
+
+/*
+ * The rest of calculate_optical_flow (coordinate_model.py:438-478): drop lost points, movers with a
+ * z-score > 2 (float32 numpy statistics) and points whose mean 3x3 hue changed by more than 25, emit
+ * the survivors as a new keypoint set (labels taken by position in the status-filtered list, :446).
+ *   frames: BGR uint8; the hue is read from frame hue0 + p * frame_step (the `frame` argument of :419)
+ */
+int egl_filter_flow(const uint8_t *frames, int H, int W, size_t row_stride, size_t frame_stride, int hue0, int frame_step,
+                    const int32_t *prev_xy, const uint8_t *prev_order, const int32_t *prev_count, const float *new_pts,
+                    const uint8_t *status, int n, int32_t *out_xy, uint8_t *out_order, int32_t *out_count,
+                    uint8_t *out_src, void *stream);
+
+/* a = {**a, **b} per frame (coordinate_model.py:311,320,322,324); apply[n] optional (0 = leave frame alone);
+ * b_src NULL = EGL_KP_PY_INT. */
+int egl_merge_keypoints(int32_t *a_xy, uint8_t *a_order, int32_t *a_count, uint8_t *a_src, const int32_t *b_xy,
+                        const uint8_t *b_order, const int32_t *b_count, const uint8_t *b_src, const uint8_t *apply, int n,
+                        void *stream);
+
+/*
+ * CoordinateModel.calibrate_keypoints (coordinate_model.py:520-555): a keypoint whose HSV value is
+ * below 150 moves to the brightest pixel of frame[y-3:y+3, x-3:x+3].  err[n] is set to 1 for frames
+ * on which the reference raises IndexError (:548, a dim keypoint in row or column 0).
+ */
+int egl_calibrate_keypoints(const uint8_t *frames, int H, int W, size_t row_stride, size_t frame_stride, int frame0,
+                            int frame_step, int32_t *kp_xy, const uint8_t *kp_order, const int32_t *kp_count,
+                            uint8_t *kp_src, int32_t *err, int n, void *stream);
+
+/* egl_fit_homography restricted to the frames with sched[f] | retry[f] (retry may be NULL): the
+ * cadence test of coordinate_model.py:333.  Other frames get status EGL_FIT_SKIPPED. */
+int egl_fit_homography_masked(const int32_t *kp_xy, const uint8_t *kp_order, const int32_t *kp_count, int F, int mode,
+                              int K, const uint8_t *hyp, uint64_t seed, double thr, double confidence, double *H,
+                              uint64_t *used_mask, uint64_t *inlier_mask, int32_t *status, int32_t *info,
+                              const uint8_t *sched, const uint8_t *retry, void *stream);
+
+/*
+ * What follows a fit attempt (coordinate_model.py:350-367): on success the keypoint set shrinks to
+ * the inliers (they become the "Keypoints" of the frame and the seed of the next flow step) and
+ * retry[f] clears; on failure retry[f] is set.  fit_ok[f] = 1 where this frame produced a new H.
+ */
+int egl_commit_fit(uint8_t *kp_order, int32_t *kp_count, uint8_t *kp_src, const int32_t *status,
+                   const uint64_t *inlier_mask, const uint8_t *sched, uint8_t *retry, uint8_t *fit_ok, int n, void *stream);
 
 #ifdef __cplusplus
 }

@@ -181,12 +181,30 @@ def resize_fixture():
     print("resize_cv2", list(out))
 
 
+def flow_fixture(name, n_frames, width, height, seed, fps, num_homography, num_keypoint_detection, pan_px):
+    """Sparse keypoint cadence (main.py:27 uses num_keypoint_detection=3): a rendered clip with a moving
+    camera, so that the reference's Lucas-Kanade propagation, its filters and (second run) the brightness
+    calibration all do real work.  The frames are reproducible from the seed; their hash is stored."""
+    clip = synthetic.make_flow_clip(n_frames, width, height, seed=seed, pan_px=pan_px)
+    out = {}
+    for cal in (False, True):
+        res, rec = ref_harness.run_reference(clip["frames"], clip["heatmaps"], clip["objects"], fps=fps, num_homography=num_homography,
+                                             num_keypoint_detection=num_keypoint_detection, calibration=cal)
+        out["result_json_cal" if cal else "result_json"] = json.dumps(res, default=float, sort_keys=True)
+        print(name, "calibration", cal, "fits", len(rec.fits), "keypoints/frame", [len(res[i]["Keypoints"]) for i in res])
+    stamped = np.stack(ref_harness.stamp_frames(clip["frames"]))
+    np.savez_compressed(os.path.join(GOLDEN, name), n_frames=n_frames, width=width, height=height, seed=seed, fps=fps,
+                        num_homography=num_homography, num_keypoint_detection=num_keypoint_detection, pan_px=pan_px,
+                        frames_sha256=sha(stamped), heatmaps_sha256=sha(clip["heatmaps"]), **out)
+
+
 def main():
     warnings.simplefilter("ignore")
     os.makedirs(GOLDEN, exist_ok=True)
     clip_fixture("ref_clip_720p.npz", 8, 1280, 720, seed=7, ghost_prob=0.05)
     clip_fixture("ref_clip_1080p.npz", 6, 1920, 1080, seed=8, ghost_prob=0.10)
     cadence_fixture("ref_cadence_720p.npz", 17, 1280, 720, seed=9, fps=5, num_homography=1, blank=[])
+    flow_fixture("ref_flow_360p.npz", 26, 640, 360, seed=31, fps=24, num_homography=1, num_keypoint_detection=3, pan_px=2.0)
     decode_fixture()
     find_homography_fixture()
     resize_fixture()

@@ -347,8 +347,6 @@ def test_drop_in_get_coordinates_with_cadence(golden_dir):
     # same through the lower-level path object
     got2 = GeometryPath("cuda:0").run(hm, clip["objects"], w, h, fps=int(g["fps"]), homography_interval=5)
     assert json.dumps(got2, default=float, sort_keys=True) == str(g["result_json"])
-    with pytest.raises(NotImplementedError):
-        model.get_coordinates(list(clip["frames"][:2]), fps=25, num_homography=1, num_keypoint_detection=3)
 
 
 def test_refit_thread_and_warp_kernels_agree():

@@ -137,3 +137,17 @@ def test_propagated_pipeline_json_identical_to_reference(fps, nh, nk, cal):
     mine = P.get_coordinates_propagated(RH.stamp_frames(c["frames"]), c["heatmaps"], c["objects"], fps, nh, nk, calibration=cal)
     assert json.dumps(ref, default=float) == json.dumps(mine, default=float)
     assert min(len(ref[i]["Keypoints"]) for i in ref) >= 4
+
+
+@pytest.mark.parametrize("cal", [False, True])
+def test_oracle_reproduces_flow_golden(golden_dir, cal):
+    """tests/golden/ref_flow_360p.npz holds what the unmodified reference returned (oracle/make_golden.py)."""
+    import hashlib
+    import os
+    g = np.load(os.path.join(golden_dir, "ref_flow_360p.npz"))
+    clip = S.make_flow_clip(int(g["n_frames"]), int(g["width"]), int(g["height"]), seed=int(g["seed"]), pan_px=float(g["pan_px"]))
+    frames = RH.stamp_frames(clip["frames"])
+    assert hashlib.sha256(np.stack(frames).tobytes()).hexdigest() == str(g["frames_sha256"])
+    mine = P.get_coordinates_propagated(frames, clip["heatmaps"], clip["objects"], int(g["fps"]), int(g["num_homography"]),
+                                        int(g["num_keypoint_detection"]), calibration=cal)
+    assert json.dumps(mine, default=float, sort_keys=True) == str(g["result_json_cal" if cal else "result_json"])
