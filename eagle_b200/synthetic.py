@@ -260,3 +260,30 @@ def make_flow_clip(n_frames: int, width: int, height: int, seed: int = 0, hide_p
         objs.append(sample_objects(cams[i], width, height, rng))
         frames[i] = render_pitch_frame(cams[i], width, height, rng)
     return {"cameras": cams, "heatmaps": heat, "objects": objs, "frames": frames, "width": width, "height": height}
+
+
+def tiled_flow_clip_device(n_frames: int, keypoint_interval: int, device, paths: int = 3, seed: int = 0, out_frames=None):
+    """A long 1080p clip for timing the keypoint-propagation path, built on the device: ``paths`` rendered
+    camera moves of ``keypoint_interval`` frames each (540p renders, upsampled 2x), tiled chain after chain
+    with +-2 levels of per-frame noise so that no two frames are equal.  Returns (frames (F,1080,1920,3) uint8,
+    head heatmaps (ceil(F/k),57,135,240) float32), both CUDA tensors."""
+    import torch
+    k = keypoint_interval
+    pool_f, pool_h = [], []
+    for p in range(paths):
+        c = make_flow_clip(k, 960, 540, seed=seed + p, pan_px=1.5)
+        fr = torch.from_numpy(c["frames"]).to(device).permute(0, 3, 1, 2).float()
+        fr = torch.nn.functional.interpolate(fr, scale_factor=2, mode="bilinear", align_corners=False)
+        pool_f.append(fr.round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous())
+        pool_h.append(torch.from_numpy(c["heatmaps"][0:1]).to(device))
+    nc = (n_frames + k - 1) // k
+    frames = out_frames if out_frames is not None else torch.empty((n_frames, 1080, 1920, 3), dtype=torch.uint8, device=device)
+    g = torch.Generator(device=device); g.manual_seed(seed)
+    for c in range(nc):
+        n = min(k, n_frames - c * k)
+        src = pool_f[c % paths][:n]
+        noise = torch.randint(-2, 3, src.shape, device=device, generator=g, dtype=torch.int16)
+        frames[c * k:c * k + n] = (src.to(torch.int16) + noise).clamp(0, 255).to(torch.uint8)
+    heads = torch.cat([pool_h[c % paths] for c in range(nc)])
+    heads = (heads + torch.rand(heads.shape, device=device, generator=g) * 0.01).clamp(0, 1).contiguous()
+    return frames, heads

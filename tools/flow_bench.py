@@ -23,24 +23,7 @@ sys.path.insert(0, ROOT)
 
 def build_clip(torch, dev, F, k, paths, seed=0):
     from eagle_b200 import synthetic
-    pool_f, pool_h = [], []
-    for p in range(paths):
-        c = synthetic.make_flow_clip(k, 960, 540, seed=seed + p, pan_px=1.5)
-        fr = torch.from_numpy(c["frames"]).to(dev).permute(0, 3, 1, 2).float()
-        fr = torch.nn.functional.interpolate(fr, scale_factor=2, mode="bilinear", align_corners=False)
-        pool_f.append(fr.round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous())
-        pool_h.append(torch.from_numpy(c["heatmaps"][0:1]).to(dev))
-    nc = (F + k - 1) // k
-    frames = torch.empty((F, 1080, 1920, 3), dtype=torch.uint8, device=dev)
-    g = torch.Generator(device=dev); g.manual_seed(seed)
-    for c in range(nc):
-        n = min(k, F - c * k)
-        src = pool_f[c % paths][:n]
-        noise = torch.randint(-2, 3, src.shape, device=dev, generator=g, dtype=torch.int16)
-        frames[c * k:c * k + n] = (src.to(torch.int16) + noise).clamp(0, 255).to(torch.uint8)
-    heads = torch.cat([pool_h[c % paths] for c in range(nc)])
-    heads = (heads + torch.rand(heads.shape, device=dev, generator=g) * 0.01).clamp(0, 1).contiguous()
-    return frames, heads
+    return synthetic.tiled_flow_clip_device(F, k, dev, paths, seed)
 
 
 def main():
@@ -50,6 +33,7 @@ def main():
     ap.add_argument("--paths", type=int, default=3)
     ap.add_argument("--fps", type=int, default=25)
     ap.add_argument("--calibration", action="store_true")
+    ap.add_argument("--streams", type=int, default=1)
     args = ap.parse_args()
     import torch
     from eagle_b200.engine import GeometryEngine
@@ -61,7 +45,7 @@ def main():
     frames, heads = build_clip(torch, dev, args.frames, k, args.paths)
     torch.cuda.synchronize()
     build_s = time.time() - t0
-    prop = PropagatedPath(e)
+    prop = PropagatedPath(e, n_streams=args.streams)
     foot = torch.rand((args.frames, 27, 2), device=dev) * torch.tensor([1920.0, 1080.0], device=dev)
     cnt = torch.full((args.frames,), 25, dtype=torch.int32, device=dev)
 
