@@ -47,8 +47,10 @@ lib.egl_merge_keypoints.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
 lib.egl_calibrate_keypoints.argtypes = [_vp, _i, _i, _sz, _sz, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
 lib.egl_fit_homography_masked.argtypes = [_vp, _vp, _vp, _i, _i, _i, _vp, _u64, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
 lib.egl_commit_fit.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]
-for _name in ("egl_gray_pyramid", "egl_track_keypoints", "egl_filter_flow", "egl_merge_keypoints", "egl_calibrate_keypoints",
-              "egl_fit_homography_masked", "egl_commit_fit"):
+lib.egl_refine_keypoints.argtypes = [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]
+lib.egl_fit_homography_subpixel.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _u64, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp]
+for _name in ("egl_refine_keypoints", "egl_fit_homography_subpixel", "egl_gray_pyramid", "egl_track_keypoints", "egl_filter_flow", "egl_merge_keypoints", "egl_calibrate_keypoints",
+              "egl_fit_homography_masked", "egl_commit_fit", "egl_refine_keypoints", "egl_fit_homography_subpixel"):
     getattr(lib, _name).restype = _i
 for _name in ("egl_preprocess_u8", "egl_decode_heatmaps", "egl_decode_logits", "egl_synthesize_keypoints", "egl_fit_homography",
               "egl_select_homography", "egl_project_points"):
@@ -57,7 +59,7 @@ for _name in ("egl_preprocess_u8", "egl_decode_heatmaps", "egl_decode_logits", "
 EXPORTS = ("egl_version", "egl_last_error", "egl_sm_count", "egl_preprocess_u8", "egl_decode_heatmaps", "egl_decode_logits",
            "egl_synthesize_keypoints", "egl_fit_homography", "egl_select_homography", "egl_project_points", "egl_pyramid_bytes",
            "egl_gray_pyramid", "egl_track_keypoints", "egl_filter_flow", "egl_merge_keypoints", "egl_calibrate_keypoints",
-           "egl_fit_homography_masked", "egl_commit_fit")
+           "egl_fit_homography_masked", "egl_commit_fit", "egl_refine_keypoints", "egl_fit_homography_subpixel")
 
 if lib.egl_version() != ABI_VERSION:
     raise NativeError(f"libeagle_b200.so has ABI {lib.egl_version()}, this package expects {ABI_VERSION}; rebuild")

@@ -461,9 +461,46 @@ __global__ void __launch_bounds__(kPostWarps * 32) postprocess_kernel(const int3
     }
 }
 
+// Sub-pixel refinement (an extension of the path: the reference decodes to the integer heatmap grid only).
+// A parabola through the maximum and its two neighbours, per axis, on the raw heatmap values:
+//   d = 0.5 * (h[+1] - h[-1]) / ((h[0] - h[-1]) + (h[0] - h[+1])),  clamped to [-0.5, 0.5], 0 on the border
+// and the image position  (x + d) / (w - 1) * img_w  (keypoint_hrnet.py:590-591 scaling, not truncated).
+__global__ void refine_kernel(const float* __restrict__ hm, int F, int hm_h, int hm_w, float img_w, float img_h,
+                              const int32_t* __restrict__ kp_flat, float* __restrict__ kp_sub) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * kLandmarks) return;
+    const int flat = kp_flat[i];
+    const int y = flat / hm_w, x = flat - y * hm_w;
+    const float* m = hm + (size_t)i * hm_h * hm_w;
+    const float c = m[flat];
+    float dx = 0.f, dy = 0.f;
+    if (x > 0 && x + 1 < hm_w) {
+        const float l = m[flat - 1], r = m[flat + 1];
+        const float den = __fadd_rn(__fsub_rn(c, l), __fsub_rn(c, r));
+        if (den > 0.f) dx = fminf(fmaxf(__fdiv_rn(__fmul_rn(0.5f, __fsub_rn(r, l)), den), -0.5f), 0.5f);
+    }
+    if (y > 0 && y + 1 < hm_h) {
+        const float u = m[flat - hm_w], d = m[flat + hm_w];
+        const float den = __fadd_rn(__fsub_rn(c, u), __fsub_rn(c, d));
+        if (den > 0.f) dy = fminf(fmaxf(__fdiv_rn(__fmul_rn(0.5f, __fsub_rn(d, u)), den), -0.5f), 0.5f);
+    }
+    kp_sub[2 * (size_t)i] = __fmul_rn(__fdiv_rn(__fadd_rn((float)x, dx), (float)(hm_w - 1)), img_w);
+    kp_sub[2 * (size_t)i + 1] = __fmul_rn(__fdiv_rn(__fadd_rn((float)y, dy), (float)(hm_h - 1)), img_h);
+}
+
 }  // namespace egl
 
 using namespace egl;
+
+extern "C" int egl_refine_keypoints(const float* hm, int F, int hm_h, int hm_w, int img_w, int img_h, const int32_t* kp_flat,
+                                    float* kp_sub, void* stream) {
+    if (F == 0) return 0;
+    EGL_REQUIRE(hm && kp_flat && kp_sub, EGL_ERR_NULL, "egl_refine_keypoints: null pointer");
+    EGL_REQUIRE(F > 0 && hm_h > 1 && hm_w > 1 && img_w > 0 && img_h > 0, EGL_ERR_SHAPE, "egl_refine_keypoints: bad shape");
+    const int n = F * kLandmarks;
+    refine_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(hm, F, hm_h, hm_w, (float)img_w, (float)img_h, kp_flat, kp_sub);
+    return cuda_status(cudaGetLastError(), "egl_refine_keypoints: kernel launch");
+}
 
 static int decode_impl(const float* hm, int F, int hm_h, int hm_w, int img_w, int img_h, double keypoint_conf,
                        int32_t* kp_flat, float* kp_score, int32_t* kp_xy, uint8_t* kp_order, int32_t* kp_count, void* stream,

@@ -45,7 +45,13 @@ struct FitArgs {
     int32_t* info;
     const uint8_t* sched;  // optional: fit frame f only where sched[f] | retry[f] (cadence of coordinate_model.py:333)
     const uint8_t* retry;
+    const float* kp_sub;   // optional: sub-pixel image positions [F][57][2] used instead of the integer kp_xy
 };
+
+__device__ __forceinline__ float image_coord(const FitArgs& a, int f, int ch, int axis) {
+    const size_t i = ((size_t)f * kLandmarks + ch) * 2 + axis;
+    return a.kp_sub ? a.kp_sub[i] : (float)a.kp_xy[i];
+}
 
 // Frames the cadence does not fit this step: status EGL_FIT_SKIPPED, nothing else touched but the masks.
 __device__ __forceinline__ bool fit_skipped(const FitArgs& a, int f) {
@@ -78,8 +84,8 @@ __device__ __forceinline__ int gather_points_warp(const FitArgs& a, int f, Point
         const unsigned bal = __ballot_sync(kFull, on);
         const int pos = base + __popc(bal & ((1u << lane) - 1u));
         if (on) {
-            pl.sx[pos] = (float)a.kp_xy[((size_t)f * kLandmarks + ch) * 2 + 0];
-            pl.sy[pos] = (float)a.kp_xy[((size_t)f * kLandmarks + ch) * 2 + 1];
+            pl.sx[pos] = image_coord(a, f, ch, 0);
+            pl.sy[pos] = image_coord(a, f, ch, 1);
             pl.dx[pos] = c_world[ch].x;
             pl.dy[pos] = c_world[ch].y;
             pl.ch[pos] = (uint8_t)ch;
@@ -103,8 +109,8 @@ __device__ int gather_points_thread(const FitArgs& a, int f, float* sx, float* s
     for (int j = 0; j < n_total; ++j) {
         const int ch = a.kp_order[(size_t)f * EGL_ORDER_STRIDE + j];
         if (ch >= kLandmarks || ((kOffPlaneMask >> ch) & 1ull)) continue;
-        sx[n] = (float)a.kp_xy[((size_t)f * kLandmarks + ch) * 2 + 0];
-        sy[n] = (float)a.kp_xy[((size_t)f * kLandmarks + ch) * 2 + 1];
+        sx[n] = image_coord(a, f, ch, 0);
+        sy[n] = image_coord(a, f, ch, 1);
         dx[n] = c_world[ch].x;
         dy[n] = c_world[ch].y;
         chs[n] = (uint8_t)ch;
@@ -863,7 +869,8 @@ using namespace egl;
 
 static int fit_impl(const char* who, const int32_t* kp_xy, const uint8_t* kp_order, const int32_t* kp_count, int F, int mode, int K,
                     const uint8_t* hyp, uint64_t seed, double thr, double confidence, double* H, uint64_t* used_mask,
-                    uint64_t* inlier_mask, int32_t* status, int32_t* info, const uint8_t* sched, const uint8_t* retry, void* stream) {
+                    uint64_t* inlier_mask, int32_t* status, int32_t* info, const uint8_t* sched, const uint8_t* retry, void* stream,
+                    const float* kp_sub = nullptr) {
     if (F == 0) return 0;  // empty batch: nothing to enqueue, pointers may be null
     EGL_REQUIRE(kp_xy && kp_order && kp_count && H && used_mask && inlier_mask && status && info, EGL_ERR_NULL, "%s: null pointer", who);
     EGL_REQUIRE(F >= 0 && K >= 1, EGL_ERR_SHAPE, "%s: need F >= 0 and K >= 1 (F=%d K=%d)", who, F, K);
@@ -871,7 +878,7 @@ static int fit_impl(const char* who, const int32_t* kp_xy, const uint8_t* kp_ord
     EGL_REQUIRE(confidence > 0 && confidence < 1, EGL_ERR_SHAPE, "%s: confidence must be in (0,1)", who);
     if (!(thr > 0)) thr = 3.0;  // findHomography: ransacReprojThreshold <= 0 -> 3
     FitArgs a{kp_xy, kp_order, kp_count, F, K, hyp, seed, (float)(thr * thr), confidence, H, used_mask, inlier_mask, status, info,
-              sched, retry};
+              sched, retry, kp_sub};
     cudaStream_t s = (cudaStream_t)stream;
     if (mode == EGL_FIT_CV2_COMPAT) {
         ransac_cv2_kernel<<<(F + kCv2Warps - 1) / kCv2Warps, kCv2Warps * 32, 0, s>>>(a);
@@ -909,4 +916,13 @@ extern "C" int egl_fit_homography_masked(const int32_t* kp_xy, const uint8_t* kp
     if (F > 0) EGL_REQUIRE(sched, EGL_ERR_NULL, "egl_fit_homography_masked: sched is null");
     return fit_impl("egl_fit_homography_masked", kp_xy, kp_order, kp_count, F, mode, K, hyp, seed, thr, confidence, H, used_mask,
                     inlier_mask, status, info, sched, retry, stream);
+}
+
+extern "C" int egl_fit_homography_subpixel(const float* kp_sub, const int32_t* kp_xy, const uint8_t* kp_order, const int32_t* kp_count,
+                                           int F, int mode, int K, const uint8_t* hyp, uint64_t seed, double thr, double confidence,
+                                           double* H, uint64_t* used_mask, uint64_t* inlier_mask, int32_t* status, int32_t* info,
+                                           void* stream) {
+    if (F > 0) EGL_REQUIRE(kp_sub, EGL_ERR_NULL, "egl_fit_homography_subpixel: kp_sub is null");
+    return fit_impl("egl_fit_homography_subpixel", kp_xy, kp_order, kp_count, F, mode, K, hyp, seed, thr, confidence, H, used_mask,
+                    inlier_mask, status, info, nullptr, nullptr, stream, kp_sub);
 }

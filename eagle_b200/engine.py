@@ -106,6 +106,17 @@ class GeometryEngine:
                        _ptr(kp.order), _ptr(kp.count), _stream()), "egl_decode_logits" if from_logits else "egl_decode_heatmaps")
         return kp
 
+    def refine(self, heatmaps: torch.Tensor, kp: KeypointSet, img_w: int, img_h: int) -> torch.Tensor:
+        """Sub-pixel positions (F, 57, 2) float32 of every channel's arg-max (extension; see the header)."""
+        F, C, h, w = heatmaps.shape
+        _require(heatmaps.dtype == torch.float32 and heatmaps.is_cuda and heatmaps.is_contiguous() and C == NUM_LANDMARKS,
+                 "refine: heatmaps must be a contiguous CUDA float32 tensor of shape (F, 57, h, w)")
+        sub = torch.empty((F, NUM_LANDMARKS, 2), dtype=torch.float32, device=heatmaps.device)
+        with torch.cuda.device(heatmaps.device):
+            N.check(N.lib.egl_refine_keypoints(_ptr(heatmaps), F, h, w, img_w, img_h, _ptr(kp.flat), _ptr(sub), _stream()),
+                    "egl_refine_keypoints")
+        return sub
+
     # -- F1 ---------------------------------------------------------------------------------
     def synthesize(self, kp: KeypointSet, max_new: int = 30) -> KeypointSet:
         with torch.cuda.device(kp.xy.device):
@@ -122,15 +133,24 @@ class GeometryEngine:
 
     def fit(self, kp: KeypointSet, mode: int = N.FIT_CV2_COMPAT, K: int = 2000, hyp: torch.Tensor | None = None,
             seed: int = 0, thr: float = 5.0, confidence: float = 0.995, out: FitResult | None = None,
-            sched: torch.Tensor | None = None, retry: torch.Tensor | None = None) -> FitResult:
-        """sched / retry (F,) uint8: fit only the frames with sched | retry (the reference's cadence test, :333)."""
+            sched: torch.Tensor | None = None, retry: torch.Tensor | None = None, sub: torch.Tensor | None = None) -> FitResult:
+        """sched / retry (F,) uint8: fit only the frames with sched | retry (the reference's cadence test, :333).
+        sub (F, 57, 2) float32: fit on these sub-pixel positions instead of the integer kp.xy (extension)."""
         F = kp.n_frames
         r = out if out is not None else self.alloc_fit(F)
         if hyp is not None:
             _require(hyp.dtype == torch.uint8 and hyp.is_cuda and hyp.is_contiguous() and tuple(hyp.shape) == (F, K, 4),
                      "fit: hyp must be a contiguous CUDA uint8 tensor of shape (F, K, 4)")
         with torch.cuda.device(kp.xy.device):
-            if sched is None:
+            if sub is not None:
+                _require(sched is None, "fit: sub-pixel positions and a cadence mask cannot be combined")
+                _require(sub.dtype == torch.float32 and sub.is_contiguous() and tuple(sub.shape) == (F, NUM_LANDMARKS, 2),
+                         "fit: sub must be a contiguous (F, 57, 2) float32 tensor")
+                N.check(N.lib.egl_fit_homography_subpixel(_ptr(sub), _ptr(kp.xy), _ptr(kp.order), _ptr(kp.count), F, mode, K, _ptr(hyp),
+                                                          seed, float(thr), float(confidence), _ptr(r.H), _ptr(r.used_mask),
+                                                          _ptr(r.inlier_mask), _ptr(r.status), _ptr(r.info), _stream()),
+                        "egl_fit_homography_subpixel")
+            elif sched is None:
                 N.check(N.lib.egl_fit_homography(_ptr(kp.xy), _ptr(kp.order), _ptr(kp.count), F, mode, K, _ptr(hyp), seed, float(thr),
                                                  float(confidence), _ptr(r.H), _ptr(r.used_mask), _ptr(r.inlier_mask), _ptr(r.status),
                                                  _ptr(r.info), _stream()), "egl_fit_homography")

@@ -100,6 +100,22 @@ int egl_decode_logits(const float *logits, int F, int hm_h, int hm_w, int img_w,
                       void *stream);
 
 /*
+ * Sub-pixel landmark positions (an extension: the reference stops at the integer heatmap grid, which
+ * alone costs ~1e-2 relative error in H).  Per channel a parabola through the arg-max and its two
+ * neighbours per axis, offset clamped to +-0.5 px, 0 on the border; image position
+ * (x + d) / (w - 1) * img_w as float.  Parity mode (egl_fit_homography on the integer kp_xy) is unaffected.
+ *   kp_flat [F][57] int32 from egl_decode_*;  kp_sub [F][57][2] float32 out (all channels)
+ */
+int egl_refine_keypoints(const float *hm, int F, int hm_h, int hm_w, int img_w, int img_h, const int32_t *kp_flat,
+                         float *kp_sub, void *stream);
+
+/* egl_fit_homography on the sub-pixel positions kp_sub instead of the integer kp_xy (same outputs). */
+int egl_fit_homography_subpixel(const float *kp_sub, const int32_t *kp_xy, const uint8_t *kp_order,
+                                const int32_t *kp_count, int F, int mode, int K, const uint8_t *hyp, uint64_t seed,
+                                double thr, double confidence, double *H, uint64_t *used_mask, uint64_t *inlier_mask,
+                                int32_t *status, int32_t *info, void *stream);
+
+/*
  * F1  line-intersection keypoint synthesis, appended to kp_order / kp_xy in place.
  * Replaces CoordinateModel._synthesize_keypoints_with_line_intersections
  * (coordinate_model.py:140-186, with :76-138): per world-y and world-x line family with >= 2

@@ -68,3 +68,31 @@ def postprocess(kp_list, width: int, height: int, keypoint_conf: float = 0.3) ->
 def decode_frame(heatmaps: np.ndarray, width: int, height: int, keypoint_conf: float = 0.3) -> dict:
     """get_keypoints + postprocess for a single (C, H, W) frame."""
     return postprocess(get_keypoints(heatmaps[None])[0], width, height, keypoint_conf)
+
+
+def refine_subpixel(heatmap: np.ndarray, img_w: int, img_h: int) -> np.ndarray:
+    """Specification of egl_refine_keypoints (an extension; the reference has no sub-pixel step): per channel a
+    parabola through the arg-max and its two neighbours on each axis, float32 arithmetic in this order,
+    offset clamped to +-0.5 and 0 on the border; returns (57, 2) float32 image positions."""
+    F32 = np.float32
+    C, h, w = heatmap.shape
+    out = np.zeros((C, 2), F32)
+    for c in range(C):
+        m = heatmap[c].astype(F32)
+        flat = int(np.argmax(m))
+        y, x = divmod(flat, w)
+        v = m[y, x]
+        dx = dy = F32(0.0)
+        if 0 < x < w - 1:
+            l, r = m[y, x - 1], m[y, x + 1]
+            den = F32(F32(v - l) + F32(v - r))
+            if den > 0:
+                dx = F32(min(max(F32(F32(F32(0.5) * F32(r - l)) / den), F32(-0.5)), F32(0.5)))
+        if 0 < y < h - 1:
+            u, d = m[y - 1, x], m[y + 1, x]
+            den = F32(F32(v - u) + F32(v - d))
+            if den > 0:
+                dy = F32(min(max(F32(F32(F32(0.5) * F32(d - u)) / den), F32(-0.5)), F32(0.5)))
+        out[c, 0] = F32(F32(F32(F32(x) + dx) / F32(w - 1)) * F32(img_w))
+        out[c, 1] = F32(F32(F32(F32(y) + dy) / F32(h - 1)) * F32(img_h))
+    return out

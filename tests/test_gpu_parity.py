@@ -531,3 +531,46 @@ def test_rejection_heavy_sampling_matches_cv2(engine):
             n_model += 1
             assert int(inl[i]) == sum(1 << int(c) for c, m in zip(sel, mc.ravel()) if m), (i, info[i].tolist())
     assert 5 < n_model < T
+
+
+def test_subpixel_refinement_extension(engine):
+    """North-star extension (not in the reference): parabola sub-pixel positions.  Bit-exact against its
+    specification in oracle/decode.py, parity mode untouched, and a real accuracy gain against the
+    ground-truth camera of the synthetic clip."""
+    from eagle_b200 import synthetic
+    from eagle_b200.pitch import NUM_LANDMARKS, WORLD_XYZ, OFF_PLANE
+    from oracle import decode
+    rng = np.random.default_rng(12)
+    F, W, H = 24, 1920, 1080
+    cams = synthetic.sample_cameras(F, W, H, rng)
+    hm = np.empty((F, NUM_LANDMARKS, synthetic.HM_H, synthetic.HM_W), np.float32)
+    for i in range(F):
+        px, vis = synthetic.landmark_pixels(cams[i], W, H)
+        hm[i] = synthetic.render_heatmaps(px, vis, W, H, rng, jitter=0.0, background=0.02)
+    hm[0, 5, :, :] = 0.0; hm[0, 5, 0, 7] = 0.9          # maximum on the border: no offset on that axis
+    hm[1, 6, 50, 60:63] = 0.8                            # plateau: denominator 0 on x
+    d_hm = torch.from_numpy(hm).cuda()
+    kp = engine.decode(d_hm, W, H)
+    before = kp.xy.clone()
+    sub = engine.refine(d_hm, kp, W, H)
+    assert torch.equal(kp.xy, before)
+    got = sub.cpu().numpy()
+    for i in range(F):
+        want = decode.refine_subpixel(hm[i], W, H)
+        assert np.array_equal(got[i].view(np.int32), want.view(np.int32)), i
+    fit_int = engine.fit(kp)
+    fit_sub = engine.fit(kp, sub=sub)
+    assert int((fit_sub.status == 0).sum()) == F and int((fit_int.status == 0).sum()) == F
+    # error in pitch metres of the image -> pitch mapping, over the on-plane landmarks visible in the frame
+    on = np.array([c for c in range(NUM_LANDMARKS) if c not in OFF_PLANE])
+    err = {"int": [], "sub": []}
+    for name, fit in (("int", fit_int), ("sub", fit_sub)):
+        Hs = fit.H.cpu().numpy().reshape(F, 3, 3)
+        for i in range(F):
+            px, vis = synthetic.landmark_pixels(cams[i], W, H)
+            sel = on[vis[on]]
+            p = np.c_[px[sel], np.ones(len(sel))] @ Hs[i].T
+            err[name].append(float(np.mean(np.hypot(*(p[:, :2] / p[:, 2:3] - WORLD_XYZ[sel, :2]).T))))
+    e_int, e_sub = float(np.mean(err["int"])), float(np.mean(err["sub"]))
+    assert e_sub < e_int / 3.0, (e_int, e_sub)
+    print(f"mean landmark error: integer grid {e_int:.3f} m, sub-pixel {e_sub:.3f} m")
