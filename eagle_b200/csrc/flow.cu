@@ -104,12 +104,16 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(uint8_t* __restrict__ pyr,
 // general kernels above spend their time on per-byte loads and index arithmetic (1.3 TB/s on 1080p).
 //
 // gray: one thread turns 16 pixels (three 16-byte loads) into one 16-byte store.
+// The integer pipe, not HBM, bounds these kernels once the loads are wide, so the 15-bit weights are split
+// into bytes (w = 256*hi + lo) and a pixel costs two byte dot products: B,G,R sit in three bytes of one word.
+__device__ __forceinline__ uint32_t gray_px(uint32_t p) {  // p = B | G << 8 | R << 16 | (ignored) << 24
+    const uint32_t hi = __dp4a(p, 0x00264b0eu, 64u);       // 14 B + 75 G + 38 R + (1 << 14) / 256
+    return __dp4a(p, 0x00462397u, hi << 8) >> 15;          // + 151 B + 35 G + 70 R:  3735, 19235, 9798 in total
+}
 __device__ __forceinline__ uint32_t gray4(uint32_t a, uint32_t b, uint32_t c) {  // 12 bytes B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
-    const int g0 = gray_of(a & 255, (a >> 8) & 255, (a >> 16) & 255);
-    const int g1 = gray_of(a >> 24, b & 255, (b >> 8) & 255);
-    const int g2 = gray_of((b >> 16) & 255, b >> 24, c & 255);
-    const int g3 = gray_of((c >> 8) & 255, (c >> 16) & 255, c >> 24);
-    return (uint32_t)g0 | ((uint32_t)g1 << 8) | ((uint32_t)g2 << 16) | ((uint32_t)g3 << 24);
+    const uint32_t g0 = gray_px(a), g1 = gray_px(__funnelshift_r(a, b, 24));
+    const uint32_t g2 = gray_px(__funnelshift_r(b, c, 16)), g3 = gray_px(c >> 8);
+    return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
 }
 
 __global__ void __launch_bounds__(256) gray16_kernel(const uint8_t* __restrict__ frames, int H, int W16, long long row_stride,
@@ -175,6 +179,81 @@ __global__ void __launch_bounds__(256) pyrdown8_kernel(uint8_t* __restrict__ pyr
     o.x = (acc[0] >> 8) | ((acc[1] >> 8) << 8) | ((acc[2] >> 8) << 16) | ((acc[3] >> 8) << 24);
     o.y = (acc[4] >> 8) | ((acc[5] >> 8) << 8) | ((acc[6] >> 8) << 16) | ((acc[7] >> 8) << 24);
     *reinterpret_cast<uint2*>(pyr + (long long)f * pyr_stride + dst_off + (long long)oy * dw + ox) = o;
+}
+
+// gray + pyramid level 1 in one pass: the level-0 gray of a 32 x 256 tile (plus the 5x5 kernel's halo) is
+// built in shared memory, written out once, and level 1 is computed from the shared copy, so level 0 is
+// never read back from HBM.  Same arithmetic as gray16_kernel / pyrdown8_kernel.  W % 16 == 0.
+constexpr int kFuseW = 256, kFuseH = 32;
+constexpr int kFuseSmW = kFuseW + 32;  // columns x0-16 .. x0+271 (16-pixel groups)
+constexpr int kFuseSmH = kFuseH + 3;   // rows y0-2 .. y0+32
+
+__global__ void __launch_bounds__(256) gray_l1_kernel(const uint8_t* __restrict__ frames, int H, int W, long long row_stride,
+                                                      long long frame_stride, uint8_t* __restrict__ pyr, long long pyr_stride,
+                                                      long long off1, int w1, int h1, int f0) {
+    __shared__ __align__(16) uint8_t sg[kFuseSmH][kFuseSmW];
+    const int f = blockIdx.z + f0;
+    const int x0 = blockIdx.x * kFuseW, y0 = blockIdx.y * kFuseH;
+    const int tid = threadIdx.x;
+    const uint8_t* fsrc = frames + (long long)f * frame_stride;
+    uint8_t* fdst = pyr + (long long)f * pyr_stride;
+    constexpr int kGroups = kFuseSmW / 16;  // 18
+    for (int item = tid; item < kFuseSmH * kGroups; item += 256) {
+        const int r = item / kGroups, gi = item - r * kGroups;
+        const int gx = x0 - 16 + gi * 16;
+        if (gx < 0 || gx >= W) continue;
+        const int ya = y0 - 2 + r;
+        const int yy = reflect101(ya, H);
+        const uint4* s4 = reinterpret_cast<const uint4*>(fsrc + (long long)yy * row_stride + 3ll * gx);
+        const uint4 a = __ldg(s4), b = __ldg(s4 + 1), c = __ldg(s4 + 2);
+        uint4 o;
+        o.x = gray4(a.x, a.y, a.z);
+        o.y = gray4(a.w, b.x, b.y);
+        o.z = gray4(b.z, b.w, c.x);
+        o.w = gray4(c.y, c.z, c.w);
+        *reinterpret_cast<uint4*>(&sg[r][gi * 16]) = o;
+        if (r >= 2 && r < 2 + kFuseH && gi >= 1 && gi <= kFuseW / 16 && ya < H)
+            __stcs(reinterpret_cast<uint4*>(fdst + (long long)ya * W + gx), o);
+    }
+    __syncthreads();
+    // REFLECT_101 columns the kernel touches outside the image: -2, -1 and W
+    if (x0 == 0 && tid < kFuseSmH) {
+        sg[tid][15] = sg[tid][17];
+        sg[tid][14] = sg[tid][18];
+    }
+    if (x0 + kFuseW >= W && tid >= 64 && tid < 64 + kFuseSmH) {
+        const int e = W - x0 + 16;
+        sg[tid - 64][e] = sg[tid - 64][e - 2];
+    }
+    __syncthreads();
+    const int ry = tid >> 4, xb = tid & 15;
+    const int ox = x0 / 2 + xb * 8, oy = y0 / 2 + ry;
+    if (ox >= w1 || oy >= h1) return;
+    uint32_t acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 128;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        const uint8_t* row = &sg[2 * ry + r][16 + 16 * xb];
+        const uint4 m = *reinterpret_cast<const uint4*>(row);
+        uint32_t Wd[6];
+        Wd[0] = *reinterpret_cast<const uint32_t*>(row - 4);
+        Wd[1] = m.x; Wd[2] = m.y; Wd[3] = m.z; Wd[4] = m.w;
+        Wd[5] = *reinterpret_cast<const uint32_t*>(row + 16);
+        const uint32_t wr = (r == 0 || r == 4) ? 1u : (r == 2 ? 6u : 4u);
+        const uint32_t taps = wr * 0x04060401u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc[2 * j] = __dp4a(__funnelshift_r(Wd[j], Wd[j + 1], 16), taps, acc[2 * j]);
+            acc[2 * j] = __dp4a(Wd[j + 1], wr << 16, acc[2 * j]);
+            acc[2 * j + 1] = __dp4a(Wd[j + 1], taps, acc[2 * j + 1]);
+            acc[2 * j + 1] = __dp4a(Wd[j + 2], wr, acc[2 * j + 1]);
+        }
+    }
+    uint2 o;
+    o.x = (acc[0] >> 8) | ((acc[1] >> 8) << 8) | ((acc[2] >> 8) << 16) | ((acc[3] >> 8) << 24);
+    o.y = (acc[4] >> 8) | ((acc[5] >> 8) << 8) | ((acc[6] >> 8) << 16) | ((acc[7] >> 8) << 24);
+    *reinterpret_cast<uint2*>(fdst + off1 + (long long)oy * w1 + ox) = o;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -715,8 +794,9 @@ extern "C" int egl_gray_pyramid(const uint8_t* frames, int F, int H, int W, size
                 "egl_gray_pyramid: bad shape (F=%d H=%d W=%d max_level=%d)", F, H, W, max_level);
     const PyrLayout L = pyramid_layout(H, W, max_level);
     cudaStream_t s = (cudaStream_t)stream;
-    static const char* env = getenv("EGL_PYRAMID_VARIANT");  // measurement switch: 1 = general per-byte kernels only
+    static const char* env = getenv("EGL_PYRAMID_VARIANT");  // measurement switch: 1 = general per-byte kernels only, 2 = unfused fast kernels
     const bool general_only = env && atoi(env) == 1;
+    const bool unfused = env && atoi(env) == 2;
     const bool fast_gray = !general_only && W % 16 == 0 && row_stride % 16 == 0 && frame_stride % 16 == 0 &&
                            ((uintptr_t)frames & 15) == 0 && ((uintptr_t)pyr & 15) == 0;
     // One pass over all frames per level: splitting the clip into L2-sized groups (so that pyrDown would find
@@ -724,7 +804,12 @@ extern "C" int egl_gray_pyramid(const uint8_t* frames, int F, int H, int W, size
     // 32, 8.6 ms in groups of 8 for 2250 frames at 1080p -- the launch tails cost more than the re-read.
     for (int f0 = 0; f0 < F; f0 += 32768) {
         const int nf = min(32768, F - f0);
-        if (fast_gray) {
+        int first_level = 1;
+        if (fast_gray && !unfused && L.n > 1 && H >= 3) {
+            gray_l1_kernel<<<dim3((W + kFuseW - 1) / kFuseW, (H + kFuseH - 1) / kFuseH, nf), 256, 0, s>>>(
+                frames, H, W, (long long)row_stride, (long long)frame_stride, pyr, L.bytes, L.off[1], L.w[1], L.h[1], f0);
+            first_level = 2;
+        } else if (fast_gray) {
             const int items = H * (W / 16);
             gray16_kernel<<<dim3((items + 511) / 512, nf), 256, 0, s>>>(frames, H, W / 16, (long long)row_stride, (long long)frame_stride,
                                                                         pyr, L.bytes, f0);
@@ -732,7 +817,7 @@ extern "C" int egl_gray_pyramid(const uint8_t* frames, int F, int H, int W, size
             gray_kernel<<<dim3((W + 1023) / 1024, H, nf), 256, 0, s>>>(frames, H, W, (long long)row_stride, (long long)frame_stride, pyr,
                                                                        L.bytes, f0);
         }
-        for (int l = 1; l < L.n; ++l) {
+        for (int l = first_level; l < L.n; ++l) {
             if (!general_only && L.w[l - 1] % 16 == 0 && ((uintptr_t)pyr & 15) == 0)
                 pyrdown8_kernel<<<dim3((L.w[l] + 255) / 256, (L.h[l] + 7) / 8, nf), 256, 0, s>>>(pyr, L.bytes, L.off[l - 1], L.w[l - 1],
                                                                                              L.h[l - 1], L.off[l], L.w[l], L.h[l], f0);

@@ -56,7 +56,7 @@ def _keypoint_set(points_per_frame, dev="cuda"):
     return KeypointSet(None, None, t(xy), t(order), t(count), torch.zeros((n, 64), dtype=torch.uint8, device=dev))
 
 
-@pytest.mark.parametrize("shape", [(77, 101), (360, 640), (1080, 1920), (33, 18)])
+@pytest.mark.parametrize("shape", [(77, 101), (360, 640), (1080, 1920), (33, 18), (90, 160), (101, 256), (37, 48), (64, 1280), (720, 1280)])
 def test_gray_pyramid_matches_oracle(engine, shape):
     H, W = shape
     rng = np.random.default_rng(H)
