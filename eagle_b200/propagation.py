@@ -13,8 +13,9 @@ How the reference's frame loop is laid out here
   * That parallel pass speculates "heads are independent, no retry flag crosses a boundary".  The few
     chains for which that turns out wrong are re-run one by one, in order, with the same kernels on
     single-chain slices -- the reference's sequential semantics, exactly.
-  * The host sees one small D2H per round (the keypoint counts: a frame whose flow kept fewer than
-    four points asks the network for that frame, :316-320).
+  * The host reads back once per clip (head keypoint counts, retry flags, per-frame flow counts); a chain in
+    which some frame's flow kept fewer than four points -- the reference then asks the network for that
+    frame, :316-320 -- is one of those re-run chains.
 
 Nothing here computes on the CPU; the arithmetic is in csrc/flow.cu, fit.cu, synthesize.cu.
 """
@@ -75,10 +76,8 @@ class PropagatedPath:
     """The frame loop of get_coordinates for any keypoint / homography cadence, frames resident in HBM."""
 
     def __init__(self, engine: GeometryEngine, keypoint_conf: float = 0.3, fit_mode: int = N.FIT_CV2_COMPAT, max_iters: int = 2000,
-                 thr: float = 5.0, n_streams: int = 1):
+                 thr: float = 5.0):
         self.e = engine
-        self.n_streams = n_streams
-        self._streams, self._pinned = [], []
         self.keypoint_conf = keypoint_conf
         self.fit_mode, self.max_iters, self.thr = fit_mode, max_iters, thr
         self.stats = {}
@@ -113,61 +112,35 @@ class PropagatedPath:
         tmp = _new_set(nc, dev)
         e.decode(head_heatmaps, Wimg, Himg, self.keypoint_conf, out=KeypointSet(tmp.flat, tmp.score, st.xy[0], st.order[0], st.count[0]))
         self.heads = _clone(st.kp(0, 0, nc))
-        head_cnt = self.heads.count[:, 0].cpu().numpy()
 
-        # ---- parallel pass: every chain advances one frame per round.  n_streams > 1 splits the chains into
-        # groups on their own streams so that the short, latency-bound launches of a round could overlap;
-        # measured on B200 (2250 frames, interval 8) it does not pay -- 9.45 ms with one stream, 9.6 / 12.7 /
-        # 18.9 ms with 2 / 4 / 8: the host-side launch work per group costs more than the overlap gains --
-        # so the default stays one stream and the switch is kept for A/B runs.
-        G = max(1, min(self.n_streams, nc // 32))
-        bounds = [(g * nc // G, (g + 1) * nc // G) for g in range(G)]
-        cur = torch.cuda.current_stream(dev)
-        if G > 1 and len(self._streams) < G:
-            self._streams = [torch.cuda.Stream(dev) for _ in range(G)]
-        streams = [cur] if G == 1 else self._streams[:G]
-        start = cur.record_event()
-        need = max(c1 - c0 for c0, c1 in bounds)
-        if len(self._pinned) < G or self._pinned[0].numel() < need:  # page-locked allocations are slow: keep them
-            self._pinned = [torch.empty(need, dtype=torch.int32).pin_memory() for _ in range(G)]
-        pinned = self._pinned
-        for sg in streams:
-            sg.wait_event(start)
+        # ---- parallel pass: every chain advances one frame per round; nothing is read back in between, so the
+        # host runs ahead of the GPU.  (Splitting the chains over 2 / 4 / 8 streams to overlap the short,
+        # latency-bound launches of a round was measured slower -- 9.6 / 12.7 / 18.9 ms against 9.45 ms for a
+        # 2250-frame clip: the extra host-side launch work costs more than the overlap gains.)
+        flow_cnt = torch.full((k, nc), 1 << 20, dtype=torch.int32, device=dev)
         for s in range(k):
             n_s = (F - s + k - 1) // k
             if n_s <= 0:
                 break
-            pending = []
-            for g, (c0, c1) in enumerate(bounds):
-                c1 = min(c1, n_s)
-                if c1 <= c0:
-                    continue
-                with torch.cuda.stream(streams[g]):
-                    if s == 0:
-                        self._finish(0, c0, c1)
-                    else:
-                        self._flow(s, c0, c1)
-                        pinned[g][:c1 - c0].copy_(st.count[s, c0:c1, 0], non_blocking=True)
-                        pending.append((g, c0, c1, streams[g].record_event()))
-            for g, c0, c1, ev in pending:
-                ev.synchronize()
-                with torch.cuda.stream(streams[g]):
-                    for c in np.nonzero(pinned[g][:c1 - c0].numpy() < 4)[0]:
-                        self._fallback(s, c0 + int(c))
-                    self._finish(s, c0, c1)
-        for sg in streams:
-            cur.wait_stream(sg)
+            if s > 0:
+                self._flow(s, 0, n_s)
+                flow_cnt[s, :n_s].copy_(st.count[s, :n_s, 0])
+            self._finish(s, 0, n_s)
 
-        # ---- repairs, in frame order
+        # ---- one read-back, then the repairs in frame order: chains whose speculation was wrong
+        #  * a frame whose flow kept < 4 points (the reference then asks the network, :316-320),
+        #  * a head with < 4 landmarks (flow from the previous chain joins in, :308-311; frame 0: :288-307),
+        #  * a retry flag that crosses into a head the cadence does not schedule (:333).
+        host = torch.stack([self.heads.count[:, 0], st.retry.to(torch.int32), (flow_cnt < 4).any(dim=0).to(torch.int32)]).cpu().numpy()
+        head_cnt, retry_final, short = host[0], host[1].copy(), host[2]
         rerun_upto = -1
         if head_cnt[0] < 4 and F > 1:
             rerun_upto = self._rescue_first_frame()
-        retry_final = st.retry.cpu().numpy().copy()
         for c in range(nc):
             incoming = int(retry_final[c - 1]) if c > 0 else 0
             head = self.extra_mem.get(c * k)
             cnt_c = int(head.count[0, 0]) if head is not None else int(head_cnt[c])
-            need = c <= rerun_upto or (c > 0 and (cnt_c < 4 or (incoming and not self.sched_h[0, c])))
+            need = c <= rerun_upto or bool(short[c]) or (c > 0 and (cnt_c < 4 or (incoming and not self.sched_h[0, c])))
             if need:
                 self._run_chain(c, incoming)
                 retry_final[c] = int(st.retry[c].item())

@@ -33,7 +33,6 @@ def main():
     ap.add_argument("--paths", type=int, default=3)
     ap.add_argument("--fps", type=int, default=25)
     ap.add_argument("--calibration", action="store_true")
-    ap.add_argument("--streams", type=int, default=1)
     args = ap.parse_args()
     import torch
     from eagle_b200.engine import GeometryEngine
@@ -45,7 +44,7 @@ def main():
     frames, heads = build_clip(torch, dev, args.frames, k, args.paths)
     torch.cuda.synchronize()
     build_s = time.time() - t0
-    prop = PropagatedPath(e, n_streams=args.streams)
+    prop = PropagatedPath(e)
     foot = torch.rand((args.frames, 27, 2), device=dev) * torch.tensor([1920.0, 1080.0], device=dev)
     cnt = torch.full((args.frames,), 25, dtype=torch.int32, device=dev)
 
