@@ -541,10 +541,10 @@ __global__ void __launch_bounds__(kTrackWarps * 32) track_kernel(TrackArgs a) {
             if (fx < -kWin || fx >= cols || fy < -kWin || fy >= rows) status = 0;
         }
     }
-    if (lane == 0) {
-        a.out_pts[((size_t)p * kMaxPts + j) * 2] = sx;
-        a.out_pts[((size_t)p * kMaxPts + j) * 2 + 1] = sy;
-        a.out_status[(size_t)p * kMaxPts + j] = (uint8_t)status;
+    if (lane == 0) {  // results are stored by channel, so that a consumer may look at a subset of the tracked set
+        a.out_pts[((size_t)p * kMaxPts + ch) * 2] = sx;
+        a.out_pts[((size_t)p * kMaxPts + ch) * 2 + 1] = sy;
+        a.out_status[(size_t)p * kMaxPts + ch] = (uint8_t)status;
     }
 }
 
@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32) filter_kernel(FilterArgs a)
     int nk = 0;
     for (int base = 0; base < n0; base += 32) {
         const int j = base + lane;
-        const bool st = j < n0 && a.status[(size_t)p * kMaxPts + j] == 1;
+        const bool st = j < n0 && a.status[(size_t)p * kMaxPts + order[j]] == 1;
         const unsigned m = __ballot_sync(kFull, st);
         if (st) s_keep[warp][nk + __popc(m & ((1u << lane) - 1))] = (uint8_t)j;
         nk += __popc(m);
@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32) filter_kernel(FilterArgs a)
     for (int jj = lane; jj < nk; jj += 32) {
         const int j = s_keep[warp][jj];
         const int ch = order[j];
-        const float dx = __fsub_rn(npt[2 * j], (float)pxy[2 * ch]), dy = __fsub_rn(npt[2 * j + 1], (float)pxy[2 * ch + 1]);
+        const float dx = __fsub_rn(npt[2 * ch], (float)pxy[2 * ch]), dy = __fsub_rn(npt[2 * ch + 1], (float)pxy[2 * ch + 1]);
         s_move[warp][jj] = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
     }
     __syncwarp();
@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32) filter_kernel(FilterArgs a)
             const int ch = order[j];
             const float z = __fdiv_rn(__fsub_rn(s_move[warp][jj], mean), stdv);
             if (!(z > 2.f)) {
-                nxi = (long long)npt[2 * j]; nyi = (long long)npt[2 * j + 1];  // astype(int): truncation
+                nxi = (long long)npt[2 * ch]; nyi = (long long)npt[2 * ch + 1];  // astype(int): truncation
                 const double hc = mean_hue_3x3(frame, a.H, a.W, a.row_stride, nxi, nyi);
                 const double hp = mean_hue_3x3(frame, a.H, a.W, a.row_stride, (long long)pxy[2 * ch], (long long)pxy[2 * ch + 1]);
                 pass = !(fabs(hc - hp) > 25.0);

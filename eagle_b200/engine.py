@@ -181,12 +181,18 @@ class GeometryEngine:
         return out
 
     def track(self, pyr: torch.Tensor, height: int, width: int, prev: KeypointSet, prev0: int, next0: int, frame_step: int,
-              max_level: int = 2, max_count: int = 10, eps: float = 0.03):
+              max_level: int = 2, max_count: int = 10, eps: float = 0.03, out=None):
         """cv2.calcOpticalFlowPyrLK for n = prev.n_frames frame pairs (prev0 + p*step -> next0 + p*step).
-        Returns (new_pts (n, 64, 2) float32, status (n, 64) uint8)."""
+        Returns (new_pts (n, 64, 2) float32, status (n, 64) uint8), indexed by channel."""
         n = prev.n_frames
-        new_pts = torch.empty((n, N.ORDER_STRIDE, 2), dtype=torch.float32, device=pyr.device)
-        status = torch.empty((n, N.ORDER_STRIDE), dtype=torch.uint8, device=pyr.device)
+        if out is not None:
+            new_pts, status = out
+            _require(new_pts.dtype == torch.float32 and new_pts.is_contiguous() and tuple(new_pts.shape) == (n, N.ORDER_STRIDE, 2)
+                     and status.dtype == torch.uint8 and status.is_contiguous() and tuple(status.shape) == (n, N.ORDER_STRIDE),
+                     "track: out must be ((n, 64, 2) float32, (n, 64) uint8)")
+        else:
+            new_pts = torch.empty((n, N.ORDER_STRIDE, 2), dtype=torch.float32, device=pyr.device)
+            status = torch.empty((n, N.ORDER_STRIDE), dtype=torch.uint8, device=pyr.device)
         _require(pyr.dtype == torch.uint8 and pyr.is_contiguous() and pyr.dim() == 2
                  and pyr.shape[1] == int(N.lib.egl_pyramid_bytes(height, width, max_level)), "track: pyr does not match the frame size")
         last = max(prev0, next0) + (n - 1) * frame_step

@@ -78,6 +78,7 @@ class PropagatedPath:
     def __init__(self, engine: GeometryEngine, keypoint_conf: float = 0.3, fit_mode: int = N.FIT_CV2_COMPAT, max_iters: int = 2000,
                  thr: float = 5.0):
         self.e = engine
+        self._side = None
         self.keypoint_conf = keypoint_conf
         self.fit_mode, self.max_iters, self.thr = fit_mode, max_iters, thr
         self.stats = {}
@@ -117,15 +118,40 @@ class PropagatedPath:
         # host runs ahead of the GPU.  (Splitting the chains over 2 / 4 / 8 streams to overlap the short,
         # latency-bound launches of a round was measured slower -- 9.6 / 12.7 / 18.9 ms against 9.45 ms for a
         # 2250-frame clip: the extra host-side launch work costs more than the overlap gains.)
+        #
+        # Tracking a point does not depend on which other points are in the set, only the filters do.  So the
+        # tracker of round s+1 starts on a second stream as soon as round s has its synthesised (and calibrated)
+        # keypoints, on a snapshot of that full set, while the main stream fits and commits round s; the filter
+        # of round s+1 then picks, by channel, the tracked points of whatever set the commit left.  The two
+        # longest latency-bound launches of a round (tracker, refit) overlap instead of queueing.
         flow_cnt = torch.full((k, nc), 1 << 20, dtype=torch.int32, device=dev)
+        pts = torch.empty((k, nc, N.ORDER_STRIDE, 2), dtype=torch.float32, device=dev)
+        pst = torch.empty((k, nc, N.ORDER_STRIDE), dtype=torch.uint8, device=dev)
+        main = torch.cuda.current_stream(dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev)
+        side = self._side
+        tracked = None
         for s in range(k):
             n_s = (F - s + k - 1) // k
             if n_s <= 0:
                 break
+            kp = st.kp(s, 0, n_s)
             if s > 0:
-                self._flow(s, 0, n_s)
+                main.wait_event(tracked)
+                e.filter_flow(frames, s, k, st.kp(s - 1, 0, n_s), pts[s, :n_s], pst[s, :n_s], kp)
                 flow_cnt[s, :n_s].copy_(st.count[s, :n_s, 0])
-            self._finish(s, 0, n_s)
+            self._prepare(s, 0, n_s)
+            n_next = (F - s - 1 + k - 1) // k
+            if s + 1 < k and n_next > 0:
+                snap = KeypointSet(None, None, st.xy[s, :n_next], st.order[s, :n_next].clone(), st.count[s, :n_next].clone(), None)
+                ready = main.record_event()
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    e.track(self.pyr, Himg, Wimg, snap, s, s + 1, k, LK_MAX_LEVEL, LK_MAX_COUNT, LK_EPS, out=(pts[s + 1, :n_next], pst[s + 1, :n_next]))
+                    tracked = side.record_event()
+                snap.order.record_stream(side); snap.count.record_stream(side)
+            self._fit_commit(s, 0, n_s)
 
         # ---- one read-back, then the repairs in frame order: chains whose speculation was wrong
         #  * a frame whose flow kept < 4 points (the reference then asks the network, :316-320),
@@ -206,12 +232,23 @@ class PropagatedPath:
 
     def _finish(self, s: int, c0: int, c1: int) -> None:
         """:326-367 for frames i = c*k + s: synthesis, calibration, fit where the cadence asks, inlier commit."""
+        self._prepare(s, c0, c1)
+        self._fit_commit(s, c0, c1)
+
+    def _prepare(self, s: int, c0: int, c1: int) -> None:
+        """:326-330: synthesis and calibration -- after this the set is what the next frame's flow starts from,
+        unless the fit below narrows it to its inliers."""
         e, st, k = self.e, self.st, self.k
         kp = st.kp(s, c0, c1)
         e.synthesize(kp)
         if self.calibration:
             st.cal_err[s, c0:c1].zero_()
             e.calibrate(self.frames, c0 * k + s, k, kp, st.cal_err[s, c0:c1])
+
+    def _fit_commit(self, s: int, c0: int, c1: int) -> None:
+        """:333-367: fit where the cadence asks, inlier commit, retry flag."""
+        e, st = self.e, self.st
+        kp = st.kp(s, c0, c1)
         fit = st.fit(s, c0, c1)
         sched, retry = self.sched[s, c0:c1], st.retry[c0:c1]
         e.fit(kp, mode=self.fit_mode, K=self.max_iters, thr=self.thr, out=fit, sched=sched, retry=retry)

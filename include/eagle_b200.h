@@ -196,7 +196,9 @@ int egl_gray_pyramid(const uint8_t *frames, int F, int H, int W, size_t row_stri
  * cv2.calcOpticalFlowPyrLK(prev_gray, curr_gray, prev_points, None, winSize=(15,15), maxLevel,
  * criteria=(EPS|COUNT, max_count, eps)) (coordinate_model.py:431-435, lk_params :65), bit-exact with
  * OpenCV's SSE build (see oracle/optflow.py).  The points of pair p are the entries of keypoint set p.
- *   new_pts [n][64][2] float32, status [n][64] uint8 (1 = found)
+ *   new_pts [n][64][2] float32, status [n][64] uint8 (1 = found), both indexed by CHANNEL (entries of
+ *   channels that are not in the set are left untouched): egl_filter_flow may then be given a subset
+ *   of the tracked set -- the inliers a fit selected while the tracker was already running.
  */
 int egl_track_keypoints(const uint8_t *pyr, int H, int W, int max_level, const int32_t *kp_xy, const uint8_t *kp_order,
                         const int32_t *kp_count, int n, int prev0, int next0, int frame_step, int max_count, double eps,
@@ -207,6 +209,7 @@ int egl_track_keypoints(const uint8_t *pyr, int H, int W, int max_level, const i
  * z-score > 2 (float32 numpy statistics) and points whose mean 3x3 hue changed by more than 25, emit
  * the survivors as a new keypoint set (labels taken by position in the status-filtered list, :446).
  *   frames: BGR uint8; the hue is read from frame hue0 + p * frame_step (the `frame` argument of :419)
+ *   prev_*: the set the reference would have flowed (its entries must have been tracked); new_pts / status by channel
  */
 int egl_filter_flow(const uint8_t *frames, int H, int W, size_t row_stride, size_t frame_stride, int hue0, int frame_step,
                     const int32_t *prev_xy, const uint8_t *prev_order, const int32_t *prev_count, const float *new_pts,

@@ -103,10 +103,9 @@ def test_tracker_bit_exact_vs_cv2_and_oracle(engine):
             g1 = O.gray_restated(frames[2 * p]); g2 = O.gray_restated(frames[2 * p + 1])
             src = np.array([pts[c] for c in chs], np.float32)
             ref, st, _ = cv2.calcOpticalFlowPyrLK(g1, g2, src, None, **lk)
-            n = len(chs)
-            assert np.array_equal(status[p, :n], st[:, 0]), (H, W, p)
+            assert np.array_equal(status[p, chs], st[:, 0]), (H, W, p)   # results are stored by channel
             ok = st[:, 0] == 1
-            assert np.array_equal(new_pts[p, :n][ok].view(np.int32), ref[ok].view(np.int32)), (H, W, p)
+            assert np.array_equal(new_pts[p, chs][ok].view(np.int32), ref[ok].view(np.int32)), (H, W, p)
             tracked += int(ok.sum())
             if p < 2:  # and the restated oracle (slow: two pairs per size)
                 out, s = O.lk_track_restated(g1, g2, src)
