@@ -174,6 +174,7 @@ class CoordinateModel:
         self.chunk = chunk
         self.path = GeometryPath(device, keypoint_conf)
         self.always_propagate = False  # route every clip through PropagatedPath (tests)
+        self.piece_frames = 2048       # sparse cadence: frames resident in HBM at a time (12.7 GB of 1080p frames + 5.6 GB of pyramids)
         self.last_stats = {}
 
     def detect_objects(self, frame: np.ndarray) -> dict:
@@ -244,19 +245,37 @@ class CoordinateModel:
 
     def _get_coordinates_propagated(self, frames, fps: int, homography_interval: int, keypoint_interval: int, calibration: bool,
                                     all_obj=None) -> dict:
-        """Any cadence: frames to HBM, network on the chain heads, PropagatedPath, projection, dict assembly."""
-        from .propagation import PropagatedPath
+        """Any cadence: frames to HBM, network on the chain heads, PropagatedPath, projection, dict assembly.
+        Clips longer than ``piece_frames`` go through in pieces (whole chains each; the boundary state is carried)."""
+        from .propagation import PropagatedPath, finalize
         e = self.path.engine
         height, width = frames[0].shape[:2]
         if all_obj is None:
             all_obj = [self.detect_objects(f) for f in frames]
-        host = torch.from_numpy(np.ascontiguousarray(np.stack(frames)))
-        dev_frames = host.pin_memory().to(self.device, non_blocking=True)
-        heads = list(range(0, len(frames), keypoint_interval))
-        hm = torch.cat([self._heatmaps_dev(dev_frames[heads[s:s + self.chunk]]) for s in range(0, len(heads), self.chunk)])
+        k = keypoint_interval
+        piece = max(k, self.piece_frames // k * k)
         prop = PropagatedPath(e, self.keypoint_conf)
-        out = prop.run(dev_frames, hm, lambda i: self._heatmaps_dev(dev_frames[i:i + 1]), keypoint_interval, homography_interval, calibration)
-        self.last_stats = dict(prop.stats)
+        pieces, carry, prev_last = [], None, None
+        stats = {"fallback_frames": 0, "repaired_chains": 0, "first_frame_rescue": False, "pieces": 0}
+        for g0 in range(0, len(frames), piece):
+            n = min(piece, len(frames) - g0)
+            halo = 0 if carry is None else 1
+            buf = torch.empty((halo + n, height, width, 3), dtype=torch.uint8, device=self.device)
+            if halo:
+                buf[0].copy_(prev_last)
+            host = torch.from_numpy(np.ascontiguousarray(np.stack(frames[g0:g0 + n])))
+            buf[halo:].copy_(host.pin_memory(), non_blocking=True)
+            heads = [halo + i for i in range(0, n, k)]
+            hm = torch.cat([self._heatmaps_dev(buf[heads[s:s + self.chunk]]) for s in range(0, len(heads), self.chunk)])
+            pieces.append(prop.run(buf, hm, lambda i, buf=buf, g0=g0, halo=halo: self._heatmaps_dev(buf[halo + i - g0:halo + i - g0 + 1]),
+                                   k, homography_interval, calibration, first_frame=g0, carry=carry))
+            carry, prev_last = prop.carry_out, buf[-1].clone()
+            for key in ("fallback_frames", "repaired_chains"):
+                stats[key] += prop.stats[key]
+            stats["first_frame_rescue"] |= prop.stats["first_frame_rescue"]
+            stats["pieces"] += 1
+        out = finalize(e, pieces)
+        self.last_stats = stats
         max_pts = max(1, max(sum(len(v) for v in o.values()) for o in all_obj))
         foot_h, count_h = objects_to_arrays(all_obj, max_pts)
         proj = e.project(out["H"], torch.from_numpy(foot_h).to(self.device), torch.from_numpy(count_h).to(self.device), width, height,

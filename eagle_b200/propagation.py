@@ -85,25 +85,34 @@ class PropagatedPath:
 
     # ---------------------------------------------------------------------------------------------
     def run(self, frames: torch.Tensor, head_heatmaps: torch.Tensor, detect: Callable[[int], torch.Tensor] | None,
-            keypoint_interval: int, homography_interval: int, calibration: bool = False) -> dict:
+            keypoint_interval: int, homography_interval: int, calibration: bool = False, *, first_frame: int = 0,
+            carry: dict | None = None) -> dict:
         """frames (F, H, W, 3) uint8 BGR CUDA; head_heatmaps (ceil(F/k), 57, h, w) float32 CUDA = the network's
         output for frames 0, k, 2k, ...; detect(i) -> (1, 57, h, w) heatmaps of frame i on demand.
 
+        Long clips go through in pieces: ``first_frame`` (a multiple of k) is the clip index of this piece's
+        first frame and ``carry`` what the previous piece left in ``self.carry_out``; frames then has ONE extra
+        leading frame, the last frame of the previous piece (the flow into a head with < 4 landmarks starts there).
+
         Returns device tensors in frame order: xy, order, count, src (the "Keypoints" of every frame),
-        H (F, 9), fit_ok (F,), h_index (F,) and host-side counters in ``self.stats``."""
+        H (F, 9), fit_ok (F,), h_index (F,) (valid for a single piece; see ``finalize``) and counters in ``self.stats``."""
         e = self.e
-        F, Himg, Wimg, _ = frames.shape
         k = int(keypoint_interval)
+        self.base = 0 if carry is None else 1           # device index of this piece's frame 0
+        self.g0 = int(first_frame)
+        assert self.g0 % k == 0 and (carry is None) == (self.g0 == 0), "pieces start on a chain head; carry comes with every piece but the first"
+        F, Himg, Wimg = frames.shape[0] - self.base, frames.shape[1], frames.shape[2]
         nc = (F + k - 1) // k
         dev = frames.device
         assert head_heatmaps.shape[0] == nc, "one heatmap stack per chain head"
         self.frames, self.k, self.F, self.Himg, self.Wimg = frames, k, F, Himg, Wimg
         self.calibration = calibration
         self.detect = detect
+        self.carry = carry
         self.pyr = e.gray_pyramid(frames, LK_MAX_LEVEL)
         st = self.st = _Sets(k, nc, dev)
         idx = np.arange(k)[:, None] + np.arange(nc)[None, :] * k
-        self.sched_h = ((idx % homography_interval) == 0) & (idx < F)
+        self.sched_h = (((idx + self.g0) % homography_interval) == 0) & (idx < F)
         self.sched = torch.from_numpy(self.sched_h.astype(np.uint8)).to(dev)
         self.extra_mem: dict[int, KeypointSet] = {}     # entries the first-frame rescue wrote into the reference's `mem`
         self.detected: dict[int, KeypointSet] = {}      # cache of on-demand detections (not semantic: `mem[i]` is only read at frame i)
@@ -139,7 +148,7 @@ class PropagatedPath:
             kp = st.kp(s, 0, n_s)
             if s > 0:
                 main.wait_event(tracked)
-                e.filter_flow(frames, s, k, st.kp(s - 1, 0, n_s), pts[s, :n_s], pst[s, :n_s], kp)
+                e.filter_flow(frames, self.base + s, k, st.kp(s - 1, 0, n_s), pts[s, :n_s], pst[s, :n_s], kp)
                 flow_cnt[s, :n_s].copy_(st.count[s, :n_s, 0])
             self._prepare(s, 0, n_s)
             n_next = (F - s - 1 + k - 1) // k
@@ -148,7 +157,8 @@ class PropagatedPath:
                 ready = main.record_event()
                 with torch.cuda.stream(side):
                     side.wait_event(ready)
-                    e.track(self.pyr, Himg, Wimg, snap, s, s + 1, k, LK_MAX_LEVEL, LK_MAX_COUNT, LK_EPS, out=(pts[s + 1, :n_next], pst[s + 1, :n_next]))
+                    e.track(self.pyr, Himg, Wimg, snap, self.base + s, self.base + s + 1, k, LK_MAX_LEVEL, LK_MAX_COUNT, LK_EPS,
+                            out=(pts[s + 1, :n_next], pst[s + 1, :n_next]))
                     tracked = side.record_event()
                 snap.order.record_stream(side); snap.count.record_stream(side)
             self._fit_commit(s, 0, n_s)
@@ -160,17 +170,20 @@ class PropagatedPath:
         host = torch.stack([self.heads.count[:, 0], st.retry.to(torch.int32), (flow_cnt < 4).any(dim=0).to(torch.int32)]).cpu().numpy()
         head_cnt, retry_final, short = host[0], host[1].copy(), host[2]
         rerun_upto = -1
-        if head_cnt[0] < 4 and F > 1:
-            rerun_upto = self._rescue_first_frame()
+        if carry is None and head_cnt[0] < 4 and F > 1:
+            rerun_upto = self._rescue_first_frame()  # (the forward scan of :290-297 stays inside this piece)
         for c in range(nc):
-            incoming = int(retry_final[c - 1]) if c > 0 else 0
+            incoming = int(retry_final[c - 1]) if c > 0 else (int(carry["retry"]) if carry is not None else 0)
             head = self.extra_mem.get(c * k)
             cnt_c = int(head.count[0, 0]) if head is not None else int(head_cnt[c])
-            need = c <= rerun_upto or bool(short[c]) or (c > 0 and (cnt_c < 4 or (incoming and not self.sched_h[0, c])))
+            has_pred = c > 0 or carry is not None
+            need = c <= rerun_upto or bool(short[c]) or (has_pred and (cnt_c < 4 or (incoming and not self.sched_h[0, c])))
             if need:
                 self._run_chain(c, incoming)
                 retry_final[c] = int(st.retry[c].item())
                 self.stats["repaired_chains"] += 1
+        last = F - 1
+        self.carry_out = {"retry": int(retry_final[nc - 1]), "kp": _clone(st.kp(last % k, last // k, last // k + 1))}
 
         # ---- back to frame order (chain-major == frame order), cadence lookup of the H each frame uses
         fo = lambda t: t.transpose(0, 1).reshape((nc * k,) + tuple(t.shape[2:]))[:F].contiguous()
@@ -190,15 +203,16 @@ class PropagatedPath:
         """calculate_optical_flow(frame_i, gray_{i-1}, keypoints_{i-1}, gray_i) for the frames i = c*k + s (:315)."""
         e, st, k = self.e, self.st, self.k
         prev = st.kp(s - 1, c0, c1)
-        p0, n0 = c0 * k + s - 1, c0 * k + s
+        p0, n0 = self.base + c0 * k + s - 1, self.base + c0 * k + s
         pts, status = e.track(self.pyr, self.Himg, self.Wimg, prev, p0, n0, k, LK_MAX_LEVEL, LK_MAX_COUNT, LK_EPS)
         e.filter_flow(self.frames, n0, k, prev, pts, status, st.kp(s, c0, c1))
 
     def _flow_single(self, prev: KeypointSet, prev_frame: int, next_frame: int, hue_frame: int) -> KeypointSet:
         e = self.e
         out = _new_set(1, self.frames.device)
-        pts, status = e.track(self.pyr, self.Himg, self.Wimg, prev, prev_frame, next_frame, 1, LK_MAX_LEVEL, LK_MAX_COUNT, LK_EPS)
-        e.filter_flow(self.frames, hue_frame, 1, prev, pts, status, out)
+        b = self.base  # frame arguments are indices within this piece (-1 = the carried frame)
+        pts, status = e.track(self.pyr, self.Himg, self.Wimg, prev, b + prev_frame, b + next_frame, 1, LK_MAX_LEVEL, LK_MAX_COUNT, LK_EPS)
+        e.filter_flow(self.frames, b + hue_frame, 1, prev, pts, status, out)
         return out
 
     def _detect_set(self, i: int) -> KeypointSet:
@@ -213,7 +227,7 @@ class PropagatedPath:
         if self.detect is None:
             raise RuntimeError(f"frame {i}: optical flow kept fewer than 4 keypoints and no keypoint network is attached for the "
                                "fallback detection (coordinate_model.py:316-320)")
-        hm = self.detect(i)
+        hm = self.detect(self.g0 + i)
         d = _new_set(1, self.frames.device)
         self.e.decode(hm, self.Wimg, self.Himg, self.keypoint_conf, out=d)
         self.detected[i] = d
@@ -243,7 +257,7 @@ class PropagatedPath:
         e.synthesize(kp)
         if self.calibration:
             st.cal_err[s, c0:c1].zero_()
-            e.calibrate(self.frames, c0 * k + s, k, kp, st.cal_err[s, c0:c1])
+            e.calibrate(self.frames, self.base + c0 * k + s, k, kp, st.cal_err[s, c0:c1])
 
     def _fit_commit(self, s: int, c0: int, c1: int) -> None:
         """:333-367: fit where the cadence asks, inlier commit, retry flag."""
@@ -261,7 +275,7 @@ class PropagatedPath:
         i = c * k
         cur = st.kp(0, c, c + 1)
         head = KeypointSet(None, None, self.heads.xy[c:c + 1], self.heads.order[c:c + 1], self.heads.count[c:c + 1], self.heads.src[c:c + 1])
-        if c == 0:
+        if c == 0 and self.carry is None:
             _assign(cur, head)                      # :285 keypoints = decoded; the rescue only rewrote mem
             if 0 in self.extra_mem:
                 e.merge(cur, self.extra_mem[0])     # :324
@@ -269,7 +283,8 @@ class PropagatedPath:
             m = self.extra_mem.get(i, head)         # :285 mem.get(i)
             _assign(cur, m)
             if int(m.count[0, 0]) < 4:              # :308-311
-                flowed = self._flow_single(st.kp(k - 1, c - 1, c), i - 1, i, i)
+                pred = st.kp(k - 1, c - 1, c) if c > 0 else self.carry["kp"]
+                flowed = self._flow_single(pred, i - 1, i, i)
                 e.merge(cur, flowed)
                 e.merge(cur, m)                     # :324
         self._finish(0, c, c + 1)
@@ -314,3 +329,13 @@ class PropagatedPath:
             self.extra_mem[jj] = base
             next_idx = jj
         return j // k
+
+
+def finalize(engine: GeometryEngine, pieces: list) -> dict:
+    """Concatenate the outputs of consecutive ``run`` calls and look up, over the whole clip, the homography each
+    frame uses (the last successful fit at or before it, coordinate_model.py:375-378)."""
+    out = {key: (torch.cat([p[key] for p in pieces]) if len(pieces) > 1 else pieces[0][key])
+           for key in ("xy", "order", "count", "src", "H", "fit_ok", "status", "inlier_mask")}
+    sel = torch.where(out["fit_ok"] != 0, torch.full_like(out["status"], N.FIT_OK), torch.full_like(out["status"], N.FIT_NO_MODEL))
+    out["h_index"], _ = engine.select(sel, 1)
+    return out

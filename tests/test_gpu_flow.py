@@ -226,13 +226,15 @@ class _Net:
         return self.hm[idx]
 
 
-def _run_both(engine, clip, fps, nh, nk, cal=False):
+def _run_both(engine, clip, fps, nh, nk, cal=False, piece=None):
     from eagle_b200.coordinate_model import CoordinateModel
     frames = list(clip["frames"])
     net = _Net(engine, clip["frames"], clip["heatmaps"])
     objs = iter(clip["objects"])
     model = CoordinateModel(keypoint_model=net, detect_objects=lambda fr: next(objs), chunk=8)
     model.always_propagate = True
+    if piece is not None:
+        model.piece_frames = piece
     got = model.get_coordinates(frames, fps=fps, num_homography=nh, num_keypoint_detection=nk, verbose=False, calibration=cal)
     want = pipeline.get_coordinates_propagated(frames, clip["heatmaps"], clip["objects"], fps, nh, nk, calibration=cal)
     return got, want, model.last_stats, net
@@ -293,6 +295,32 @@ def test_sparse_cadence_rescues_identical_to_oracle(engine):
     clip["heatmaps"][8, 3:] = 0.01; clip["frames"][7] = 0; clip["heatmaps"][7] = 0.01
     got, want, stats, _ = _run_both(engine, clip, 8, 1, 2)
     _same(got, want)
+
+
+def test_sparse_cadence_in_pieces_identical_to_oracle(engine):
+    """Long clips are processed in pieces of whole chains with the boundary state carried over; with pieces of
+    one or two chains every boundary effect lands on a piece boundary somewhere."""
+    for piece in (4, 8):
+        clip = synthetic.make_flow_clip(22, W, H, seed=110, pan_px=2.0)
+        got, want, stats, _ = _run_both(engine, clip, 8, 1, 2, piece=piece)
+        _same(got, want); assert stats["pieces"] == (22 + piece - 1) // piece
+        # blank head + 3-landmark head: flow from the carried frame / keypoints joins in
+        clip = synthetic.make_flow_clip(14, W, H, seed=22, pan_px=2.0); clip["heatmaps"][4] = 0.01; clip["heatmaps"][8, 3:] = 0.01
+        got, want, stats, _ = _run_both(engine, clip, 8, 1, 2, piece=piece)
+        _same(got, want); assert stats["repaired_chains"] >= 2
+        # retry flag carried across a piece boundary; black frame -> fallback detection inside a later piece
+        clip = synthetic.make_flow_clip(14, W, H, seed=26, pan_px=2.0)
+        clip["heatmaps"][8, 3:] = 0.01; clip["frames"][7] = 0; clip["heatmaps"][7] = 0.01
+        got, want, stats, _ = _run_both(engine, clip, 8, 1, 2, piece=piece)
+        _same(got, want)
+        # first-frame rescue inside the first piece, calibration on
+        clip = synthetic.make_flow_clip(14, W, H, seed=21, pan_px=2.0); clip["heatmaps"][0:2] = 0.01
+        got, want, stats, _ = _run_both(engine, clip, 8, 1, 2, cal=True, piece=piece)
+        _same(got, want); assert stats["first_frame_rescue"]
+    # interval 1 in pieces of one frame: every frame is a piece
+    clip = synthetic.make_flow_clip(8, W, H, seed=25, pan_px=2.0); clip["heatmaps"][3] = 0.01
+    got, want, stats, _ = _run_both(engine, clip, 1, 1, 1, piece=1)
+    _same(got, want); assert stats["pieces"] == 8
 
 
 def test_sparse_cadence_golden_from_reference(engine, golden_dir):
