@@ -96,11 +96,20 @@ class PropagatedPath:
 
         Returns device tensors in frame order: xy, order, count, src (the "Keypoints" of every frame),
         H (F, 9), fit_ok (F,), h_index (F,) (valid for a single piece; see ``finalize``) and counters in ``self.stats``."""
+        assert (carry is None) == (first_frame == 0), "carry comes with every piece but the first"
+        self.start(frames, head_heatmaps, detect, keypoint_interval, homography_interval, calibration, first_frame=first_frame)
+        self.repair(carry)
+        return self.outputs()
+
+    def start(self, frames: torch.Tensor, head_heatmaps: torch.Tensor, detect, keypoint_interval: int, homography_interval: int,
+              calibration: bool = False, *, first_frame: int = 0) -> None:
+        """The parallel pass of one piece (everything that does not need the previous piece's final state).
+        Pieces after the first (first_frame > 0) carry one extra leading frame.  ``repair`` must follow."""
         e = self.e
         k = int(keypoint_interval)
-        self.base = 0 if carry is None else 1           # device index of this piece's frame 0
         self.g0 = int(first_frame)
-        assert self.g0 % k == 0 and (carry is None) == (self.g0 == 0), "pieces start on a chain head; carry comes with every piece but the first"
+        self.base = 0 if self.g0 == 0 else 1            # device index of this piece's frame 0
+        assert self.g0 % k == 0, "pieces start on a chain head"
         F, Himg, Wimg = frames.shape[0] - self.base, frames.shape[1], frames.shape[2]
         nc = (F + k - 1) // k
         dev = frames.device
@@ -108,7 +117,7 @@ class PropagatedPath:
         self.frames, self.k, self.F, self.Himg, self.Wimg = frames, k, F, Himg, Wimg
         self.calibration = calibration
         self.detect = detect
-        self.carry = carry
+        self.carry = None
         self.pyr = e.gray_pyramid(frames, LK_MAX_LEVEL)
         st = self.st = _Sets(k, nc, dev)
         idx = np.arange(k)[:, None] + np.arange(nc)[None, :] * k
@@ -163,6 +172,16 @@ class PropagatedPath:
                 snap.order.record_stream(side); snap.count.record_stream(side)
             self._fit_commit(s, 0, n_s)
 
+        self._flow_cnt = flow_cnt
+
+    def repair(self, carry: dict | None) -> None:
+        """Read back once, then re-run, in frame order, the chains whose speculation was wrong.  ``carry`` =
+        ``carry_out`` of the previous piece (None for the first piece of a clip)."""
+        st, k, F = self.st, self.k, self.F
+        nc = st.retry.numel()
+        flow_cnt = self._flow_cnt
+        self.carry = carry
+        assert (carry is None) == (self.base == 0)
         # ---- one read-back, then the repairs in frame order: chains whose speculation was wrong
         #  * a frame whose flow kept < 4 points (the reference then asks the network, :316-320),
         #  * a head with < 4 landmarks (flow from the previous chain joins in, :308-311; frame 0: :288-307),
@@ -185,6 +204,10 @@ class PropagatedPath:
         last = F - 1
         self.carry_out = {"retry": int(retry_final[nc - 1]), "kp": _clone(st.kp(last % k, last // k, last // k + 1))}
 
+    def outputs(self) -> dict:
+        e, st, k, F = self.e, self.st, self.k, self.F
+        nc = st.retry.numel()
+        calibration = self.calibration
         # ---- back to frame order (chain-major == frame order), cadence lookup of the H each frame uses
         fo = lambda t: t.transpose(0, 1).reshape((nc * k,) + tuple(t.shape[2:]))[:F].contiguous()
         if calibration:

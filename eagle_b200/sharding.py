@@ -120,3 +120,89 @@ def run_sharded(path, heatmaps_local: torch.Tensor, objects_local: Sequence[dict
     c = lambda t: t.cpu().numpy()
     return assemble_frames(objects_per_frame, fps, 0, c(xy), c(order), c(count), c(used), c(inl), c(status), c(attempted),
                            c(h_index), c(proj.coords_i), c(proj.in_bounds), c(proj.bounds))
+
+
+def chain_range(n_frames: int, keypoint_interval: int, rank: int, world: int) -> tuple[int, int]:
+    """Frame range [lo, hi) of ``rank`` when the clip is cut between chains (a chain = one network frame and the
+    frames propagated from it): boundaries are multiples of the keypoint interval."""
+    nc = (n_frames + keypoint_interval - 1) // keypoint_interval
+    c0, c1 = frame_range(nc, rank, world)
+    return min(c0 * keypoint_interval, n_frames), min(c1 * keypoint_interval, n_frames)
+
+
+def run_sharded_propagated(engine, frames_local: torch.Tensor, head_heatmaps_local: torch.Tensor, detect, objects_local: Sequence[dict],
+                           fps: int, keypoint_interval: int, homography_interval: int, first_frame: int, calibration: bool = False,
+                           keypoint_conf: float = 0.3, group=None):
+    """The sparse keypoint cadence (eagle_b200.propagation) for one clip cut between chains over the ranks.
+
+    Rank r holds the frames of its chain_range -- plus, when first_frame > 0, ONE leading frame (the last frame
+    of rank r-1) -- and the network's heatmaps of its chain heads.  Every rank runs its parallel pass at once;
+    then the boundary state (final keypoint set + retry flag, < 1 KB) is handed from rank to rank while each
+    repairs the few chains that depend on it, and the per-frame results are gathered to rank 0, which looks up
+    the homography cadence over the whole clip, projects and assembles the dict.  Returns it on rank 0."""
+    from .boxes import objects_to_arrays
+    from .coordinate_model import assemble_frames
+    from .engine import KeypointSet
+    from .propagation import PropagatedPath, finalize
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    backend = dist.get_backend(group) if (dist.is_initialized() and world > 1) else None
+    dev = engine.device
+    height, width = frames_local.shape[1], frames_local.shape[2]
+    prop = PropagatedPath(engine, keypoint_conf)
+    prop.start(frames_local, head_heatmaps_local, detect, keypoint_interval, homography_interval, calibration, first_frame=first_frame)
+
+    def carry_like():
+        return [torch.zeros((1, 57, 2), dtype=torch.int32, device=dev), torch.zeros((1, 64), dtype=torch.uint8, device=dev),
+                torch.zeros((1, 2), dtype=torch.int32, device=dev), torch.zeros((1, 64), dtype=torch.uint8, device=dev),
+                torch.zeros((1, 1), dtype=torch.int32, device=dev)]
+
+    carry = None
+    if rank > 0:
+        buf = pack_results(carry_like())
+        buf = buf.cpu() if backend == "gloo" else buf
+        dist.recv(buf, src=rank - 1, group=group)
+        xy, order, count, src, retry = unpack_results(buf.to(dev), carry_like())
+        carry = {"retry": int(retry.item()), "kp": KeypointSet(None, None, xy, order, count, src)}
+    prop.repair(carry)
+    if rank < world - 1:
+        co = prop.carry_out
+        msg = pack_results([co["kp"].xy, co["kp"].order, co["kp"].count, co["kp"].src,
+                            torch.tensor([[co["retry"]]], dtype=torch.int32, device=dev)])
+        dist.send(msg.cpu() if backend == "gloo" else msg, dst=rank + 1, group=group)
+    out = prop.outputs()
+
+    F_r = out["xy"].shape[0]
+    local_meta = (F_r, max([1] + [sum(len(v) for v in o.values()) for o in objects_local]), dict(prop.stats))
+    metas = [None] * world
+    if world > 1:
+        dist.all_gather_object(metas, local_meta, group=group)
+    else:
+        metas = [local_meta]
+    counts = [m[0] for m in metas]
+    P = max(m[1] for m in metas)
+    foot_h, cnt_h = objects_to_arrays(list(objects_local), P)
+    foot = torch.from_numpy(foot_h).to(dev); cnt = torch.from_numpy(cnt_h).to(dev)
+    like = [out["xy"], out["order"], out["count"], out["src"], out["H"], out["fit_ok"], out["status"], out["inlier_mask"], foot, cnt]
+    rec = pack_results(like)
+    if backend == "gloo":
+        rec = rec.cpu()
+    all_rec = gather_to_rank0(rec, counts, group) if world > 1 else rec
+    objs_all = [None] * world
+    if world > 1:
+        dist.gather_object(list(objects_local), objs_all if rank == 0 else None, dst=0, group=group)
+    else:
+        objs_all = [list(objects_local)]
+    if rank != 0:
+        return None
+    xy, order, count, src, H, fit_ok, status, inl, foot_a, cnt_a = unpack_results(all_rec.to(dev), like)
+    whole = finalize(engine, [{"xy": xy, "order": order, "count": count, "src": src, "H": H.contiguous(), "fit_ok": fit_ok.contiguous(),
+                               "status": status.contiguous(), "inlier_mask": inl}])
+    proj = engine.project(whole["H"], foot_a.contiguous(), cnt_a.contiguous(), width, height, h_index=whole["h_index"])
+    objects_per_frame = [o for part in objs_all for o in part]
+    c = lambda t: t.cpu().numpy()
+    res = assemble_frames(objects_per_frame, fps, 0, c(xy), c(order), c(count), None, None, None, None, c(whole["h_index"]),
+                          c(proj.coords_i), c(proj.in_bounds), c(proj.bounds), kp_src=c(src))
+    run_sharded_propagated.last_stats = [m[2] for m in metas]
+    return res

@@ -363,3 +363,50 @@ def test_propagated_path_full_size_properties(engine):
         for name, v in got[i]["Keypoints"].items():
             worst = max(worst, float(np.hypot(v[0] - px[LANDMARK_INDEX[name], 0], v[1] - px[LANDMARK_INDEX[name], 1])))
     assert worst < 40.0, worst
+
+
+def _sharded_flow_worker(rank, world, port, scenario, q):
+    import torch.distributed as dist
+    from eagle_b200.engine import GeometryEngine
+    from eagle_b200.sharding import chain_range, run_sharded_propagated
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        eng = GeometryEngine("cuda:0")
+        n, k, h, fps = 14, 4, 8, 8
+        if scenario == "plain":
+            clip = synthetic.make_flow_clip(n, W, H, seed=110, pan_px=2.0)
+        else:  # blank head + 3-landmark head on shard boundaries, retry flag crossing, fallback frame
+            clip = synthetic.make_flow_clip(n, W, H, seed=22, pan_px=2.0)
+            clip["heatmaps"][4] = 0.01; clip["heatmaps"][8, 3:] = 0.01; clip["frames"][10] = 0
+        lo, hi = chain_range(n, k, rank, world)
+        halo = 1 if lo > 0 else 0
+        dev_frames = torch.from_numpy(np.ascontiguousarray(clip["frames"][lo - halo:hi])).cuda()
+        net = _Net(eng, clip["frames"], clip["heatmaps"])
+        x_heads = eng.preprocess(dev_frames[halo::k].contiguous())
+        heads = net(x_heads).contiguous()
+        detect = lambda i: net(eng.preprocess(dev_frames[halo + i - lo:halo + i - lo + 1].contiguous())).contiguous()
+        res = run_sharded_propagated(eng, dev_frames, heads, detect, clip["objects"][lo:hi], fps, k, h, first_frame=lo)
+        if rank == 0:
+            want = pipeline.get_coordinates_propagated(list(clip["frames"]), clip["heatmaps"], clip["objects"], fps, 1, 2)
+            q.put(json.dumps(res, default=float) == json.dumps(want, default=float))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,scenario", [(2, "plain"), (3, "rescues")])
+def test_sparse_cadence_sharded_between_chains(world, scenario):
+    """Chains shard over ranks (here the ranks share cuda:0 and talk over gloo; NCCL on a multi-GPU box): the
+    parallel passes run at once, the boundary state is handed from rank to rank, rank 0 assembles the dict."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_flow_worker, args=(r, world, port, scenario, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
