@@ -61,3 +61,17 @@ def test_gather_to_rank0_gloo(world, n_frames):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_chain_range_cuts_between_chains():
+    """Ranges of the sparse keypoint cadence: contiguous, covering, every boundary a multiple of the interval."""
+    from eagle_b200.sharding import chain_range
+    for n in (1, 7, 8, 9, 26, 2250, 135000):
+        for k in (1, 3, 8, 25):
+            for world in (1, 2, 3, 8):
+                prev = 0
+                for r in range(world):
+                    lo, hi = chain_range(n, k, r, world)
+                    assert lo == prev and lo <= hi <= n and (lo % k == 0 or lo == n)
+                    prev = hi
+                assert prev == n
