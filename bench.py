@@ -426,6 +426,20 @@ def main():
                                        "frac": pyr_bytes / (g_ms * 1e-3) / 1e9 / peak,
                                        "algorithmic_bytes_per_frame": H * W * 3 + int(N.lib.egl_pyramid_bytes(H, W, 2))},
                       "parity": "bit-exact with cv2.calcOpticalFlowPyrLK / the reference's dict (tests/test_gpu_flow.py)"}
+        if rank == 0 and not args.no_cpu_baseline:
+            # the reference's CPU statements for the same cadence (cv2.calcOpticalFlowPyrLK, cv2.cvtColor, cv2.fitLine,
+            # cv2.findHomography, cv2.perspectiveTransform), one thread, on the first chains of the same clip
+            from oracle import pipeline as _pipe
+            n_cpu = min(F, 50 * kint)
+            fr_h = pf[:n_cpu].cpu().numpy()
+            hm_h = {i: heads[i // kint].cpu().numpy() for i in range(0, n_cpu, kint)}
+            objs_h = [pool["objects"][i % len(pool["objects"])] for i in range(n_cpu)]
+            t_c = time.perf_counter()
+            _pipe.get_coordinates_propagated(list(fr_h), hm_h, objs_h, fps_ref, 1, 3, library_calls=True)
+            dt_c = time.perf_counter() - t_c
+            propagated["cpu_baseline"] = {"value": n_cpu / dt_c, "unit": "frames/s", "cores": 1, "kind": "port",
+                                          "sample": f"first {n_cpu} frames of the same clip, one thread: the reference's cv2/numpy calls for this "
+                                                    "cadence (oracle/pipeline.py, library_calls=True); K1 and the network not included on either side"}
 
     if rank != 0:
         if world > 1:

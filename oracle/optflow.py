@@ -375,3 +375,41 @@ def calibrate_keypoints_restated(frame: np.ndarray, keypoints: dict) -> dict:
         by, bx = np.unravel_index(np.argmax(v), v.shape)
         out[key] = (np.clip(x + bx - OFFSET, 0, w - 1), np.clip(y + by - OFFSET, 0, h - 1))
     return out
+
+
+def calculate_optical_flow_cv2(frame, prev_gray, prev_keypoints: dict, curr_gray, win=15, max_level=2, max_count=10, eps=0.03) -> dict:
+    """coordinate_model.py:419-478 with the library calls the reference itself makes (cv2.calcOpticalFlowPyrLK,
+    cv2.cvtColor, numpy statistics): the CPU baseline of the propagation step, and a cross-check of the
+    restated version above."""
+    import cv2
+    if prev_gray is None or curr_gray is None or prev_keypoints is None or len(prev_keypoints) == 0:
+        return {}
+    prev_points = np.array(list(prev_keypoints.values()), dtype=F32)
+    if prev_points.ndim != 2 or prev_points.shape[0] == 0 or prev_points.shape[1] != 2:
+        return {}
+    new_points, status, _ = cv2.calcOpticalFlowPyrLK(prev_gray, curr_gray, prev_points, None, winSize=(win, win), maxLevel=max_level,
+                                                     criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, max_count, eps))
+    new_points = new_points[status[:, 0] == 1]
+    prev_points = prev_points[status[:, 0] == 1]
+    out = {}
+    if len(new_points) == 0:
+        return out
+    move = np.linalg.norm(new_points - prev_points, axis=1)
+    mean = np.mean(move)
+    std = np.std(move) + 1e-6
+    keys = list(prev_keypoints.keys())
+    h, w = frame.shape[:2]
+
+    def mean_hue(pt):
+        x, y = pt.astype(int)
+        x = np.clip(x, 0, w - 1); y = np.clip(y, 0, h - 1)
+        grid = frame[max(0, y - 1):min(h, y + 2), max(0, x - 1):min(w, x + 2)]
+        return np.mean(cv2.cvtColor(grid, cv2.COLOR_BGR2HSV)[:, :, 0])
+
+    for j, (point, new_point) in enumerate(zip(prev_points, new_points)):
+        if (move[j] - mean) / std > 2:
+            continue
+        if abs(mean_hue(new_point) - mean_hue(point)) > 25:
+            continue
+        out[keys[j]] = tuple(new_point.astype(int))
+    return out

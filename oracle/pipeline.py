@@ -95,7 +95,7 @@ def get_coordinates(heatmaps, objects_per_frame, width: int, height: int, fps: i
 
 def get_coordinates_propagated(frames, heatmaps, objects_per_frame, fps: int, num_homography: int = 1,
                                num_keypoint_detection: int = 1, calibration: bool = False, keypoint_conf: float = 0.3,
-                               fit=None, trace: list | None = None) -> dict:
+                               fit=None, trace: list | None = None, library_calls: bool = False) -> dict:
     """The full frame loop of ``get_coordinates`` (coordinate_model.py:205-417) including the sparse
     keypoint cadence: the network's heatmaps are decoded every ``keypoint_interval`` frames (:206,:216)
     and the landmarks are carried in between by Lucas-Kanade flow (:313-322), with the model fallback
@@ -103,15 +103,20 @@ def get_coordinates_propagated(frames, heatmaps, objects_per_frame, fps: int, nu
 
     frames: sequence of (H, W, 3) uint8 BGR; heatmaps: indexable by frame (only the frames the loop
     actually asks the network about are read).  Built from the restated pieces in oracle/optflow.py,
-    each pinned against the live library."""
+    each pinned against the live library; library_calls=True swaps in the cv2 calls themselves."""
     from . import optflow as _of
 
     height, width = frames[0].shape[:2]
     homography_interval = max(1, int(fps / max(1, num_homography)))
     keypoint_interval = max(1, int(fps / max(1, num_keypoint_detection)))
     detect = lambda j: _decode.decode_frame(np.asarray(heatmaps[j]), width, height, keypoint_conf)  # :480-518
-    gray = lambda j: _of.gray_restated(frames[j])
-    flow = lambda frame, pg, pk, cg: _of.calculate_optical_flow_restated(frame, pg, pk, cg)
+    if library_calls:  # the reference's own cv2 calls instead of their restatements (CPU baseline; same results)
+        import cv2
+        gray = lambda j: cv2.cvtColor(frames[j], cv2.COLOR_BGR2GRAY)
+        flow = lambda frame, pg, pk, cg: _of.calculate_optical_flow_cv2(frame, pg, pk, cg)
+    else:
+        gray = lambda j: _of.gray_restated(frames[j])
+        flow = lambda frame, pg, pk, cg: _of.calculate_optical_flow_restated(frame, pg, pk, cg)
     prev_gray = None
     prev_keypoints = {}
     res = {}

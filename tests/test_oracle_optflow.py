@@ -151,3 +151,12 @@ def test_oracle_reproduces_flow_golden(golden_dir, cal):
     mine = P.get_coordinates_propagated(frames, clip["heatmaps"], clip["objects"], int(g["fps"]), int(g["num_homography"]),
                                         int(g["num_keypoint_detection"]), calibration=cal)
     assert json.dumps(mine, default=float, sort_keys=True) == str(g["result_json_cal" if cal else "result_json"])
+
+
+def test_library_call_variant_equals_restated_pipeline():
+    """oracle/pipeline.py with the cv2 calls themselves (the CPU baseline bench.py times) == the restated pieces."""
+    c = S.make_flow_clip(12, 640, 360, seed=5, pan_px=2.0)
+    c["heatmaps"][4] = 0.01
+    a = P.get_coordinates_propagated(list(c["frames"]), c["heatmaps"], c["objects"], 8, 1, 2)
+    b = P.get_coordinates_propagated(list(c["frames"]), c["heatmaps"], c["objects"], 8, 1, 2, library_calls=True)
+    assert json.dumps(a, default=float) == json.dumps(b, default=float)
