@@ -266,6 +266,16 @@ def test_sparse_cadence_clip_identical_to_oracle(engine, fps, nh, nk, cal, n):
     assert sorted(set(net.calls)) == list(range(0, n, k))  # the network ran on the chain heads only
 
 
+@pytest.mark.parametrize("n", [1, 2, 5])
+def test_sparse_cadence_very_short_clips(engine, n):
+    """Clips shorter than one chain (and one frame longer than a chain)."""
+    clip = synthetic.make_flow_clip(n, W, H, seed=40 + n, pan_px=2.0)
+    got, want, stats, _ = _run_both(engine, clip, 8, 1, 2)   # keypoint interval 4
+    _same(got, want)
+    got, want, stats, _ = _run_both(engine, clip, 8, 1, 2, cal=True, piece=4)
+    _same(got, want)
+
+
 def test_sparse_cadence_rescues_identical_to_oracle(engine):
     """The rare branches: first-frame rescue (:288-307), a head with < 4 landmarks (:308-311), flow that
     loses the scene (:316-320), a failed fit whose retry flag crosses a chain boundary (:333)."""
