@@ -247,7 +247,7 @@ class CoordinateModel:
                                     all_obj=None) -> dict:
         """Any cadence: frames to HBM, network on the chain heads, PropagatedPath, projection, dict assembly.
         Clips longer than ``piece_frames`` go through in pieces (whole chains each; the boundary state is carried)."""
-        from .propagation import PropagatedPath, finalize
+        from .propagation import FirstPieceTooShort, PropagatedPath, finalize
         e = self.path.engine
         height, width = frames[0].shape[:2]
         if all_obj is None:
@@ -257,8 +257,10 @@ class CoordinateModel:
         prop = PropagatedPath(e, self.keypoint_conf)
         pieces, carry, prev_last = [], None, None
         stats = {"fallback_frames": 0, "repaired_chains": 0, "first_frame_rescue": False, "pieces": 0}
-        for g0 in range(0, len(frames), piece):
-            n = min(piece, len(frames) - g0)
+        g0 = 0
+        first_piece = piece
+        while g0 < len(frames):
+            n = min(first_piece if g0 == 0 else piece, len(frames) - g0)
             halo = 0 if carry is None else 1
             buf = torch.empty((halo + n, height, width, 3), dtype=torch.uint8, device=self.device)
             if halo:
@@ -267,9 +269,14 @@ class CoordinateModel:
             buf[halo:].copy_(host.pin_memory(), non_blocking=True)
             heads = [halo + i for i in range(0, n, k)]
             hm = torch.cat([self._heatmaps_dev(buf[heads[s:s + self.chunk]]) for s in range(0, len(heads), self.chunk)])
-            pieces.append(prop.run(buf, hm, lambda i, buf=buf, g0=g0, halo=halo: self._heatmaps_dev(buf[halo + i - g0:halo + i - g0 + 1]),
-                                   k, homography_interval, calibration, first_frame=g0, carry=carry))
+            try:
+                pieces.append(prop.run(buf, hm, lambda i, buf=buf, g0=g0, halo=halo: self._heatmaps_dev(buf[halo + i - g0:halo + i - g0 + 1]),
+                                       k, homography_interval, calibration, first_frame=g0, carry=carry, clip_continues=g0 + n < len(frames)))
+            except FirstPieceTooShort:
+                first_piece *= 2  # the reference's scan for the first usable frame (:290-297) runs past this piece: take a longer one
+                continue
             carry, prev_last = prop.carry_out, buf[-1].clone()
+            g0 += n
             for key in ("fallback_frames", "repaired_chains"):
                 stats[key] += prop.stats[key]
             stats["first_frame_rescue"] |= prop.stats["first_frame_rescue"]

@@ -33,6 +33,11 @@ from .pitch import NUM_LANDMARKS
 LK_MAX_LEVEL, LK_MAX_COUNT, LK_EPS = 2, 10, 0.03  # lk_params, coordinate_model.py:65
 
 
+class FirstPieceTooShort(RuntimeError):
+    """Frame 0 decoded < 4 landmarks and no frame of the first piece has >= 4: the reference's forward scan
+    (coordinate_model.py:290-297) would go on into later frames, so the caller must retry with a longer first piece."""
+
+
 class _Sets:
     """(step, chain) arrays of keypoint sets and fit results."""
 
@@ -86,7 +91,7 @@ class PropagatedPath:
     # ---------------------------------------------------------------------------------------------
     def run(self, frames: torch.Tensor, head_heatmaps: torch.Tensor, detect: Callable[[int], torch.Tensor] | None,
             keypoint_interval: int, homography_interval: int, calibration: bool = False, *, first_frame: int = 0,
-            carry: dict | None = None) -> dict:
+            carry: dict | None = None, clip_continues: bool = False) -> dict:
         """frames (F, H, W, 3) uint8 BGR CUDA; head_heatmaps (ceil(F/k), 57, h, w) float32 CUDA = the network's
         output for frames 0, k, 2k, ...; detect(i) -> (1, 57, h, w) heatmaps of frame i on demand.
 
@@ -97,14 +102,17 @@ class PropagatedPath:
         Returns device tensors in frame order: xy, order, count, src (the "Keypoints" of every frame),
         H (F, 9), fit_ok (F,), h_index (F,) (valid for a single piece; see ``finalize``) and counters in ``self.stats``."""
         assert (carry is None) == (first_frame == 0), "carry comes with every piece but the first"
-        self.start(frames, head_heatmaps, detect, keypoint_interval, homography_interval, calibration, first_frame=first_frame)
+        self.start(frames, head_heatmaps, detect, keypoint_interval, homography_interval, calibration, first_frame=first_frame,
+                   clip_continues=clip_continues)
         self.repair(carry)
         return self.outputs()
 
     def start(self, frames: torch.Tensor, head_heatmaps: torch.Tensor, detect, keypoint_interval: int, homography_interval: int,
-              calibration: bool = False, *, first_frame: int = 0) -> None:
+              calibration: bool = False, *, first_frame: int = 0, clip_continues: bool = False) -> None:
         """The parallel pass of one piece (everything that does not need the previous piece's final state).
-        Pieces after the first (first_frame > 0) carry one extra leading frame.  ``repair`` must follow."""
+        Pieces after the first (first_frame > 0) carry one extra leading frame.  ``repair`` must follow.
+        clip_continues: more frames follow this piece (only matters for the first-frame rescue, see FirstPieceTooShort)."""
+        self.clip_continues = clip_continues
         e = self.e
         k = int(keypoint_interval)
         self.g0 = int(first_frame)
@@ -189,8 +197,8 @@ class PropagatedPath:
         host = torch.stack([self.heads.count[:, 0], st.retry.to(torch.int32), (flow_cnt < 4).any(dim=0).to(torch.int32)]).cpu().numpy()
         head_cnt, retry_final, short = host[0], host[1].copy(), host[2]
         rerun_upto = -1
-        if carry is None and head_cnt[0] < 4 and F > 1:
-            rerun_upto = self._rescue_first_frame()  # (the forward scan of :290-297 stays inside this piece)
+        if carry is None and head_cnt[0] < 4 and (F > 1 or self.clip_continues):
+            rerun_upto = self._rescue_first_frame()
         for c in range(nc):
             incoming = int(retry_final[c - 1]) if c > 0 else (int(carry["retry"]) if carry is not None else 0)
             head = self.extra_mem.get(c * k)
@@ -336,6 +344,8 @@ class PropagatedPath:
                 prev = d
                 break
         if prev is None:
+            if self.clip_continues:
+                raise FirstPieceTooShort(f"no frame with >= 4 landmarks among the first {F}")
             return -1
         next_idx = j
         for jj in range(j - 1, -1, -1):

@@ -327,10 +327,17 @@ def test_sparse_cadence_in_pieces_identical_to_oracle(engine):
         clip = synthetic.make_flow_clip(14, W, H, seed=21, pan_px=2.0); clip["heatmaps"][0:2] = 0.01
         got, want, stats, _ = _run_both(engine, clip, 8, 1, 2, cal=True, piece=piece)
         _same(got, want); assert stats["first_frame_rescue"]
+    # the scan for the first usable frame runs past the first piece (frames 0-5 blank, pieces of 4): the adapter retries longer
+    clip = synthetic.make_flow_clip(14, W, H, seed=27, pan_px=2.0); clip["heatmaps"][0:6] = 0.01
+    got, want, stats, _ = _run_both(engine, clip, 8, 1, 2, piece=4)
+    _same(got, want); assert stats["first_frame_rescue"]
     # interval 1 in pieces of one frame: every frame is a piece
     clip = synthetic.make_flow_clip(8, W, H, seed=25, pan_px=2.0); clip["heatmaps"][3] = 0.01
     got, want, stats, _ = _run_both(engine, clip, 1, 1, 1, piece=1)
     _same(got, want); assert stats["pieces"] == 8
+    clip["heatmaps"][0:2] = 0.01   # ... and the clip starts blank: the one-frame first piece has to grow
+    got, want, stats, _ = _run_both(engine, clip, 1, 1, 1, piece=1)
+    _same(got, want); assert stats["first_frame_rescue"]
 
 
 def test_sparse_cadence_golden_from_reference(engine, golden_dir):
