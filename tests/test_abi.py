@@ -48,3 +48,31 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_assembler_reproduces_reference_value_types():
+    """Host-side dict assembly for the sparse cadence: kp_src says which Python type the reference holds each
+    keypoint value in (int tuple / numpy-int tuple / float list) -- json.dumps(default=float) depends on it."""
+    import json
+
+    import numpy as np
+
+    from eagle_b200 import _native as N
+    from eagle_b200.coordinate_model import assemble_frames
+    from eagle_b200.pitch import LANDMARK_NAMES
+    xy = np.zeros((2, 57, 2), np.int32); order = np.zeros((2, 64), np.uint8); count = np.zeros((2, 2), np.int32); src = np.zeros((2, 64), np.uint8)
+    order[0, :3] = (42, 13, 5); count[0] = (3, 3)
+    xy[0, 42] = (10, 20); xy[0, 13] = (30, 40); xy[0, 5] = (50, 60)
+    src[0, 42] = N.KP_PY_INT; src[0, 13] = N.KP_NUMPY_INT; src[0, 5] = N.KP_FLOAT
+    objs = [{"Player": {}, "Goalkeeper": {}}, {"Player": {7: {"BBox": [1, 2, 3, 4], "Confidence": 0.5, "Bottom_center": [2, 4]}}, "Goalkeeper": {}}]
+    res = assemble_frames(objs, 25, 0, xy, order, count, None, None, None, None, np.array([-1, -1], np.int32),
+                          np.zeros((2, 1, 2), np.int64), np.zeros((2, 1), np.uint8), np.full((2, 4), np.nan), kp_src=src)
+    kp = res[0]["Keypoints"]
+    assert list(kp) == [LANDMARK_NAMES[42], LANDMARK_NAMES[13], LANDMARK_NAMES[5]]
+    a, b, c = kp.values()
+    assert a == (10, 20) and type(a) is tuple and type(a[0]) is int
+    assert type(b) is tuple and isinstance(b[0], np.int64) and tuple(int(v) for v in b) == (30, 40)
+    assert c == [50.0, 60.0] and type(c) is list and type(c[0]) is float
+    assert json.dumps(kp, default=float) == '{"%s": [10, 20], "%s": [30.0, 40.0], "%s": [50.0, 60.0]}' % tuple(kp)
+    assert res[1]["Keypoints"] == {} and res[1]["Boundaries"] == [None] * 4
+    assert res[1]["Coordinates"]["Player"][7]["Transformed_Coordinates"] is None and res[1]["Time"] == "00:00"
