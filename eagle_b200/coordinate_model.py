@@ -173,6 +173,7 @@ class CoordinateModel:
         self._detect_objects = detect_objects
         self.chunk = chunk
         self.path = GeometryPath(device, keypoint_conf)
+        self._staging, self._staged = None, [None, None]
         self.always_propagate = False  # route every clip through PropagatedPath (tests)
         self.piece_frames = 2048       # sparse cadence: frames resident in HBM at a time (12.7 GB of 1080p frames + 5.6 GB of pyramids)
         self.last_stats = {}
@@ -190,6 +191,25 @@ class CoordinateModel:
         x = self.path.engine.preprocess(dev_frames.contiguous())
         outs = [self.keypoint_model(x[i:i + BATCH]) for i in range(0, x.shape[0], BATCH)]
         return torch.cat(outs).to(torch.float32).contiguous()
+
+    def _upload(self, frames: Sequence[np.ndarray], dst: torch.Tensor, group: int = 32) -> None:
+        """Host frames -> dst (n, H, W, 3) on the device through two reusable page-locked staging buffers
+        (a page-locked copy of a whole piece would cost a multi-GB cudaHostAlloc per call)."""
+        n = len(frames)
+        shape = (min(group, max(n, 1)),) + tuple(dst.shape[1:])
+        if self._staging is None or tuple(self._staging[0].shape[1:]) != shape[1:] or self._staging[0].shape[0] < shape[0]:
+            self._staging = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self._staged = [None, None]
+        for b, s in enumerate(range(0, n, shape[0])):
+            slot = b & 1
+            if self._staged[slot] is not None:
+                self._staged[slot].synchronize()   # the previous copy out of this buffer has finished
+            m = min(shape[0], n - s)
+            stage = self._staging[slot].numpy()
+            for j in range(m):
+                np.copyto(stage[j], frames[s + j])
+            dst[s:s + m].copy_(self._staging[slot][:m], non_blocking=True)
+            self._staged[slot] = torch.cuda.current_stream(self.device).record_event()
 
     @torch.no_grad()
     def _heatmaps(self, frames: Sequence[np.ndarray]) -> torch.Tensor:
@@ -265,8 +285,7 @@ class CoordinateModel:
             buf = torch.empty((halo + n, height, width, 3), dtype=torch.uint8, device=self.device)
             if halo:
                 buf[0].copy_(prev_last)
-            host = torch.from_numpy(np.ascontiguousarray(np.stack(frames[g0:g0 + n])))
-            buf[halo:].copy_(host.pin_memory(), non_blocking=True)
+            self._upload(frames[g0:g0 + n], buf[halo:])
             heads = [halo + i for i in range(0, n, k)]
             hm = torch.cat([self._heatmaps_dev(buf[heads[s:s + self.chunk]]) for s in range(0, len(heads), self.chunk)])
             try:
