@@ -424,7 +424,6 @@ __global__ void __launch_bounds__(kPostWarps * 32) postprocess_kernel(const int3
     __syncwarp();
     const unsigned long long kept_mask = ((unsigned long long)kept_bits[1] << 32) | kept_bits[0];
     unsigned emit_bits[2];
-    int label[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int c = lane + 32 * h;
@@ -447,7 +446,6 @@ __global__ void __launch_bounds__(kPostWarps * 32) postprocess_kernel(const int3
             }
         }
         emit_bits[h] = __ballot_sync(kFull, emit);
-        label[h] = last;
         if (emit) {
             const int pos = (h ? __popc(emit_bits[0]) : 0) + __popc(emit_bits[h] & ((1u << lane) - 1u));
             kp_order[(size_t)f * EGL_ORDER_STRIDE + pos] = (uint8_t)last;

@@ -12,50 +12,14 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "flow_core.cuh"  // the scalar statement of the same arithmetic (also compiled for the host by the CPU tests)
 
 namespace egl {
 
-constexpr int kWin = 15;         // lk_params winSize (coordinate_model.py:65)
-constexpr int kHalf = 7;         // (winSize - 1) / 2
-constexpr int kWinPx = kWin * kWin;
-constexpr int kMaxLevels = 4;    // maxLevel <= 3
-constexpr int kWBits = 14;
-
-struct PyrLayout {
-    int n;
-    int w[kMaxLevels], h[kMaxLevels];
-    long long off[kMaxLevels];
-    long long bytes;
-};
-
-// buildOpticalFlowPyramid: halve until a level would not be larger than the window
-static PyrLayout pyramid_layout(int H, int W, int max_level) {
-    PyrLayout L{};
-    int w = W, h = H;
-    long long off = 0;
-    for (int l = 0; l <= max_level && l < kMaxLevels; ++l) {
-        if (l > 0) {
-            w = (w + 1) / 2;
-            h = (h + 1) / 2;
-            if (w <= kWin || h <= kWin) break;
-        }
-        L.w[l] = w;
-        L.h[l] = h;
-        L.off[l] = off;
-        off += ((long long)w * h + 15) / 16 * 16;
-        L.n++;
-    }
-    L.bytes = off;
-    return L;
-}
-
-__device__ __forceinline__ int reflect101(int i, int n) {
-    if (n == 1) return 0;
-    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
-    return i;
-}
-
-__device__ __forceinline__ int gray_of(int b, int g, int r) { return (b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15; }
+constexpr int kWin = kLkWin;      // 15: lk_params winSize (coordinate_model.py:65)
+constexpr int kHalf = kLkHalf;    // (winSize - 1) / 2
+constexpr int kMaxLevels = kLkMaxLevels;
+constexpr int kWBits = kLkWBits;
 
 // ------------------------------------------------------------------------------------------------
 // gray + pyramid
@@ -285,20 +249,6 @@ struct TrackArgs {
     float* out_pts;
     uint8_t* out_status;
 };
-
-__device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
-    const float s = (float)(1 << kWBits);
-    const float na = __fsub_rn(1.f, a), nb = __fsub_rn(1.f, b);
-    w00 = __float2int_rn(__fmul_rn(__fmul_rn(na, nb), s));
-    w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, nb), s));
-    w10 = __float2int_rn(__fmul_rn(__fmul_rn(na, b), s));
-    w11 = (1 << kWBits) - w00 - w01 - w10;
-}
-
-// (l0 + l2) + (l1 + l3): the movehl/shuffle reduction of a 4-lane float register
-__device__ __forceinline__ float reduce4(float l0, float l1, float l2, float l3) {
-    return __fadd_rn(__fadd_rn(l0, l2), __fadd_rn(l1, l3));
-}
 
 __device__ __forceinline__ void unpack9(const uint8_t* row8, int* v) {  // 9 bytes from an 8-byte aligned shared address
     const uint32_t* w = reinterpret_cast<const uint32_t*>(row8);
@@ -548,6 +498,23 @@ __global__ void __launch_bounds__(kTrackWarps * 32) track_kernel(TrackArgs a) {
     }
 }
 
+// The same tracker as one thread per point: lk_track_point of flow_core.cuh, the scalar statement that the
+// CPU suite compiles for the host and holds against live cv2.  EGL_TRACK_VARIANT=1 selects it (cross-check
+// of the warp kernel above; ~20x slower).
+__global__ void __launch_bounds__(64) track_thread_kernel(TrackArgs a) {
+    const int p = blockIdx.x, j = threadIdx.x;
+    if (j >= min(a.kp_count[2 * p], kMaxPts)) return;
+    const int ch = a.kp_order[(size_t)p * EGL_ORDER_STRIDE + j];
+    const uint8_t* I = a.pyr + (long long)(a.prev0 + p * a.fstep) * a.pyr_stride;
+    const uint8_t* J = a.pyr + (long long)(a.next0 + p * a.fstep) * a.pyr_stride;
+    float out[2];
+    const int status = lk_track_point(I, J, a.L, (float)a.kp_xy[((size_t)p * kLandmarks + ch) * 2],
+                                      (float)a.kp_xy[((size_t)p * kLandmarks + ch) * 2 + 1], a.max_count, a.eps2, a.min_eig, out);
+    a.out_pts[((size_t)p * kMaxPts + ch) * 2] = out[0];
+    a.out_pts[((size_t)p * kMaxPts + ch) * 2 + 1] = out[1];
+    a.out_status[(size_t)p * kMaxPts + ch] = (uint8_t)status;
+}
+
 // ------------------------------------------------------------------------------------------------
 // the reference's filters on the tracked points (coordinate_model.py:438-478): one warp per frame pair
 // ------------------------------------------------------------------------------------------------
@@ -570,25 +537,6 @@ struct FilterArgs {
     uint8_t* out_src;
 };
 
-// numpy's pairwise float32 sum for n <= 128 (sequential for n < 8, else 8 interleaved accumulators)
-__device__ float pairwise_sum_f32(const float* v, int n) {
-    if (n < 8) {
-        float s = n > 0 ? v[0] : 0.f;  // numpy starts from the first element (-0.0 matters not here)
-        for (int i = 1; i < n; ++i) s = __fadd_rn(s, v[i]);
-        return s;
-    }
-    float r[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = v[k];
-    int i = 8;
-    for (; i + 8 <= n; i += 8)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = __fadd_rn(r[k], v[i + k]);
-    float s = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-    for (; i < n; ++i) s = __fadd_rn(s, v[i]);
-    return s;
-}
-
 // mean hue (cv2 BGR2HSV, 0..179) of the clipped 3x3 block around (x, y), as np.mean gives it (float64)
 __device__ double mean_hue_3x3(const uint8_t* frame, int H, int W, long long row_stride, long long xi, long long yi) {
     const int x = (int)max(0ll, min(xi, (long long)W - 1)), y = (int)max(0ll, min(yi, (long long)H - 1));
@@ -597,12 +545,7 @@ __device__ double mean_hue_3x3(const uint8_t* frame, int H, int W, long long row
     for (int yy = y0; yy < y1; ++yy)
         for (int xx = x0; xx < x1; ++xx) {
             const uint8_t* px = frame + (long long)yy * row_stride + 3ll * xx;
-            const int b = px[0], g = px[1], r = px[2];
-            const int v = max(max(b, g), r), vmin = min(min(b, g), r), diff = v - vmin;
-            int h = v == r ? g - b : (v == g ? b - r + 2 * diff : r - g + 4 * diff);
-            const int hdiv = diff ? __double2int_rn((double)(180 << 12) / (6.0 * diff)) : 0;
-            h = (h * hdiv + (1 << 11)) >> 12;
-            if (h < 0) h += 180;
+            const int h = hue_of(px[0], px[1], px[2]);
             sum += h;
         }
     return (double)sum / (double)((y1 - y0) * (x1 - x0));
@@ -847,7 +790,11 @@ extern "C" int egl_track_keypoints(const uint8_t* pyr, int H, int W, int max_lev
     a.eps2 = e * e;
     a.min_eig = 1e-4;
     a.out_pts = new_pts; a.out_status = status;
-    track_kernel<<<dim3(kMaxPts / kTrackWarps, n), kTrackWarps * 32, 0, (cudaStream_t)stream>>>(a);
+    static const char* env = getenv("EGL_TRACK_VARIANT");  // 1 = one thread per point (the host-checkable scalar code)
+    if (env && atoi(env) == 1)
+        track_thread_kernel<<<n, 64, 0, (cudaStream_t)stream>>>(a);
+    else
+        track_kernel<<<dim3(kMaxPts / kTrackWarps, n), kTrackWarps * 32, 0, (cudaStream_t)stream>>>(a);
     return cuda_status(cudaGetLastError(), "egl_track_keypoints: kernel launch");
 }
 

@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "native", "host_check.cpp")
 LIB = os.path.join(HERE, "native", "libhostcheck.so")
 CORE = os.path.join(os.path.dirname(HERE), "eagle_b200", "csrc", "geometry_core.cuh")
+FLOW_CORE = os.path.join(os.path.dirname(HERE), "eagle_b200", "csrc", "flow_core.cuh")
 
 _lib = None
 
@@ -20,7 +21,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        stale = (not os.path.exists(LIB)) or any(os.path.getmtime(p) > os.path.getmtime(LIB) for p in (SRC, CORE))
+        stale = (not os.path.exists(LIB)) or any(os.path.getmtime(p) > os.path.getmtime(LIB) for p in (SRC, CORE, FLOW_CORE))
         if stale:
             subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", LIB, SRC])
         _lib = C.CDLL(LIB)
@@ -104,3 +105,43 @@ def project(H, pts):
     of = np.zeros_like(pts); oi = np.zeros(pts.shape, np.int64)
     lib().hc_project(_p(H, C.c_double), _p(pts, C.c_float), len(pts), _p(of, C.c_float), _p(oi, C.c_int64))
     return of, oi
+
+
+def gray_hue(bgr):
+    """(gray, hue) uint8 of an (..., 3) uint8 BGR array through the kernels' colour formulas."""
+    a = np.ascontiguousarray(bgr, np.uint8).reshape(-1, 3)
+    g = np.zeros(len(a), np.uint8); h = np.zeros(len(a), np.uint8)
+    lib().hc_gray_hue(_p(a, C.c_uint8), len(a), _p(g, C.c_uint8), _p(h, C.c_uint8))
+    return g.reshape(bgr.shape[:-1]), h.reshape(bgr.shape[:-1])
+
+
+def build_pyramid(gray, max_level=2):
+    """Pyramid levels of a gray image as the kernels lay them out (list of 2-D arrays)."""
+    g = np.ascontiguousarray(gray, np.uint8)
+    H, W = g.shape
+    lib().hc_pyramid_bytes.restype = C.c_longlong
+    buf = np.zeros(lib().hc_pyramid_bytes(H, W, max_level), np.uint8)
+    n = lib().hc_build_pyramid(_p(g, C.c_uint8), H, W, max_level, _p(buf, C.c_uint8))
+    out, off, h, w = [], 0, H, W
+    for l in range(n):
+        if l > 0:
+            h, w = (h + 1) // 2, (w + 1) // 2
+        out.append(buf[off:off + h * w].reshape(h, w).copy())
+        off += (h * w + 15) // 16 * 16
+    return out
+
+
+def track(prev_gray, next_gray, pts, max_level=2, max_count=10, eps=0.03):
+    """cv2.calcOpticalFlowPyrLK with winSize (15, 15) through the kernels' scalar tracker: (next_pts, status)."""
+    a = np.ascontiguousarray(prev_gray, np.uint8); b = np.ascontiguousarray(next_gray, np.uint8)
+    p = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    out = np.zeros_like(p); st = np.zeros(len(p), np.uint8)
+    lib().hc_track(_p(a, C.c_uint8), _p(b, C.c_uint8), a.shape[0], a.shape[1], max_level, _p(p, C.c_float), len(p), max_count,
+                   C.c_double(eps), _p(out, C.c_float), _p(st, C.c_uint8))
+    return out, st
+
+
+def pairwise_sum(v):
+    a = np.ascontiguousarray(v, np.float32)
+    lib().hc_pairwise_sum.restype = C.c_float
+    return np.float32(lib().hc_pairwise_sum(_p(a, C.c_float), len(a)))

@@ -1,4 +1,4 @@
-// TEST ARTEFACT: compiles eagle_b200/csrc/geometry_core.cuh -- the exact scalar code the CUDA
+// TEST ARTEFACT: compiles eagle_b200/csrc/geometry_core.cuh and flow_core.cuh -- the exact scalar code the CUDA
 // kernels execute -- for the host with g++ -ffp-contract=off, so that its arithmetic can be compared
 // with the oracle on a machine without a GPU (tests/test_host_core.py).  Never used by the product.
 #include <stdint.h>
@@ -6,6 +6,8 @@
 #define __constant__ static const
 #include "../../include/eagle_b200.h"
 #include "../../eagle_b200/csrc/geometry_core.cuh"
+#include "../../eagle_b200/csrc/flow_core.cuh"
+#include <vector>
 
 namespace egl {
 #include "../../eagle_b200/csrc/line_families.inc"
@@ -120,5 +122,41 @@ void hc_project(const double* H, const float* pts, int n, float* out_f, int64_t*
         out_i[2 * i + 1] = trunc_like_numpy(out_f[2 * i + 1]);
     }
 }
+
+// ---- keypoint propagation (flow_core.cuh) ----------------------------------------------------------
+void hc_gray_hue(const uint8_t* bgr, int n, uint8_t* gray, uint8_t* hue) {
+    for (int i = 0; i < n; ++i) {
+        gray[i] = (uint8_t)gray_of(bgr[3 * i], bgr[3 * i + 1], bgr[3 * i + 2]);
+        hue[i] = (uint8_t)hue_of(bgr[3 * i], bgr[3 * i + 1], bgr[3 * i + 2]);
+    }
+}
+
+long long hc_pyramid_bytes(int H, int W, int max_level) { return pyramid_layout(H, W, max_level).bytes; }
+
+// gray image -> pyramid in the layout the kernels use (level 0 copied, further levels by pyrdown_pixel)
+int hc_build_pyramid(const uint8_t* gray, int H, int W, int max_level, uint8_t* pyr) {
+    const PyrLayout L = pyramid_layout(H, W, max_level);
+    memcpy(pyr, gray, (size_t)H * W);
+    for (int l = 1; l < L.n; ++l)
+        for (int y = 0; y < L.h[l]; ++y)
+            for (int x = 0; x < L.w[l]; ++x)
+                pyr[L.off[l] + (long long)y * L.w[l] + x] = (uint8_t)pyrdown_pixel(pyr + L.off[l - 1], L.w[l - 1], L.h[l - 1], x, y);
+    return L.n;
+}
+
+// cv2.calcOpticalFlowPyrLK(prev, next, pts, winSize=(15,15), maxLevel, criteria=(EPS|COUNT, max_count, eps)) through lk_track_point
+void hc_track(const uint8_t* prev_gray, const uint8_t* next_gray, int H, int W, int max_level, const float* pts, int n, int max_count,
+              double eps, float* out_pts, uint8_t* out_status) {
+    const PyrLayout L = pyramid_layout(H, W, max_level);
+    std::vector<uint8_t> a((size_t)L.bytes), b((size_t)L.bytes);
+    hc_build_pyramid(prev_gray, H, W, max_level, a.data());
+    hc_build_pyramid(next_gray, H, W, max_level, b.data());
+    const int mc = max_count < 0 ? 0 : (max_count > 100 ? 100 : max_count);
+    const double e = eps < 0 ? 0.0 : (eps > 10.0 ? 10.0 : eps);
+    for (int i = 0; i < n; ++i)
+        out_status[i] = (uint8_t)lk_track_point(a.data(), b.data(), L, pts[2 * i], pts[2 * i + 1], mc, e * e, 1e-4, out_pts + 2 * i);
+}
+
+float hc_pairwise_sum(const float* v, int n) { return pairwise_sum_f32(v, n); }
 
 }  // extern "C"

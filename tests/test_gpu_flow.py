@@ -113,6 +113,46 @@ def test_tracker_bit_exact_vs_cv2_and_oracle(engine):
         assert tracked > 60
 
 
+def test_tracker_warp_and_thread_kernels_agree():
+    """EGL_TRACK_VARIANT=1 runs lk_track_point (csrc/flow_core.cuh, the scalar statement the CPU suite compiles for
+    the host and compares with live cv2) one thread per point; the default warp kernel has to produce the same
+    bits.  Subprocesses, because the switch is read once per process."""
+    import subprocess
+    import sys
+    import tempfile
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from eagle_b200 import synthetic
+from eagle_b200.engine import GeometryEngine, KeypointSet
+e = GeometryEngine("cuda:0")
+rng = np.random.default_rng(11)
+outs = []
+for (W, H) in [(640, 360), (202, 117)]:
+    clip = synthetic.make_flow_clip(6, W, H, seed=9, pan_px=3.0)
+    fr = clip["frames"].copy(); fr[4] = rng.integers(0, 256, fr[4].shape, dtype=np.uint8)   # one white-noise frame
+    pyr = e.gray_pyramid(torch.from_numpy(fr).cuda())
+    xy = np.zeros((5, 57, 2), np.int32); order = np.zeros((5, 64), np.uint8); count = np.zeros((5, 2), np.int32)
+    for f in range(5):
+        chs = rng.permutation(57)[:rng.integers(1, 58)]
+        order[f, :len(chs)] = chs; count[f] = len(chs)
+        xy[f, chs] = np.c_[rng.integers(-3, W + 3, len(chs)), rng.integers(-3, H + 3, len(chs))]
+    t = lambda a: torch.from_numpy(a).cuda()
+    kp = KeypointSet(None, None, t(xy), t(order), t(count), None)
+    pts = torch.zeros((5, 64, 2), device="cuda"); st = torch.zeros((5, 64), dtype=torch.uint8, device="cuda")
+    e.track(pyr, H, W, kp, 0, 1, 1, out=(pts, st))
+    outs += [pts.cpu().numpy().ravel().view(np.int32).astype(np.int64), st.cpu().numpy().ravel().astype(np.int64)]
+np.save(sys.argv[1], np.concatenate(outs))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = []
+    for variant in ("0", "1"):
+        with tempfile.NamedTemporaryFile(suffix=".npy") as tf:
+            env = dict(os.environ, EGL_TRACK_VARIANT=variant)
+            subprocess.run([sys.executable, "-c", code, tf.name], check=True, env=env, timeout=300)
+            res.append(np.load(tf.name))
+    assert np.array_equal(res[0], res[1]) and int((res[0] != 0).sum()) > 200
+
+
 def test_filter_flow_matches_oracle(engine):
     from eagle_b200.engine import KeypointSet
     from eagle_b200.pitch import LANDMARK_NAMES

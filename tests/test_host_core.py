@@ -140,3 +140,58 @@ def test_postprocess_randomised_collisions_and_ties():
         xy, order = hostcore.postprocess(flat, score, h, w, W, H)
         got = {landmarks.INDEX_TO_NAME[int(c)]: (int(xy[c, 0]), int(xy[c, 1])) for c in order}
         assert list(got) == list(want) and got == {k: tuple(v) for k, v in want.items()}, t
+
+
+# ---- keypoint propagation: the kernels' scalar flow code (csrc/flow_core.cuh) on the host ------------------
+def test_flow_core_colour_and_pyramid_match_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    v = np.unique(np.r_[np.arange(0, 256, 5), 254, 255]).astype(np.uint8)
+    c = np.stack(np.meshgrid(v, v, v, indexing="ij"), -1).reshape(len(v), -1, 3)
+    g, h = hostcore.gray_hue(c)
+    assert np.array_equal(g, cv2.cvtColor(c, cv2.COLOR_BGR2GRAY)) and np.array_equal(h, cv2.cvtColor(c, cv2.COLOR_BGR2HSV)[..., 0])
+    for shape in [(37, 53), (135, 240), (64, 65), (33, 18)]:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        lv = hostcore.build_pyramid(img, 2)
+        want = [img]
+        for _ in range(2):
+            nxt = cv2.pyrDown(want[-1])
+            if nxt.shape[0] <= 15 or nxt.shape[1] <= 15:
+                break
+            want.append(nxt)
+        assert len(lv) == len(want) and all(np.array_equal(a, b) for a, b in zip(lv, want))
+    for n in list(range(0, 20)) + [31, 57, 64, 100]:
+        a = (rng.uniform(0, 30, n) ** 2).astype(np.float32)
+        assert hostcore.pairwise_sum(a) == (a.sum() if n else np.float32(0))
+
+
+@pytest.mark.parametrize("seed", [2, 3, 4])
+def test_flow_core_tracker_bit_exact_vs_cv2(seed):
+    """The CUDA tracker's scalar statement (lk_track_point, also the EGL_TRACK_VARIANT=1 kernel), compiled for
+    the host, against live cv2.calcOpticalFlowPyrLK: status and float32 positions bit for bit."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(seed)
+    lk = dict(winSize=(15, 15), maxLevel=2, criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 10, 0.03))
+    tracked = 0
+    for trial in range(10):
+        h, w = [(270, 480), (135, 240), (100, 70), (360, 640), (40, 50)][trial % 5]
+        cell = [2, 4, 8, 16][trial % 4]
+        base = rng.integers(0, 256, (h // cell + 2, w // cell + 2), dtype=np.uint8)
+        g1 = cv2.resize(base, (w, h), interpolation=cv2.INTER_CUBIC)
+        if trial % 3 == 0:
+            g1 = (g1.astype(np.int32) + rng.integers(-40, 40, g1.shape)).clip(0, 255).astype(np.uint8)
+        if trial == 7:
+            g1 = rng.integers(0, 256, (h, w), dtype=np.uint8)   # white noise: every float sum rounds
+        ang = rng.uniform(-0.03, 0.03); tx, ty = rng.uniform(-6, 6, 2)
+        M = np.float32([[np.cos(ang), np.sin(ang), tx], [-np.sin(ang), np.cos(ang), ty]])
+        g2 = cv2.warpAffine(g1, M, (w, h), borderMode=cv2.BORDER_REFLECT)
+        pts = rng.uniform([-3, -3], [w + 2, h + 2], (40, 2)).astype(np.float32)
+        if trial % 2 == 0:
+            pts = np.trunc(pts)
+        ref, st, _ = cv2.calcOpticalFlowPyrLK(g1, g2, pts, None, **lk)
+        out, s = hostcore.track(g1, g2, pts)
+        assert np.array_equal(s, st[:, 0]), trial
+        ok = st[:, 0] == 1
+        assert np.array_equal(out[ok].view(np.int32), ref[ok].view(np.int32)), trial
+        tracked += int(ok.sum())
+    assert tracked > 250
