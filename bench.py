@@ -426,6 +426,49 @@ def main():
                                        "frac": pyr_bytes / (g_ms * 1e-3) / 1e9 / peak,
                                        "algorithmic_bytes_per_frame": H * W * 3 + int(N.lib.egl_pyramid_bytes(H, W, 2))},
                       "parity": "bit-exact with cv2.calcOpticalFlowPyrLK / the reference's dict (tests/test_gpu_flow.py)"}
+        # end to end for this cadence: frames (uint8), the heads' heatmaps and the foot points come from pinned host
+        # memory every clip, every per-frame result goes back; only 1 frame in 8 brings a heatmap along
+        BL = 16 * kint
+        nbl = (F + BL - 1) // BL
+        st_fr = torch.empty((2, BL, H, W, 3), dtype=torch.uint8).pin_memory(); st_fr.copy_(pf[:2 * BL].view(2, BL, H, W, 3).cpu())
+        st_hm = torch.empty((2, BL // kint, 57, 135, 240), dtype=torch.float32).pin_memory()
+        st_hm.copy_(heads[:2 * (BL // kint)].view(2, BL // kint, 57, 135, 240).cpu())
+        st_foot = torch.empty(foot.shape, dtype=foot.dtype).pin_memory(); st_foot.copy_(foot.cpu())
+        st_cnt = torch.empty(count.shape, dtype=count.dtype).pin_memory(); st_cnt.copy_(count.cpu())
+        h_res = None
+
+        def prop_e2e():
+            nonlocal h_res
+            for b in range(nbl):
+                n = min(BL, F - b * BL)
+                pf[b * BL:b * BL + n].copy_(st_fr[b & 1, :n], non_blocking=True)
+                nh_ = (n + kint - 1) // kint
+                heads[b * (BL // kint):b * (BL // kint) + nh_].copy_(st_hm[b & 1, :nh_], non_blocking=True)
+            foot.copy_(st_foot, non_blocking=True); count.copy_(st_cnt, non_blocking=True)
+            o = prop.run(pf, heads, None, kint, hint, False)
+            eng.project(o["H"], foot, count, W, H, h_index=o["h_index"], out=proj)
+            rec = pack_results([o["xy"], o["order"], o["count"], o["src"], o["H"], o["fit_ok"], o["h_index"], proj.coords, proj.coords_i,
+                                proj.in_bounds, proj.bounds])
+            if h_res is None:
+                h_res = torch.empty(rec.shape, dtype=torch.uint8).pin_memory()
+            h_res.copy_(rec, non_blocking=True)
+            torch.cuda.synchronize()
+
+        prop_e2e()
+        barrier()
+        t_e = time.perf_counter()
+        for _ in range(2):
+            prop_e2e()
+        pe_dt = (time.perf_counter() - t_e) / 2
+        if world > 1:
+            t = torch.tensor([pe_dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pe_dt = float(t.item())
+        propagated["e2e"] = {"value": F * world / pe_dt, "unit": "frames/s", "ms_per_clip": pe_dt * 1e3,
+                             "h2d_bytes_per_step": world * (F * H * W * 3 + ((F + kint - 1) // kint) * HM_BYTES + F * (MAX_OBJ * 8 + 4)),
+                             "d2h_bytes_per_step": world * int(h_res.numel()),
+                             "note": "pinned host -> H2D of all frames, the chain heads' heatmaps and the foot points -> PropagatedPath + "
+                                     "projection -> D2H of every per-frame result; PCIe-bound"}
         if rank == 0 and not args.no_cpu_baseline:
             # the reference's CPU statements for the same cadence (cv2.calcOpticalFlowPyrLK, cv2.cvtColor, cv2.fitLine,
             # cv2.findHomography, cv2.perspectiveTransform), one thread, on the first chains of the same clip
