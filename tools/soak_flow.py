@@ -102,6 +102,16 @@ def main():
             bad = None if (err_g or err_o) else next(i for i in want if json.dumps(got[i], default=float) != json.dumps(want[i], default=float))
             print(f"MISMATCH clip {ci}: {W}x{H} n={n} fps={fps} nh={nh} nk={nk} cal={cal} piece={model.piece_frames} first bad frame {bad} "
                   f"errors gpu={err_g} oracle={err_o}", flush=True)
+            if args.only >= 0 and not (err_g or err_o):
+                for i in want:
+                    keys = [key for key in want[i] if json.dumps(got[i][key], default=float) != json.dumps(want[i][key], default=float)]
+                    if keys:
+                        print(f"  frame {i}: differing {keys}")
+                        if "Keypoints" in keys:
+                            print("    gpu   ", json.dumps(got[i]["Keypoints"], default=float))
+                            print("    oracle", json.dumps(want[i]["Keypoints"], default=float))
+                        if "Boundaries" in keys:
+                            print("    gpu   ", got[i]["Boundaries"], "oracle", want[i]["Boundaries"])
     tot["seconds"] = round(time.time() - t0, 1)
     print(json.dumps(tot))
 
