@@ -2,7 +2,7 @@
 
 Importing the package does not load CUDA; `eagle_b200.CoordinateModel` / `GeometryEngine` do, and
 raise if libeagle_b200.so has not been built (there is no CPU fallback)."""
-__all__ = ["CoordinateModel", "GeometryPath", "GeometryEngine", "KeypointDecoder"]
+__all__ = ["CoordinateModel", "GeometryPath", "GeometryEngine", "KeypointDecoder", "PropagatedPath"]
 
 
 def __getattr__(name):
@@ -12,6 +12,9 @@ def __getattr__(name):
     if name == "KeypointDecoder":
         from .keypoints import KeypointDecoder
         return KeypointDecoder
+    if name == "PropagatedPath":
+        from .propagation import PropagatedPath
+        return PropagatedPath
     if name == "GeometryEngine":
         from .engine import GeometryEngine
         return GeometryEngine
