@@ -76,3 +76,24 @@ def test_assembler_reproduces_reference_value_types():
     assert json.dumps(kp, default=float) == '{"%s": [10, 20], "%s": [30.0, 40.0], "%s": [50.0, 60.0]}' % tuple(kp)
     assert res[1]["Keypoints"] == {} and res[1]["Boundaries"] == [None] * 4
     assert res[1]["Coordinates"]["Player"][7]["Transformed_Coordinates"] is None and res[1]["Time"] == "00:00"
+
+
+def test_binding_argument_counts_match_the_header():
+    """Every ctypes prototype in eagle_b200/_native.py has as many arguments as the declaration in the header."""
+    from eagle_b200 import _native
+    txt = open(os.path.join(ROOT, "include", "eagle_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    for name, params in re.findall(r"\b(egl_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", txt):
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        argtypes = getattr(_native.lib, name).argtypes
+        if argtypes is None:
+            assert n == 0, f"{name}: header has {n} parameters, binding declares none"
+        else:
+            assert len(argtypes) == n, f"{name}: header has {n} parameters, binding {len(argtypes)}"
+    # new propagation entry points reject null pointers before touching CUDA
+    N = _native
+    assert N.lib.egl_gray_pyramid(None, 1, 64, 64, 192, 64 * 192, 2, None, None) == 1
+    assert N.lib.egl_track_keypoints(None, 64, 64, 2, None, None, None, 1, 0, 1, 1, 10, 0.03, None, None, None) == 1
+    assert N.lib.egl_pyramid_bytes(1080, 1920, 2) == 2721600 and N.lib.egl_pyramid_bytes(16, 16, 2) == 256
+    assert N.lib.egl_gray_pyramid(None, 0, 64, 64, 192, 64 * 192, 2, None, None) == 0   # empty batch: no-op
