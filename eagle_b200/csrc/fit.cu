@@ -19,6 +19,8 @@
 //                       the host-checkable scalar code of geometry_core.cuh; EGL_REFIT_VARIANT=1.)
 #include <stdlib.h>
 
+#include <stddef.h>
+
 #include "common.cuh"
 #include "geometry_core.cuh"
 
@@ -606,7 +608,25 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
     for (int i = 0; i < 9; ++i) H[i] = a.H[(size_t)f * 9 + i];
     __syncwarp();
     int count = a.info[4 * f + 1];
-    if (N > 4) {
+    if (N > 4 && __popcll(pm) <= kLmExactMaxPoints) {
+        // Few inliers: nothing for 32 lanes to share, and the undamped LM steps need OpenCV's eigenvalue
+        // threshold (eig_threshold_solve9) to stay with cv2 on these numerically singular fits.  Lane 0 runs the
+        // scalar code of geometry_core.cuh -- the same the one-thread-per-frame kernel and the host check run.
+        if (lane == 0) {
+            static_assert(offsetof(RefitShared, vec) - offsetof(RefitShared, A) >= 191 * sizeof(double) &&
+                          sizeof(((RefitShared*)0)->vec) >= sizeof(double), "A, aug, vec are used as one 192-double scratch");
+            double* scratch = sh.A;  // A[81] + aug[110] + vec[0]: unused on this path until the results are parked below
+            uint64_t fm = 0;
+            const int c = refit_on_inliers(H, sh.pl.sx, sh.pl.sy, sh.pl.dx, sh.pl.dy, N, pm, a.thr_sq, &fm, scratch);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) a.H[(size_t)f * 9 + i] = H[i];
+            sh.vec[0] = __longlong_as_double((long long)fm);
+            sh.vec[1] = (double)c;
+        }
+        __syncwarp();
+        pm = (uint64_t)__double_as_longlong(sh.vec[0]);
+        count = (int)sh.vec[1];
+    } else if (N > 4) {
         const int m = __popcll(pm);
         // this lane's (up to two) inlier points
         bool act[2];

@@ -574,3 +574,53 @@ def test_subpixel_refinement_extension(engine):
     e_int, e_sub = float(np.mean(err["int"])), float(np.mean(err["sub"]))
     assert e_sub < e_int / 3.0, (e_int, e_sub)
     print(f"mean landmark error: integer grid {e_int:.3f} m, sub-pixel {e_sub:.3f} m")
+
+
+def test_few_inlier_fit_follows_cv2_eigenvalue_threshold(engine):
+    """Frame 8 of a soak clip: 22 meaningless correspondences, cv2 ends with 6 inliers.  With so few inliers the
+    undamped LM steps depend on the eigenvalue threshold of cv::solve(DECOMP_EIG); the refit kernels (warp kernel:
+    lane 0 runs the scalar code for <= 9 inliers) must keep the same 6 and the same H.  Plus hard synthetic sets."""
+    cv2 = pytest.importorskip("cv2")
+    from eagle_b200 import synthetic
+    from eagle_b200.engine import KeypointSet
+    from eagle_b200.pitch import OFF_PLANE, WORLD_XYZ
+    ip0 = np.array([[57, 332], [98, 393], [461, 89], [854, 258], [895, 40], [644, 328], [333, 147], [698, 381], [450, 163], [566, 357],
+                    [609, 345], [527, 199], [199, 393], [156, 356], [151, 340], [182, 411], [163, 306], [863, 127], [898, 379], [846, 76],
+                    [646, 397], [136, 377]], np.int32)
+    wp0 = np.array([[5.5, 24.84], [5.5, 43.16], [16.5, 13.84], [16.5, 54.16], [0.0, 54.16], [52.5, 0.0], [88.5, 13.84], [105.0, 0.0],
+                    [61.31, 36.46], [43.69, 36.46], [61.31, 31.54], [43.69, 31.54], [58.97, 40.47], [58.97, 27.53], [52.5, 43.15],
+                    [52.5, 24.85], [20.15, 34.0], [19.99, 35.7], [19.99, 32.3], [11.0, 34.0], [16.5, 34.0], [52.5, 34.0]], np.float32)
+    on = [i for i in range(57) if i not in OFF_PLANE]
+    ch0 = [next(c for c in on if np.allclose(WORLD_XYZ[c, :2], w, atol=0.006)) for w in wp0]
+    assert len(set(ch0)) == len(ch0)
+    sets = [(ch0, ip0)]
+    rng = np.random.default_rng(0)
+    for t in range(120):
+        W, Himg = [(1280, 720), (1920, 1080), (960, 540)][t % 3]
+        cam = synthetic.sample_cameras(1, W, Himg, rng)[0]
+        px, vis = synthetic.landmark_pixels(cam, W, Himg)
+        sel = np.array(on)[vis[on]]
+        if len(sel) < 6:
+            continue
+        good = rng.choice(sel, min(int(rng.integers(6, 9)), len(sel)), replace=False)
+        bad = rng.choice(np.setdiff1d(on, good), int(rng.integers(5, 20)), replace=False)
+        pts = {int(c): px[c] + rng.normal(0, 0.7, 2) for c in good}
+        pts.update({int(c): rng.uniform([0, 0], [W, Himg]) for c in bad})
+        chs = sorted(pts)
+        sets.append((chs, np.rint(np.array([pts[c] for c in chs])).astype(np.int32)))
+    T = len(sets)
+    xy = np.zeros((T, 57, 2), np.int32); order = np.full((T, 64), 255, np.uint8); count = np.zeros((T, 2), np.int32)
+    for i, (chs, ip) in enumerate(sets):
+        xy[i, chs] = ip; order[i, :len(chs)] = chs; count[i] = len(chs)
+    kp = KeypointSet(None, None, torch.from_numpy(xy).cuda(), torch.from_numpy(order).cuda(), torch.from_numpy(count).cuda())
+    fit = engine.fit(kp)
+    Hs = fit.H.cpu().numpy().reshape(-1, 3, 3); status = fit.status.cpu().numpy(); inl = fit.inlier_mask.cpu().numpy()
+    checked = 0
+    for i, (chs, ip) in enumerate(sets):
+        H, m = cv2.findHomography(ip.astype(np.float32), WORLD_XYZ[chs, :2].astype(np.float32), cv2.RANSAC, 5.0)
+        if H is None or int(m.sum()) < 6:
+            continue
+        checked += 1
+        assert status[i] == 0 and int(inl[i]) == sum(1 << int(c) for c, mm in zip(chs, m.ravel()) if mm), i
+        assert float(np.max(np.abs(Hs[i] - H) / np.abs(H))) < H_REL_TOL, i
+    assert checked > 40 and int(inl[0]).bit_count() == 6
