@@ -278,19 +278,61 @@ __global__ void __launch_bounds__(kCv2Warps * 32) ransac_cv2_kernel(FitArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// mode EGL_FIT_FIXED_K: thread per hypothesis, FP32 registers
+// mode EGL_FIT_FIXED_K: packed FP32 (FFMA2 / FMUL2 / FADD2) throughout
 // ------------------------------------------------------------------------------------------------
 constexpr int kFixedThreads = 128;
+constexpr int kFixedWarps = kFixedThreads / 32;
+constexpr int kFixedQueue = 96;  // per-warp queue of accepted samples: <= 63 left over + 32 new
 
-__global__ void __launch_bounds__(kFixedThreads) ransac_fixedk_kernel(FitArgs a, float inv_thr, double thr) {
+// sample h of frame f: indices from the explicit table or the counter-based generator; false if unusable
+__device__ __forceinline__ bool fixedk_sample(const FitArgs& a, int f, uint64_t key, int h, int N, int idx[4]) {
+    if (!a.hyp) {
+        seeded_subset_keyed(key, (uint32_t)h, N, idx);  // always four distinct indices below N
+        return h < a.K;
+    }
+    bool ok = h < a.K;
+    const uchar4 q = ok ? reinterpret_cast<const uchar4*>(a.hyp)[(size_t)f * a.K + h] : make_uchar4(0, 1, 2, 3);
+    idx[0] = q.x; idx[1] = q.y; idx[2] = q.z; idx[3] = q.w;
+    ok = ok && idx[0] < N && idx[1] < N && idx[2] < N && idx[3] < N && idx[0] != idx[1] && idx[0] != idx[2] && idx[0] != idx[3] &&
+         idx[1] != idx[2] && idx[1] != idx[3] && idx[2] != idx[3];
+    if (!ok) { idx[0] = 0; idx[1] = 1; idx[2] = 2; idx[3] = 3; }
+    return ok;
+}
+
+// shared-memory read of data that is not written again after the barrier that published it
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// asm keeps the count at one compare and one predicated add per hypothesis and point
+__device__ __forceinline__ void count_if_le0(int& c, float t) {
+    asm("{\n.reg .pred p;\nsetp.le.f32 p, %1, 0f00000000;\n@p add.s32 %0, %0, 1;\n}" : "+r"(c) : "f"(t));
+}
+
+__device__ __forceinline__ float warp_tree_sum_f32(float lo, float hi) {  // tree_sum64 with lanes as the 32 partial sums
+    float t = fadd(lo, hi);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) t = fadd(t, __shfl_xor_sync(kFull, t, m));
+    return t;
+}
+
+__global__ void __launch_bounds__(kFixedThreads, 6) ransac_fixedk_kernel(FitArgs a, float inv_thr, double thr) {
     __shared__ PointList s_pl;
-    __shared__ float4 s_pt[kMaxPts];  // normalised (X', Y', x', y'): one broadcast LDS.128 per point
-    __shared__ int s_cnt[kFixedThreads / 32], s_hyp[kFixedThreads / 32];
-    __shared__ float s_H[8];
-    __shared__ float s_qH[kFixedThreads / 32][64][9];  // per-warp queue of accepted hypotheses (padded rows)
-    __shared__ int s_qh[kFixedThreads / 32][64];
+    // normalised points as (X', x', Y', y') -- image/pitch pairs for the sample test -- replicated into the eight
+    // 16-byte columns of a 128-byte row: lane l gathers from column l & 7, so the eight lanes of a quarter warp never
+    // share a bank whatever indices they drew (a random LDS.128 gather from an unreplicated table averages 3
+    // wavefronts per quarter warp)
+    __shared__ float4 s_ps[kMaxPts][8];
+    __shared__ float4 s_bc[kMaxPts + 4][2];  // for the scoring loop: (X',X',Y',Y') (-x',-x',-y',-y'), padded to a multiple of 4
+    __shared__ int s_cnt[kFixedWarps], s_hyp[kFixedWarps];
+    __shared__ uint32_t s_qi[kFixedWarps][kFixedQueue];  // accepted samples: four packed indices ...
+    __shared__ int s_qh[kFixedWarps][kFixedQueue];       // ... and the hypothesis number
+    __shared__ uint32_t s_pi[kFixedWarps * 64];          // what the warps had left over, pooled
+    __shared__ int s_ph[kFixedWarps * 64];
     __shared__ FixedKNorm s_nm;
-    __shared__ int s_N, s_ok;
+    __shared__ int s_N, s_ok, s_pool;
     __shared__ unsigned long long s_used;
     const int f = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -301,10 +343,25 @@ __global__ void __launch_bounds__(kFixedThreads) ransac_fixedk_kernel(FitArgs a,
     if (warp == 0) {
         uint64_t used;
         const int n = gather_points_warp(a, f, s_pl, &used);
+        // fixedk_normalise, lanes as the partial sums of the tree order
+        const bool v0 = lane < n, v1 = lane + 32 < n;
+        const float X0 = v0 ? s_pl.sx[lane] : 0.f, X1 = v1 ? s_pl.sx[lane + 32] : 0.f;
+        const float Y0 = v0 ? s_pl.sy[lane] : 0.f, Y1 = v1 ? s_pl.sy[lane + 32] : 0.f;
+        const float x0 = v0 ? s_pl.dx[lane] : 0.f, x1 = v1 ? s_pl.dx[lane + 32] : 0.f;
+        const float y0 = v0 ? s_pl.dy[lane] : 0.f, y1 = v1 ? s_pl.dy[lane + 32] : 0.f;
+        const float fn = (float)n;
+        FixedKNorm nm;
+        nm.cX = fdiv(warp_tree_sum_f32(X0, X1), fn); nm.cY = fdiv(warp_tree_sum_f32(Y0, Y1), fn);
+        nm.cx = fdiv(warp_tree_sum_f32(x0, x1), fn); nm.cy = fdiv(warp_tree_sum_f32(y0, y1), fn);
+        const float aX = warp_tree_sum_f32(v0 ? fabsf(fsub(X0, nm.cX)) : 0.f, v1 ? fabsf(fsub(X1, nm.cX)) : 0.f);
+        const float aY = warp_tree_sum_f32(v0 ? fabsf(fsub(Y0, nm.cY)) : 0.f, v1 ? fabsf(fsub(Y1, nm.cY)) : 0.f);
+        nm.sX = fdiv(fn, aX); nm.sY = fdiv(fn, aY); nm.rt = inv_thr;
         if (lane == 0) {
             s_N = n;
             s_used = used;
-            s_ok = n >= 4 && fixedk_normalise(s_pl.sx, s_pl.sy, s_pl.dx, s_pl.dy, n, inv_thr, &s_nm);
+            s_ok = n >= 4 && aX > 0.f && aY > 0.f;
+            s_nm = nm;
+            s_pool = 0;
         }
     }
     __syncthreads();
@@ -313,99 +370,135 @@ __global__ void __launch_bounds__(kFixedThreads) ransac_fixedk_kernel(FitArgs a,
         if (tid == 0) park(a, f, N < 4 ? EGL_FIT_FEW_POINTS : EGL_FIT_NO_MODEL, N, 0, -1, 0, nullptr, 0, s_used);
         return;
     }
-    for (int i = tid; i < N; i += kFixedThreads) {
-        float o[4];
-        fixedk_normalise_point(s_nm, s_pl.sx[i], s_pl.sy[i], s_pl.dx[i], s_pl.dy[i], o);
-        s_pt[i] = make_float4(o[0], o[1], o[2], o[3]);
+    const int N4 = (N + 3) & ~3;
+    for (int e = tid; e < N4 * 8; e += kFixedThreads) {
+        const int i = e >> 3, col = e & 7;
+        if (i < N) {
+            float o[4];
+            fixedk_normalise_point(s_nm, s_pl.sx[i], s_pl.sy[i], s_pl.dx[i], s_pl.dy[i], o);
+            s_ps[i][col] = make_float4(o[0], o[2], o[1], o[3]);
+            if (col == 0) s_bc[i][0] = make_float4(o[0], o[0], o[1], o[1]);
+            if (col == 1) s_bc[i][1] = make_float4(-o[2], -o[2], -o[3], -o[3]);
+        } else if (col < 2) {  // padding rows: NaN residuals are never counted
+            const float q = col ? __int_as_float(0x7fffffff) : 0.f;
+            s_bc[i][col] = make_float4(q, q, q, q);
+        }
     }
     __syncthreads();
+    const uint64_t key = seeded_frame_key(a.seed, (uint64_t)f);
+    // 32-bit shared-window addresses, formed once: this lane's column of the gather table (row stride 128 bytes) and
+    // the scoring table
+    const uint32_t ps_addr = smem_u32(&s_ps[0][lane & 7]), bc_addr = smem_u32(&s_bc[0][0]);
 
-    // Two phases per batch of 32 candidates so that no lane idles while others score:
-    //   A  every lane draws one sample and solves it (cheap); samples rejected by the checkSubset
-    //      rules -- about half of them at 40 % outliers -- simply produce no queue entry;
-    //   B  accepted hypotheses are compacted (ballot) into a per-warp queue in shared memory and scored
-    //      32 at a time, one hypothesis per lane over all N points (the expensive part, all lanes busy).
+    // Two phases so that no lane idles while others score:
+    //   A  every lane draws one sample and tests it (checkSubset rules; 50-70 % are rejected at 40 % outliers).  The
+    //      image-side and pitch-side triple areas are the same formula on (X,Y) and (x,y), so the packed halves are
+    //      the two SIDES: one LDS.128 per sampled point lands as the pairs (X,x) (Y,y), no register shuffling.
+    //      Accepted samples are ballot-compacted into a per-warp queue (8 bytes per entry);
+    //   B  whenever 64 samples are queued, every lane takes two, solves both minimal systems and scores all N points
+    //      against both -- the packed halves are now the two HYPOTHESES: 11 FFMA2/FMUL2 per point for the pair.
+    // What the warps have left at the end is pooled so that at most one batch per frame runs partly empty.
     // The result is order independent: most inliers, ties to the lowest hypothesis index.
-    float (*qH)[9] = s_qH[warp];
+    uint32_t* qi = s_qi[warp];
     int* qh = s_qh[warp];
     int qn = 0;
     int best_cnt = 0, best_h = 0x7fffffff;
-    float best_H[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    auto score_queue = [&](int n_active) {  // lanes < n_active score queue entry `lane`
-        if (lane < n_active) {
-            float Hn[8];
+    typedef lane_ops<float2> L;
+    auto solve_and_score = [&](const uint32_t* ei, const int* eh, int e0, int e1, bool v0, bool v1) {
+        const uint32_t pa = ei[e0], pb = ei[e1];
+        const int ha = eh[e0], hb = eh[e1];
+        float2 X[4], Y[4], x[4], y[4], S[4], H[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) Hn[k] = qH[lane][k];
-            const int h = qh[lane];
-            int cnt = 0;
-#pragma unroll 4
-            for (int i = 0; i < N; ++i) {
-                const float4 q = s_pt[i];
-                cnt += fixedk_inlier(Hn, q.x, q.y, q.z, q.w);
-            }
-            if (cnt > best_cnt || (cnt == best_cnt && h < best_h)) {
-                best_cnt = cnt;
-                best_h = h;
+        for (int k = 0; k < 4; ++k) {
+            const float4 p = lds128(ps_addr + 128u * ((pa >> (8 * k)) & 255u)), q = lds128(ps_addr + 128u * ((pb >> (8 * k)) & 255u));
+            X[k] = make_float2(p.x, q.x); x[k] = make_float2(p.y, q.y);
+            Y[k] = make_float2(p.z, q.z); y[k] = make_float2(p.w, q.w);
+        }
+        S[0] = det3_v<float2>(X[0], Y[0], X[1], Y[1], X[2], Y[2]);
+        S[1] = det3_v<float2>(X[1], Y[1], X[2], Y[2], X[3], Y[3]);
+        S[2] = det3_v<float2>(X[0], Y[0], X[2], Y[2], X[3], Y[3]);
+        S[3] = det3_v<float2>(X[0], Y[0], X[1], Y[1], X[3], Y[3]);
+        const bool2 fin = fixedk_solve_v<float2>(X, Y, x, y, S, H);
+        const float2 one = make_float2(1.f, 1.f);
+        int c0 = 0, c1 = 0;
+        for (int i = 0; i < N4; i += 4) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) best_H[k] = Hn[k];
+            for (int j = 0; j < 4; ++j) {
+                const float4 u = lds128(bc_addr + 32u * (i + j)), m = lds128(bc_addr + 32u * (i + j) + 16u);
+                const float2 PX = make_float2(u.x, u.y), PY = make_float2(u.z, u.w), nx = make_float2(m.x, m.y), ny = make_float2(m.z, m.w);
+                const float2 w = L::fma(H[6], PX, L::fma(H[7], PY, one));
+                const float2 ex = L::fma(nx, w, L::fma(H[0], PX, L::fma(H[1], PY, H[2])));
+                const float2 ey = L::fma(ny, w, L::fma(H[3], PX, L::fma(H[4], PY, H[5])));
+                const float2 e = L::fma(ex, ex, L::mul(ey, ey));
+                const float2 t = L::fma(L::neg(w), w, e);
+                count_if_le0(c0, t.x);
+                count_if_le0(c1, t.y);
             }
         }
+        if (v0 && fin.x && (c0 > best_cnt || (c0 == best_cnt && ha < best_h))) { best_cnt = c0; best_h = ha; }
+        if (v1 && fin.y && (c1 > best_cnt || (c1 == best_cnt && hb < best_h))) { best_cnt = c1; best_h = hb; }
     };
     for (int base = warp * 32; base < a.K; base += kFixedThreads) {
         const int h = base + lane;
-        bool ok = h < a.K;
-        int idx[4] = {0, 1, 2, 3};
-        if (ok) {
-            if (a.hyp) {
-                const uchar4 q = reinterpret_cast<const uchar4*>(a.hyp)[(size_t)f * a.K + h];
-                idx[0] = q.x; idx[1] = q.y; idx[2] = q.z; idx[3] = q.w;
-            } else {
-                seeded_subset(a.seed, (uint64_t)f, (uint64_t)a.K, (uint64_t)h, N, idx);
-            }
-        }
-        ok = ok && idx[0] < N && idx[1] < N && idx[2] < N && idx[3] < N;
-        ok = ok && idx[0] != idx[1] && idx[0] != idx[2] && idx[0] != idx[3] && idx[1] != idx[2] && idx[1] != idx[3] &&
-             idx[2] != idx[3];
-        float p[4][4];
+        int idx[4];
+        bool ok = fixedk_sample(a, f, key, h, N, idx);
+        float2 V[4], W[4];  // V = (X', x'), W = (Y', y')
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float4 q = s_pt[ok ? idx[k] : k];
-            p[k][0] = q.x; p[k][1] = q.y; p[k][2] = q.z; p[k][3] = q.w;
+            const float4 p = lds128(ps_addr + 128u * idx[k]);
+            V[k] = make_float2(p.x, p.y);
+            W[k] = make_float2(p.z, p.w);
         }
-        float Hn[8];
-        ok = fixedk_hypothesis(p, Hn) && ok;
+        // (S, D): oriented areas of the triples (0,1,2) (1,2,3) (0,2,3) (0,1,3) on the image and the pitch side
+        const float2 a012 = det3_v<float2>(V[0], W[0], V[1], W[1], V[2], W[2]);
+        const float2 a123 = det3_v<float2>(V[1], W[1], V[2], W[2], V[3], W[3]);
+        const float2 a023 = det3_v<float2>(V[0], W[0], V[2], W[2], V[3], W[3]);
+        const float2 a013 = det3_v<float2>(V[0], W[0], V[1], W[1], V[3], W[3]);
+        const float tiny = 1e-6f;
+        ok = ok && fabsf(a123.x) > tiny && fabsf(a023.x) > tiny && fabsf(a013.x) > tiny && fabsf(a123.y) > tiny &&
+             fabsf(a023.y) > tiny && fabsf(a013.y) > tiny;
+        // orientation kept by all four triples or flipped by all four
+        const bool n0 = fmul(a012.x, a012.y) < 0.f, n1 = fmul(a123.x, a123.y) < 0.f, n2 = fmul(a023.x, a023.y) < 0.f,
+                   n3 = fmul(a013.x, a013.y) < 0.f;
+        ok = ok && n0 == n1 && n1 == n2 && n2 == n3;
         const unsigned bal = __ballot_sync(kFull, ok);
         if (ok) {
             const int pos = qn + __popc(bal & ((1u << lane) - 1u));
-#pragma unroll
-            for (int k = 0; k < 8; ++k) qH[pos][k] = Hn[k];
+            qi[pos] = (uint32_t)idx[0] | ((uint32_t)idx[1] << 8) | ((uint32_t)idx[2] << 16) | ((uint32_t)idx[3] << 24);
             qh[pos] = h;
         }
         qn += __popc(bal);
         __syncwarp();
-        if (qn >= 32) {
-            score_queue(32);
+        if (qn >= 64) {
+            solve_and_score(qi, qh, lane, lane + 32, true, true);
             __syncwarp();
-            // move the leftover entries [32, qn) to the front
-            float t[8];
-            int th = 0;
-            const bool mv = lane < qn - 32;
-            if (mv) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) t[k] = qH[32 + lane][k];
-                th = qh[32 + lane];
-            }
+            // move the leftover entries [64, qn) to the front (at most 31 of them)
+            const int left = qn - 64;
+            uint32_t t0 = 0;
+            int g0 = 0;
+            if (lane < left) { t0 = qi[64 + lane]; g0 = qh[64 + lane]; }
             __syncwarp();
-            if (mv) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) qH[lane][k] = t[k];
-                qh[lane] = th;
-            }
-            qn -= 32;
+            if (lane < left) { qi[lane] = t0; qh[lane] = g0; }
+            qn = left;
             __syncwarp();
         }
     }
-    score_queue(qn);
+    // pool the leftovers (< 64 per warp) and share them out again in batches of 64
+    {
+        int off = 0;
+        if (lane == 0) off = atomicAdd(&s_pool, qn);
+        off = __shfl_sync(kFull, off, 0);
+        if (lane < qn) { s_pi[off + lane] = qi[lane]; s_ph[off + lane] = qh[lane]; }
+        if (lane + 32 < qn) { s_pi[off + lane + 32] = qi[lane + 32]; s_ph[off + lane + 32] = qh[lane + 32]; }
+    }
+    __syncthreads();
+    {
+        const int total = s_pool, e0 = warp * 64 + lane, e1 = e0 + 32;
+        if (warp * 64 < total) {  // unused slots score a copy of entry 0 and are discarded
+            const bool v0 = e0 < total, v1 = e1 < total;
+            solve_and_score(s_pi, s_ph, v0 ? e0 : 0, v1 ? e1 : 0, v0, v1);
+        }
+    }
     // block arg-max: most inliers, ties -> lowest hypothesis index
     int c = best_cnt, hh = best_h;
 #pragma unroll
@@ -415,39 +508,41 @@ __global__ void __launch_bounds__(kFixedThreads) ransac_fixedk_kernel(FitArgs a,
     }
     if (lane == 0) { s_cnt[warp] = c; s_hyp[warp] = hh; }
     __syncthreads();
+    if (warp != 0) return;
     c = s_cnt[0]; hh = s_hyp[0];
 #pragma unroll
-    for (int w2 = 1; w2 < kFixedThreads / 32; ++w2)
+    for (int w2 = 1; w2 < kFixedWarps; ++w2)
         if (s_cnt[w2] > c || (s_cnt[w2] == c && s_hyp[w2] < hh)) { c = s_cnt[w2]; hh = s_hyp[w2]; }
     const bool have = c > 3;  // cv2: goodCount > max(maxGoodCount, modelPoints - 1)
-    if (have && best_h == hh && best_cnt == c) {
+    // The winner's model is recomputed from its sample (same arithmetic, same bits) instead of being carried through
+    // the scoring loop in registers; then back to image -> pitch units, and its inlier list in OpenCV's float scoring
+    // (lanes are points, ballots make the mask) is what the refit starts from.
+    double Hd[9];
+    uint64_t pm = 0;
+    if (have) {
+        int idx[4];
+        fixedk_sample(a, f, key, hh, N, idx);
+        float p[4][4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s_H[k] = best_H[k];
+        for (int k = 0; k < 4; ++k) {
+            const float4 q = s_ps[idx[k]][0];
+            p[k][0] = q.x; p[k][1] = q.z; p[k][2] = q.y; p[k][3] = q.w;
+        }
+        float Hn[8];
+        fixedk_hypothesis(p, Hn);
+        fixedk_denormalise(Hn, s_nm, thr, Hd);
+        float Hf[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) Hf[k] = (float)Hd[k];
+        for (int pass = 0; pass < 2; ++pass) {
+            const int i = pass * 32 + lane;
+            const bool in = i < N && reproj_err_f32(Hf, s_pl.sx[i], s_pl.sy[i], s_pl.dx[i], s_pl.dy[i]) <= a.thr_sq;
+            pm |= (uint64_t)__ballot_sync(kFull, in) << (32 * pass);
+        }
     }
-    __syncthreads();
-    if (warp == 0) {
-        // winner back in image -> pitch units; its inlier list in OpenCV's float scoring (lanes are
-        // points, ballots make the mask) is what the refit starts from
-        double Hd[9];
-        uint64_t pm = 0;
-        if (have) {
-            float Hn[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) Hn[k] = s_H[k];
-            fixedk_denormalise(Hn, s_nm, thr, Hd);
-            float Hf[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) Hf[k] = (float)Hd[k];
-            for (int pass = 0; pass < 2; ++pass) {
-                const int i = pass * 32 + lane;
-                const bool in = i < N && reproj_err_f32(Hf, s_pl.sx[i], s_pl.sy[i], s_pl.dx[i], s_pl.dy[i]) <= a.thr_sq;
-                pm |= (uint64_t)__ballot_sync(kFull, in) << (32 * pass);
-            }
-        }
-        if (lane == 0) {
-            const bool good = have && __popcll(pm) >= 4;
-            park(a, f, good ? EGL_FIT_OK : EGL_FIT_NO_MODEL, N, good ? __popcll(pm) : 0, have ? hh : -1, a.K, Hd, pm, s_used);
-        }
+    if (lane == 0) {
+        const bool good = have && __popcll(pm) >= 4;
+        park(a, f, good ? EGL_FIT_OK : EGL_FIT_NO_MODEL, N, good ? __popcll(pm) : 0, have ? hh : -1, a.K, Hd, pm, s_used);
     }
 }
 

@@ -729,28 +729,50 @@ EGL_HD_NOINLINE int postprocess_keypoints(const int32_t* flat, const float* scor
 }
 
 // ---- fixed-K mode: sample generator and the FP32 minimal solve ------------------------------
-// counter-based sample generator: ONE SplitMix64 output keyed by (seed, frame, hypothesis) gives four
-// 16-bit fields, each scaled to [0, N); a repeated index is bumped to the next free one (mod N).  Cheap
-// (a dozen integer instructions) and reproducible anywhere -- oracle/ransac_f32.c restates it.
+// counter-based sample generator, branch free: a per-frame 64-bit key (one SplitMix64 output of seed and frame)
+// gives two 32-bit keys; hypothesis h hashes (h ^ key) with a 32-bit integer mixer twice -> four 16-bit fields;
+// field i is scaled to [0, N - i) and mapped to the r-th index not drawn yet ("skip" mapping over the sorted
+// earlier picks), so the four indices are distinct and uniform over all ordered 4-subsets.  ~45 integer
+// instructions, reproducible anywhere -- oracle/ransac_f32.c restates it.  Needs N >= 4.
 EGL_HD uint64_t splitmix_mix(uint64_t s) {
     uint64_t z = s + 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
 }
+EGL_HD uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du;
+    x ^= x >> 15; x *= 0x846ca68bu;
+    return x ^ (x >> 16);
+}
+// i += (i >= a): one compare and one predicated add on the device
+EGL_HD void bump_if_ge(int& i, int a) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n.reg .pred p;\nsetp.ge.s32 p, %0, %1;\n@p add.s32 %0, %0, 1;\n}" : "+r"(i) : "r"(a));
+#else
+    i += (i >= a);
+#endif
+}
+EGL_HD uint64_t seeded_frame_key(uint64_t seed, uint64_t frame) { return splitmix_mix(seed ^ (0xD1B54A32D192ED03ull * (frame + 1))); }
+EGL_HD void seeded_subset_keyed(uint64_t key, uint32_t h, int N, int idx[4]) {
+    const uint32_t z0 = mix32(h ^ (uint32_t)key), z1 = mix32(h ^ (uint32_t)(key >> 32));
+    const int r0 = (int)(((z0 & 0xFFFFu) * (uint32_t)N) >> 16), r1 = (int)(((z0 >> 16) * (uint32_t)(N - 1)) >> 16);
+    const int r2 = (int)(((z1 & 0xFFFFu) * (uint32_t)(N - 2)) >> 16), r3 = (int)(((z1 >> 16) * (uint32_t)(N - 3)) >> 16);
+    const int i0 = r0;
+    int i1 = r1, i2 = r2, i3 = r3;
+    bump_if_ge(i1, i0);
+    const int a = i0 < i1 ? i0 : i1, b = i0 < i1 ? i1 : i0;
+    bump_if_ge(i2, a);
+    bump_if_ge(i2, b);
+    const int lo = a < i2 ? a : i2, hi = b > i2 ? b : i2, mid = a + b + i2 - lo - hi;
+    bump_if_ge(i3, lo);
+    bump_if_ge(i3, mid);
+    bump_if_ge(i3, hi);
+    idx[0] = i0; idx[1] = i1; idx[2] = i2; idx[3] = i3;
+}
 EGL_HD void seeded_subset(uint64_t seed, uint64_t frame, uint64_t K, uint64_t h, int N, int idx[4]) {
-    const uint64_t z = splitmix_mix(seed ^ (0xD1B54A32D192ED03ull * (frame * K + h + 1)));
-EGL_UNROLL
-    for (int i = 0; i < 4; ++i) {
-        int v = (int)((((uint32_t)(z >> (16 * i)) & 0xFFFFu) * (uint32_t)N) >> 16);
-        for (int guard = 0; guard < 4; ++guard) {  // at most 3 earlier indices to step over
-            bool dup = false;
-            for (int k = 0; k < i; ++k) dup |= (idx[k] == v);
-            if (!dup) break;
-            v = v + 1 == N ? 0 : v + 1;
-        }
-        idx[i] = v;
-    }
+    (void)K;  // the first K hypotheses of a frame do not depend on K
+    seeded_subset_keyed(seeded_frame_key(seed, frame), (uint32_t)h, N, idx);
 }
 
 // ---- fixed-K hypothesis arithmetic (FP32, every operation explicit so that oracle/ransac_f32.c
@@ -759,7 +781,8 @@ EGL_UNROLL
 // Per FRAME (once): the N correspondences are normalised
 //     X' = (X - cX) * sX,  Y' = (Y - cY) * sY      cX = (sum X)/N, sX = N / sum|X - cX|   (image)
 //     x' = (x - cx) * rt,  y' = (y - cy) * rt      cx = (sum x)/N, rt = 1/thr             (pitch)
-// sums taken sequentially in point order.  Scaling the pitch side by 1/thr turns the inlier test
+// sums in WARP-TREE order (tree_sum64: t_i = v_i + v_{i+32}, then t_i += t_{i^16}, ^8, ^4, ^2, ^1; result t_0), which
+// one warp evaluates with five shuffles.  Scaling the pitch side by 1/thr turns the inlier test
 // |proj - dst|^2 <= thr^2 into  (nx - x'w)^2 + (ny - y'w)^2 <= w^2  with w the projective
 // denominator: no division and no threshold multiply per point.
 // Per HYPOTHESIS: the 8x8 DLT system of the 4 sampled points (h33 = 1)
@@ -771,20 +794,28 @@ struct FixedKNorm {
     float cX, cY, sX, sY, cx, cy, rt;
 };
 
+// sum of v[0..n), n <= 64, in warp-tree order (scalar statement; the kernel does the same with shuffles)
+EGL_HD float tree_sum64(const float* v, int n) {
+    float t[32], u[32];
+    for (int i = 0; i < 32; ++i) t[i] = fadd(i < n ? v[i] : 0.f, i + 32 < n ? v[i + 32] : 0.f);
+    for (int m = 16; m > 0; m >>= 1) {
+        for (int i = 0; i < 32; ++i) u[i] = fadd(t[i], t[i ^ m]);
+        for (int i = 0; i < 32; ++i) t[i] = u[i];
+    }
+    return t[0];
+}
+
 EGL_HD bool fixedk_normalise(const float* sx, const float* sy, const float* dx, const float* dy, int n, float inv_thr,
                              FixedKNorm* nm) {
-    float sX = 0.f, sY = 0.f, sx_ = 0.f, sy_ = 0.f;
-    for (int i = 0; i < n; ++i) {
-        sX = fadd(sX, sx[i]); sY = fadd(sY, sy[i]);
-        sx_ = fadd(sx_, dx[i]); sy_ = fadd(sy_, dy[i]);
-    }
     const float fn = (float)n;
-    nm->cX = fdiv(sX, fn); nm->cY = fdiv(sY, fn); nm->cx = fdiv(sx_, fn); nm->cy = fdiv(sy_, fn);
-    float aX = 0.f, aY = 0.f;
+    nm->cX = fdiv(tree_sum64(sx, n), fn); nm->cY = fdiv(tree_sum64(sy, n), fn);
+    nm->cx = fdiv(tree_sum64(dx, n), fn); nm->cy = fdiv(tree_sum64(dy, n), fn);
+    float dX[64], dY[64];
     for (int i = 0; i < n; ++i) {
-        aX = fadd(aX, fabsf(fsub(sx[i], nm->cX)));
-        aY = fadd(aY, fabsf(fsub(sy[i], nm->cY)));
+        dX[i] = fabsf(fsub(sx[i], nm->cX));
+        dY[i] = fabsf(fsub(sy[i], nm->cY));
     }
+    const float aX = tree_sum64(dX, n), aY = tree_sum64(dY, n);
     if (!(aX > 0.f) || !(aY > 0.f)) return false;
     nm->sX = fdiv(fn, aX);
     nm->sY = fdiv(fn, aY);
@@ -799,84 +830,148 @@ EGL_HD void fixedk_normalise_point(const FixedKNorm& nm, float X, float Y, float
     o[3] = fmul(fsub(y, nm.cy), nm.rt);
 }
 
+// The hypothesis arithmetic is written once, over a lane type V: float (one hypothesis; host + device,
+// the form tests/native/host_check.cpp and the C mirror are held against) or float2 (device only: TWO
+// hypotheses per thread in Blackwell's packed FP32 instructions FFMA2 / FMUL2 / FADD2, IEEE per half,
+// so each half is bit-identical to the float instantiation).  lane_ops<V> supplies the single-rounded
+// operations; M is the per-lane predicate type.
+template <class V> struct lane_ops;
+template <> struct lane_ops<float> {
+    typedef bool M;
+    static EGL_HD float set(float v) { return v; }
+    static EGL_HD float fma(float a, float b, float c) { return fmaf(a, b, c); }
+    static EGL_HD float mul(float a, float b) { return fmul(a, b); }
+    static EGL_HD float add(float a, float b) { return fadd(a, b); }
+    static EGL_HD float sub(float a, float b) { return fsub(a, b); }
+    static EGL_HD float neg(float a) { return -a; }
+    static EGL_HD float abs(float a) { return fabsf(a); }
+    static EGL_HD float rcp(float a) { return fdiv(1.f, a); }
+    static EGL_HD bool gt(float a, float b) { return a > b; }
+    static EGL_HD bool lt(float a, float b) { return a < b; }
+    static EGL_HD float sel(bool m, float a, float b) { return m ? a : b; }
+    static EGL_HD bool land(bool a, bool b) { return a && b; }
+    static EGL_HD bool all_or_none(bool a, bool b, bool c, bool d) { const int n = a + b + c + d; return n == 0 || n == 4; }
+};
+#if defined(__CUDACC__)
+struct bool2 { bool x, y; };
+template <> struct lane_ops<float2> {
+    typedef bool2 M;
+    static __device__ __forceinline__ float2 set(float v) { return make_float2(v, v); }
+    static __device__ __forceinline__ float2 fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+    static __device__ __forceinline__ float2 mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+    static __device__ __forceinline__ float2 add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+    static __device__ __forceinline__ float2 neg(float2 a) { return make_float2(-a.x, -a.y); }
+    static __device__ __forceinline__ float2 sub(float2 a, float2 b) { return __fadd2_rn(a, neg(b)); }  // a - b == a + (-b) exactly
+    static __device__ __forceinline__ float2 abs(float2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }
+    static __device__ __forceinline__ float2 rcp(float2 a) { return make_float2(__fdiv_rn(1.f, a.x), __fdiv_rn(1.f, a.y)); }
+    static __device__ __forceinline__ bool2 gt(float2 a, float2 b) { return bool2{a.x > b.x, a.y > b.y}; }
+    static __device__ __forceinline__ bool2 lt(float2 a, float2 b) { return bool2{a.x < b.x, a.y < b.y}; }
+    static __device__ __forceinline__ float2 sel(bool2 m, float2 a, float2 b) { return make_float2(m.x ? a.x : b.x, m.y ? a.y : b.y); }
+    static __device__ __forceinline__ bool2 land(bool2 a, bool2 b) { return bool2{a.x && b.x, a.y && b.y}; }
+    static __device__ __forceinline__ bool2 all_or_none(bool2 a, bool2 b, bool2 c, bool2 d) {
+        const int nx = a.x + b.x + c.x + d.x, ny = a.y + b.y + c.y + d.y;
+        return bool2{nx == 0 || nx == 4, ny == 0 || ny == 4};
+    }
+};
+#endif
+
 // det of rows (Xa,Ya,1),(Xb,Yb,1),(Xc,Yc,1):  Xa(Yb-Yc) - Ya(Xb-Xc) + (Xb Yc - Xc Yb)
-EGL_HD float det3_f32(float Xa, float Ya, float Xb, float Yb, float Xc, float Yc) {
-    const float t = fmaf(Xb, Yc, -fmul(Xc, Yb));
-    return fmaf(Xa, fsub(Yb, Yc), fmaf(-Ya, fsub(Xb, Xc), t));
+template <class V>
+EGL_HD V det3_v(V Xa, V Ya, V Xb, V Yb, V Xc, V Yc) {
+    typedef lane_ops<V> L;
+    const V t = L::fma(Xb, Yc, L::neg(L::mul(Xc, Yb)));
+    return L::fma(Xa, L::sub(Yb, Yc), L::fma(L::neg(Ya), L::sub(Xb, Xc), t));
+}
+EGL_HD float det3_f32(float Xa, float Ya, float Xb, float Yb, float Xc, float Yc) { return det3_v<float>(Xa, Ya, Xb, Yb, Xc, Yc); }
+
+// Sample test (OpenCV's checkSubset rules evaluated in float on the normalised points: last point collinear
+// with an earlier pair on either side, or orientation not preserved).  S[4] = oriented areas of the image-side
+// triples (0,1,2) (1,2,3) (0,2,3) (0,1,3), which the solve reuses as the left null vector of [X Y 1].
+template <class V>
+EGL_HD typename lane_ops<V>::M fixedk_check_v(const V* X, const V* Y, const V* x, const V* y, V* S) {
+    typedef lane_ops<V> L;
+    S[0] = det3_v<V>(X[0], Y[0], X[1], Y[1], X[2], Y[2]);
+    S[1] = det3_v<V>(X[1], Y[1], X[2], Y[2], X[3], Y[3]);
+    S[2] = det3_v<V>(X[0], Y[0], X[2], Y[2], X[3], Y[3]);
+    S[3] = det3_v<V>(X[0], Y[0], X[1], Y[1], X[3], Y[3]);
+    const V D012 = det3_v<V>(x[0], y[0], x[1], y[1], x[2], y[2]);
+    const V D123 = det3_v<V>(x[1], y[1], x[2], y[2], x[3], y[3]);
+    const V D023 = det3_v<V>(x[0], y[0], x[2], y[2], x[3], y[3]);
+    const V D013 = det3_v<V>(x[0], y[0], x[1], y[1], x[3], y[3]);
+    const V tiny = L::set(1e-6f), zero = L::set(0.f);
+    typename L::M ok = L::land(L::land(L::gt(L::abs(S[1]), tiny), L::gt(L::abs(S[2]), tiny)), L::gt(L::abs(S[3]), tiny));
+    ok = L::land(ok, L::land(L::land(L::gt(L::abs(D123), tiny), L::gt(L::abs(D023), tiny)), L::gt(L::abs(D013), tiny)));
+    return L::land(ok, L::all_or_none(L::lt(L::mul(S[0], D012), zero), L::lt(L::mul(S[1], D123), zero),
+                                      L::lt(L::mul(S[2], D023), zero), L::lt(L::mul(S[3], D013), zero)));
 }
 
-// One hypothesis from 4 normalised correspondences p[k] = (X', Y', x', y').  Returns false when the
-// sample is rejected (OpenCV's checkSubset rules evaluated in float on the normalised points: last
-// point collinear with an earlier pair on either side, or orientation not preserved) or degenerate.
-EGL_HD bool fixedk_hypothesis(const float (*p)[4], float* H /*8*/) {
-    float X[4], Y[4], x[4], y[4];
-EGL_UNROLL
-    for (int k = 0; k < 4; ++k) { X[k] = p[k][0]; Y[k] = p[k][1]; x[k] = p[k][2]; y[k] = p[k][3]; }
-    // oriented areas of the four triples, image side (S) and pitch side (D)
-    const float S012 = det3_f32(X[0], Y[0], X[1], Y[1], X[2], Y[2]);
-    const float S123 = det3_f32(X[1], Y[1], X[2], Y[2], X[3], Y[3]);
-    const float S023 = det3_f32(X[0], Y[0], X[2], Y[2], X[3], Y[3]);
-    const float S013 = det3_f32(X[0], Y[0], X[1], Y[1], X[3], Y[3]);
-    const float D012 = det3_f32(x[0], y[0], x[1], y[1], x[2], y[2]);
-    const float D123 = det3_f32(x[1], y[1], x[2], y[2], x[3], y[3]);
-    const float D023 = det3_f32(x[0], y[0], x[2], y[2], x[3], y[3]);
-    const float D013 = det3_f32(x[0], y[0], x[1], y[1], x[3], y[3]);
-    const float tiny = 1e-6f;
-    bool ok = fabsf(S123) > tiny && fabsf(S023) > tiny && fabsf(S013) > tiny && fabsf(D123) > tiny && fabsf(D023) > tiny &&
-              fabsf(D013) > tiny;
-    const int neg = (fmul(S012, D012) < 0.f) + (fmul(S123, D123) < 0.f) + (fmul(S023, D023) < 0.f) + (fmul(S013, D013) < 0.f);
-    ok = ok && (neg == 0 || neg == 4);
+// Minimal solve of an accepted sample: H[8] (h33 = 1) and the largest-|entry| guard; returns "all entries finite".
+// X, Y, x, y are permuted in place by the pivoting.
+template <class V>
+EGL_HD typename lane_ops<V>::M fixedk_solve_v(V* X, V* Y, V* x, V* y, const V* S, V* H /*8*/) {
+    typedef lane_ops<V> L;
     // left null vector of [X Y 1]: n0 = S123, n1 = -S023, n2 = S013, n3 = -S012
-    float n[4] = {S123, -S023, S013, -S012};
+    V n[4] = {S[1], L::neg(S[2]), S[3], L::neg(S[0])};
     // pivot: move the row with the largest |n| to slot 3 (the other three rows then have the largest 3x3 determinant)
 EGL_UNROLL
     for (int k = 0; k < 3; ++k) {
-        const bool sw = fabsf(n[k]) > fabsf(n[3]);
-        float t;
-        t = n[3]; n[3] = sw ? n[k] : t; n[k] = sw ? t : n[k];
-        t = X[3]; X[3] = sw ? X[k] : t; X[k] = sw ? t : X[k];
-        t = Y[3]; Y[3] = sw ? Y[k] : t; Y[k] = sw ? t : Y[k];
-        t = x[3]; x[3] = sw ? x[k] : t; x[k] = sw ? t : x[k];
-        t = y[3]; y[3] = sw ? y[k] : t; y[k] = sw ? t : y[k];
+        const typename L::M sw = L::gt(L::abs(n[k]), L::abs(n[3]));
+        V t;
+        t = n[3]; n[3] = L::sel(sw, n[k], t); n[k] = L::sel(sw, t, n[k]);
+        t = X[3]; X[3] = L::sel(sw, X[k], t); X[k] = L::sel(sw, t, X[k]);
+        t = Y[3]; Y[3] = L::sel(sw, Y[k], t); Y[k] = L::sel(sw, t, Y[k]);
+        t = x[3]; x[3] = L::sel(sw, x[k], t); x[k] = L::sel(sw, t, x[k]);
+        t = y[3]; y[3] = L::sel(sw, y[k], t); y[k] = L::sel(sw, t, y[k]);
     }
     // 2x2 system for (h6, h7):  sum n_i * row_i
-    float a11 = 0.f, a12 = 0.f, a21 = 0.f, a22 = 0.f, b1 = 0.f, b2 = 0.f;
+    V a11 = L::set(0.f), a12 = a11, a21 = a11, a22 = a11, b1 = a11, b2 = a11;
 EGL_UNROLL
     for (int k = 0; k < 4; ++k) {
-        const float nx = fmul(n[k], x[k]), ny = fmul(n[k], y[k]);
-        a11 = fmaf(-nx, X[k], a11); a12 = fmaf(-nx, Y[k], a12); b1 = fadd(b1, nx);
-        a21 = fmaf(-ny, X[k], a21); a22 = fmaf(-ny, Y[k], a22); b2 = fadd(b2, ny);
+        const V nx = L::mul(n[k], x[k]), ny = L::mul(n[k], y[k]);
+        a11 = L::fma(L::neg(nx), X[k], a11); a12 = L::fma(L::neg(nx), Y[k], a12); b1 = L::add(b1, nx);
+        a21 = L::fma(L::neg(ny), X[k], a21); a22 = L::fma(L::neg(ny), Y[k], a22); b2 = L::add(b2, ny);
     }
-    const float Dt = fmaf(a11, a22, -fmul(a12, a21));
-    const float rD = fdiv(1.f, Dt);
-    const float h6 = fmul(fmaf(b1, a22, -fmul(a12, b2)), rD);
-    const float h7 = fmul(fmaf(a11, b2, -fmul(b1, a21)), rD);
+    const V Dt = L::fma(a11, a22, L::neg(L::mul(a12, a21)));
+    const V rD = L::rcp(Dt);
+    const V h6 = L::mul(L::fma(b1, a22, L::neg(L::mul(a12, b2))), rD);
+    const V h7 = L::mul(L::fma(a11, b2, L::neg(L::mul(b1, a21))), rD);
     // h0..h5 from rows 0,1,2:  [X Y 1] (h0,h1,h2)^T = x*w,  (h3,h4,h5)^T likewise with y*w
-    float u[3], v[3];
+    V u[3], v[3];
 EGL_UNROLL
     for (int k = 0; k < 3; ++k) {
-        const float w = fmaf(h6, X[k], fmaf(h7, Y[k], 1.f));
-        u[k] = fmul(x[k], w);
-        v[k] = fmul(y[k], w);
+        const V w = L::fma(h6, X[k], L::fma(h7, Y[k], L::set(1.f)));
+        u[k] = L::mul(x[k], w);
+        v[k] = L::mul(y[k], w);
     }
-    const float dP = det3_f32(X[0], Y[0], X[1], Y[1], X[2], Y[2]);
-    const float rP = fdiv(1.f, dP);
-    const float c0 = fsub(Y[1], Y[2]), c1 = fsub(Y[2], Y[0]), c2 = fsub(Y[0], Y[1]);
-    const float d0 = fsub(X[2], X[1]), d1 = fsub(X[0], X[2]), d2 = fsub(X[1], X[0]);
-    const float e0 = fmaf(X[1], Y[2], -fmul(X[2], Y[1])), e1 = fmaf(X[2], Y[0], -fmul(X[0], Y[2])),
-                e2 = fmaf(X[0], Y[1], -fmul(X[1], Y[0]));
-    H[0] = fmul(fmaf(u[0], c0, fmaf(u[1], c1, fmul(u[2], c2))), rP);
-    H[1] = fmul(fmaf(u[0], d0, fmaf(u[1], d1, fmul(u[2], d2))), rP);
-    H[2] = fmul(fmaf(u[0], e0, fmaf(u[1], e1, fmul(u[2], e2))), rP);
-    H[3] = fmul(fmaf(v[0], c0, fmaf(v[1], c1, fmul(v[2], c2))), rP);
-    H[4] = fmul(fmaf(v[0], d0, fmaf(v[1], d1, fmul(v[2], d2))), rP);
-    H[5] = fmul(fmaf(v[0], e0, fmaf(v[1], e1, fmul(v[2], e2))), rP);
+    const V dP = det3_v<V>(X[0], Y[0], X[1], Y[1], X[2], Y[2]);
+    const V rP = L::rcp(dP);
+    const V c0 = L::sub(Y[1], Y[2]), c1 = L::sub(Y[2], Y[0]), c2 = L::sub(Y[0], Y[1]);
+    const V d0 = L::sub(X[2], X[1]), d1 = L::sub(X[0], X[2]), d2 = L::sub(X[1], X[0]);
+    const V e0 = L::fma(X[1], Y[2], L::neg(L::mul(X[2], Y[1]))), e1 = L::fma(X[2], Y[0], L::neg(L::mul(X[0], Y[2]))),
+            e2 = L::fma(X[0], Y[1], L::neg(L::mul(X[1], Y[0])));
+    H[0] = L::mul(L::fma(u[0], c0, L::fma(u[1], c1, L::mul(u[2], c2))), rP);
+    H[1] = L::mul(L::fma(u[0], d0, L::fma(u[1], d1, L::mul(u[2], d2))), rP);
+    H[2] = L::mul(L::fma(u[0], e0, L::fma(u[1], e1, L::mul(u[2], e2))), rP);
+    H[3] = L::mul(L::fma(v[0], c0, L::fma(v[1], c1, L::mul(v[2], c2))), rP);
+    H[4] = L::mul(L::fma(v[0], d0, L::fma(v[1], d1, L::mul(v[2], d2))), rP);
+    H[5] = L::mul(L::fma(v[0], e0, L::fma(v[1], e1, L::mul(v[2], e2))), rP);
     H[6] = h6;
     H[7] = h7;
-    float acc = 0.f;
+    V acc = L::set(0.f);
 EGL_UNROLL
-    for (int k = 0; k < 8; ++k) acc = fadd(acc, fabsf(H[k]));
-    return ok && (acc < INFINITY);  // false for inf / NaN entries
+    for (int k = 0; k < 8; ++k) acc = L::add(acc, L::abs(H[k]));
+    return L::lt(acc, L::set(INFINITY));  // false for inf / NaN entries
+}
+
+// One hypothesis from 4 normalised correspondences p[k] = (X', Y', x', y').  Returns false when the
+// sample is rejected or degenerate.
+EGL_HD bool fixedk_hypothesis(const float (*p)[4], float* H /*8*/) {
+    float X[4], Y[4], x[4], y[4], S[4];
+EGL_UNROLL
+    for (int k = 0; k < 4; ++k) { X[k] = p[k][0]; Y[k] = p[k][1]; x[k] = p[k][2]; y[k] = p[k][3]; }
+    const bool ok = fixedk_check_v<float>(X, Y, x, y, S);
+    const bool fin = fixedk_solve_v<float>(X, Y, x, y, S, H);
+    return ok && fin;
 }
 
 // Inlier test of one normalised point under a normalised hypothesis (division-free).

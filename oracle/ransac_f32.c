@@ -23,15 +23,32 @@ static float det_rows(float Xa, float Ya, float Xb, float Yb, float Xc, float Yc
     return fmaf(Xa, Yb - Yc, fmaf(-Ya, Xb - Xc, t));
 }
 
-/* frame normalisation: sequential sums in point order */
+/* sum of v[0..n), n <= 64, in the specification's tree order: 32 partial sums t[i] = v[i] + v[i+32] (absent terms are
+ * +0), then five pairwise rounds combining t[i] with t[i ^ 16], t[i ^ 8], ... t[i ^ 1]; the total is t[0] */
+static float tree_total(const float *v, int n)
+{
+    float t[32], u[32];
+    int i, m;
+    for (i = 0; i < 32; i++) {
+        float lo = (i < n) ? v[i] : 0.0f, hi = (i + 32 < n) ? v[i + 32] : 0.0f;
+        t[i] = lo + hi;
+    }
+    for (m = 16; m >= 1; m /= 2) {
+        for (i = 0; i < 32; i++) u[i] = t[i] + t[i ^ m];
+        memcpy(t, u, sizeof(t));
+    }
+    return t[0];
+}
+
+/* frame normalisation */
 static int frame_norm(const float *X, const float *Y, const float *x, const float *y, int n, float inv_thr, norm_t *m)
 {
-    float a = 0, b = 0, c = 0, d = 0;
+    float dX[64], dY[64], a, b;
     int i;
-    for (i = 0; i < n; i++) { a = a + X[i]; b = b + Y[i]; c = c + x[i]; d = d + y[i]; }
-    m->cX = a / (float)n; m->cY = b / (float)n; m->cx = c / (float)n; m->cy = d / (float)n;
-    a = 0; b = 0;
-    for (i = 0; i < n; i++) { a = a + fabsf(X[i] - m->cX); b = b + fabsf(Y[i] - m->cY); }
+    m->cX = tree_total(X, n) / (float)n; m->cY = tree_total(Y, n) / (float)n;
+    m->cx = tree_total(x, n) / (float)n; m->cy = tree_total(y, n) / (float)n;
+    for (i = 0; i < n; i++) { dX[i] = fabsf(X[i] - m->cX); dY[i] = fabsf(Y[i] - m->cY); }
+    a = tree_total(dX, n); b = tree_total(dY, n);
     if (!(a > 0) || !(b > 0)) return 0;
     m->sX = (float)n / a; m->sY = (float)n / b; m->rt = inv_thr;
     return 1;
@@ -145,27 +162,41 @@ int orc_fixedk_frame(const float *X, const float *Y, const float *x, const float
     return 0;
 }
 
-/* the kernel's counter-based sample generator, restated: one SplitMix64 output per hypothesis, four 16-bit
- * fields scaled to [0, n), repeated indices bumped to the next free index modulo n */
+/* the kernel's counter-based sample generator, restated: a per-frame key (one SplitMix64 output of seed and frame)
+ * split into two 32-bit keys; hypothesis hh hashes (hh ^ key) with a 32-bit mixer twice -> four 16-bit fields; field i
+ * is scaled to [0, n - i) and selects the r-th index that has not been drawn yet */
+static uint32_t mixer32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352du;
+    x ^= x >> 15; x *= 0x846ca68bu;
+    return x ^ (x >> 16);
+}
+
 void orc_seeded_table(uint64_t seed, uint64_t frame, int K, int n, uint8_t *table)
 {
-    int hh, i, k, g;
+    uint64_t z = (seed ^ (0xD1B54A32D192ED03ull * (frame + 1))) + 0x9E3779B97F4A7C15ull;
+    int hh, i, j;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
     for (hh = 0; hh < K; hh++) {
-        uint64_t z = (seed ^ (0xD1B54A32D192ED03ull * (frame * (uint64_t)K + (uint64_t)hh + 1))) + 0x9E3779B97F4A7C15ull;
-        int idx[4];
-        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-        z ^= z >> 31;
+        uint32_t w[2], field[4];
+        int taken[4], cnt = 0;
+        w[0] = mixer32((uint32_t)hh ^ (uint32_t)z);
+        w[1] = mixer32((uint32_t)hh ^ (uint32_t)(z >> 32));
+        field[0] = w[0] & 0xFFFFu; field[1] = w[0] >> 16; field[2] = w[1] & 0xFFFFu; field[3] = w[1] >> 16;
         for (i = 0; i < 4; i++) {
-            int v = (int)(((uint32_t)((z >> (16 * i)) & 0xFFFFu) * (uint32_t)n) >> 16);
-            for (g = 0; g < 4; g++) {
-                int dup = 0;
-                for (k = 0; k < i; k++) dup |= (idx[k] == v);
-                if (!dup) break;
-                v = (v + 1 == n) ? 0 : v + 1;
+            /* r-th free index: walk the indices in increasing order, skipping the ones already taken */
+            int r = (int)((field[i] * (uint32_t)(n - i)) >> 16), v;
+            for (v = 0; v < n; v++) {
+                int used = 0;
+                for (j = 0; j < cnt; j++) used |= (taken[j] == v);
+                if (used) continue;
+                if (r == 0) break;
+                r--;
             }
-            idx[i] = v;
+            taken[cnt++] = v;
+            table[4 * hh + i] = (uint8_t)v;
         }
-        for (i = 0; i < 4; i++) table[4 * hh + i] = (uint8_t)idx[i];
     }
 }

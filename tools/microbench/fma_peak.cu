@@ -1,5 +1,7 @@
-// FP32 FMA throughput microbenchmark (roofline denominator for the RANSAC hypothesis kernel):
-// every thread runs 8 independent FFMA chains; reports TFLOP/s (FMA = 2 FLOP).
+// FP32 throughput microbenchmark (roofline denominator for the RANSAC hypothesis kernel).
+// Two kernels: scalar FFMA (8 independent chains per thread) and Blackwell's packed FFMA2 (8 independent float2
+// chains per thread = 16 FMAs per instruction group).  Reports TFLOP/s (FMA = 2 FLOP) for both, best of 5 after a
+// warm-up, as one JSON line; `python tools/microbench/run_fma_peak.py` stores it in profiles/fp32_peak.json.
 #include <cstdio>
 #include <cuda_runtime.h>
 
@@ -15,27 +17,55 @@ __global__ void __launch_bounds__(256) fma_kernel(float* out, int iters, float a
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
-int main() {
-    int sms = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    const int blocks = sms * 8, threads = 256, iters = 20000;
-    float* out;
-    cudaMalloc(&out, (size_t)blocks * threads * sizeof(float));
+__global__ void __launch_bounds__(256) fma2_kernel(float* out, int iters, float a, float b) {
+    float2 x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = make_float2(threadIdx.x + k, threadIdx.x + k + 0.5f);
+    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = __ffma2_rn(x[k], a2, b2);
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += x[k].x + x[k].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <class Kern>
+static double run(Kern kern, float* out, int blocks, int threads, int iters, double fma_per_thread_iter, const char* name) {
     cudaEvent_t s, e;
     cudaEventCreate(&s); cudaEventCreate(&e);
     double best = 0;
     for (int rep = 0; rep < 6; ++rep) {
         cudaEventRecord(s);
-        fma_kernel<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+        kern<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
         cudaEventRecord(e);
         cudaEventSynchronize(e);
         float ms = 0;
         cudaEventElapsedTime(&ms, s, e);
-        const double flop = 2.0 * 64.0 * iters * (double)blocks * threads;
+        const double flop = 2.0 * fma_per_thread_iter * iters * (double)blocks * threads;
         const double tf = flop / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
-        printf("rep %d: %.3f ms  %.2f TFLOP/s\n", rep, ms, tf);
+        fprintf(stderr, "%s rep %d: %.3f ms  %.2f TFLOP/s\n", name, rep, ms, tf);
     }
-    printf("{\"fp32_fma_tflops\": %.2f, \"sms\": %d}\n", best, sms);
+    return best;
+}
+
+int main() {
+    int sms = 0, khz = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+    const int blocks = sms * 8, threads = 256, iters = 20000;
+    float* out;
+    cudaMalloc(&out, (size_t)blocks * threads * sizeof(float));
+    const double ffma = run(fma_kernel, out, blocks, threads, iters, 64.0, "FFMA ");
+    const double ffma2 = run(fma2_kernel, out, blocks, threads, iters, 128.0, "FFMA2");
+    printf("{\"fp32_fma_tflops\": %.2f, \"fp32_fma2_tflops\": %.2f, \"sms\": %d, \"max_sm_mhz\": %d, "
+           "\"nominal_tflops_at_max_clock\": %.2f}\n",
+           ffma, ffma2, sms, khz / 1000, 2.0 * 128 * sms * (khz * 1e3) / 1e12);
     return 0;
 }
