@@ -37,6 +37,7 @@ lib.egl_decode_logits.argtypes = [_vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _v
 lib.egl_synthesize_keypoints.argtypes = [_vp, _vp, _vp, _i, _i, _vp]
 lib.egl_fit_homography.argtypes = [_vp, _vp, _vp, _i, _i, _i, _vp, _u64, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp]
 lib.egl_select_homography.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp]
+lib.egl_select_homography_chunk.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
 lib.egl_project_points.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
 lib.egl_pyramid_bytes.argtypes = [_i, _i, _i]
 lib.egl_pyramid_bytes.restype = C.c_int64
@@ -53,13 +54,14 @@ for _name in ("egl_refine_keypoints", "egl_fit_homography_subpixel", "egl_gray_p
               "egl_fit_homography_masked", "egl_commit_fit", "egl_refine_keypoints", "egl_fit_homography_subpixel"):
     getattr(lib, _name).restype = _i
 for _name in ("egl_preprocess_u8", "egl_decode_heatmaps", "egl_decode_logits", "egl_synthesize_keypoints", "egl_fit_homography",
-              "egl_select_homography", "egl_project_points"):
+              "egl_select_homography", "egl_select_homography_chunk", "egl_project_points"):
     getattr(lib, _name).restype = _i
 
 EXPORTS = ("egl_version", "egl_last_error", "egl_sm_count", "egl_preprocess_u8", "egl_decode_heatmaps", "egl_decode_logits",
            "egl_synthesize_keypoints", "egl_fit_homography", "egl_select_homography", "egl_project_points", "egl_pyramid_bytes",
            "egl_gray_pyramid", "egl_track_keypoints", "egl_filter_flow", "egl_merge_keypoints", "egl_calibrate_keypoints",
-           "egl_fit_homography_masked", "egl_commit_fit", "egl_refine_keypoints", "egl_fit_homography_subpixel")
+           "egl_fit_homography_masked", "egl_commit_fit", "egl_refine_keypoints", "egl_fit_homography_subpixel",
+           "egl_select_homography_chunk")
 
 if lib.egl_version() != ABI_VERSION:
     raise NativeError(f"libeagle_b200.so has ABI {lib.egl_version()}, this package expects {ABI_VERSION}; rebuild")

@@ -24,16 +24,36 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
+def assemble_module_path() -> str:
+    import sysconfig
+    return os.path.join(PKG, "_assemble" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_assemble(force: bool = False) -> str:
+    """The CPython extension that builds the result dicts (csrc/assemble.c), compiled with gcc."""
+    import sysconfig
+    out = assemble_module_path()
+    src = os.path.join(CSRC, "assemble.c")
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        raise RuntimeError("gcc not found")
+    subprocess.check_call([cc, "-O2", "-fPIC", "-shared", "-Wall", "-I", sysconfig.get_paths()["include"], src, "-o", out])
+    return out
+
+
 def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(PKG), "include", "eagle_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f != "assemble.c"] + [os.path.join(os.path.dirname(PKG), "include", "eagle_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build_native(force: bool = False, verbose: bool = False) -> str:
     """Compile every .cu under csrc/ into one shared object; returns its path."""
+    build_assemble(force)
     if not force and not _stale():
         return LIB
     nvcc = nvcc_path()

@@ -26,6 +26,7 @@ reference's Lucas-Kanade propagation (coordinate_model.py:277-330, 419-478, 520-
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Sequence
 
 import numpy as np
@@ -34,7 +35,7 @@ import torch
 from . import _native as N
 from .engine import GeometryEngine
 from .pitch import LANDMARK_NAMES, OFF_PLANE, PITCH_LENGTH_M, PITCH_WIDTH_M
-from .boxes import objects_to_arrays
+from .boxes import max_objects, objects_to_arrays
 
 BATCH = 4  # reference's HRNet batch (coordinate_model.py:20); only the chunking of the network calls
 
@@ -55,12 +56,11 @@ def _bbox_list(bbox):
     return np.array(bbox, dtype=np.uint16).tolist()
 
 
-def assemble_frames(objects_per_frame, fps: int, first_index: int, kp_xy, kp_order, kp_count, used_mask, inlier_mask,
-                    status, attempted, h_index, coords_i, in_bounds, bounds, kp_src=None) -> dict:
-    """Host-side dict assembly (coordinate_model.py:359-362, 369-392, 405-415) from the arrays the
-    kernels produced (all numpy, already on the host).  The arrays are turned into plain Python lists
-    once, so the per-frame loop only touches native ints and floats (this loop is the serial part of the
-    drop-in API: ~0.1 ms per frame).
+def assemble_frames_py(objects_per_frame, fps: int, first_index: int, kp_xy, kp_order, kp_count, used_mask, inlier_mask,
+                       status, attempted, h_index, coords_i, in_bounds, bounds, kp_src=None) -> dict:
+    """The readable statement of the dict assembly (coordinate_model.py:359-362, 369-392, 405-415) from the arrays
+    the kernels produced (all numpy, already on the host).  ``assemble_frames`` -- the C extension built from
+    csrc/assemble.c -- must return exactly this (tests/test_assemble.py); it is what the product calls.
 
     With ``kp_src`` (keypoint propagation) the keypoint sets are already what the reference holds in
     ``prev_keypoints`` at the end of each frame -- the inlier commit ran on the device -- and kp_src says
@@ -121,6 +121,42 @@ def assemble_frames(objects_per_frame, fps: int, first_index: int, kp_xy, kp_ord
     return res
 
 
+_OFF_PLANE_MASK = sum(1 << c for c in OFF_PLANE)
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def assemble_frames(objects_per_frame, fps: int, first_index: int, kp_xy, kp_order, kp_count, used_mask, inlier_mask,
+                    status, attempted, h_index, coords_i, in_bounds, bounds, kp_src=None, out: dict | None = None) -> dict:
+    """Dict assembly through the C extension (csrc/assemble.c): a few microseconds per frame instead of 50-150.
+    Same arguments and result as assemble_frames_py; ``out`` lets a caller append the frames of successive chunks
+    to one dict.  The cyclic garbage collector is paused meanwhile: the records are millions of small containers,
+    none of them cyclic, and generation-2 passes over them would cost more than the assembly itself."""
+    import gc
+
+    from . import _assemble
+    res = {} if out is None else out
+    objects_per_frame = objects_per_frame if type(objects_per_frame) is list else list(objects_per_frame)
+    if kp_src is None:
+        fitted = _c((np.asarray(attempted) != 0) & (np.asarray(status) == N.FIT_OK), np.uint8)
+        inl, src = _c(inlier_mask, np.int64), None
+    else:
+        fitted, inl, src = None, None, _c(kp_src, np.uint8)
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        _assemble.assemble(res, objects_per_frame, int(fps), int(first_index), LANDMARK_NAMES, _c(kp_xy, np.int32), _c(kp_order, np.uint8),
+                           _c(kp_count, np.int32), inl, fitted, _c(h_index, np.int32), _c(coords_i, np.int64), _c(in_bounds, np.uint8),
+                           _c(bounds, np.float64), src, _OFF_PLANE_MASK, int(PITCH_WIDTH_M), _bbox_list, np.int64, int(N.KP_PY_INT),
+                           int(N.KP_FLOAT))
+    finally:
+        if was:
+            gc.enable()
+    return res
+
+
 class GeometryPath:
     """decode -> synthesis -> fit -> cadence -> projection for frames whose heatmaps and boxes exist."""
 
@@ -148,16 +184,16 @@ class GeometryPath:
     def run(self, heatmaps: torch.Tensor, objects_per_frame: Sequence[dict], width: int, height: int, fps: int,
             homography_interval: int = 1, first_index: int = 0) -> dict:
         """heatmaps (F,57,h,w) float32 CUDA tensor + detect_objects() dicts -> reference result dict."""
-        max_pts = max(1, max(sum(len(v) for v in o.values()) for o in objects_per_frame))
-        foot_h, count_h = objects_to_arrays(list(objects_per_frame), max_pts)
+        objects_per_frame = list(objects_per_frame)
+        foot_h, count_h = objects_to_arrays(objects_per_frame, max(1, max_objects(objects_per_frame)))
         dev = self.engine.device
         foot = torch.from_numpy(foot_h).to(dev, non_blocking=True)
         count = torch.from_numpy(count_h).to(dev, non_blocking=True)
         kp, fit, h_index, attempted, proj = self.run_device(heatmaps, foot, count, width, height, homography_interval)
-        c = lambda t: t.cpu().numpy()
-        return assemble_frames(objects_per_frame, fps, first_index, c(kp.xy), c(kp.order), c(kp.count), c(fit.used_mask),
-                               c(fit.inlier_mask), c(fit.status), c(attempted), c(h_index), c(proj.coords_i),
-                               c(proj.in_bounds), c(proj.bounds))
+        from .sharding import download
+        return assemble_frames(objects_per_frame, fps, first_index, *download([kp.xy, kp.order, kp.count, fit.used_mask, fit.inlier_mask,
+                                                                               fit.status, attempted, h_index, proj.coords_i,
+                                                                               proj.in_bounds, proj.bounds]))
 
 
 class CoordinateModel:
@@ -174,6 +210,12 @@ class CoordinateModel:
         self.chunk = chunk
         self.path = GeometryPath(device, keypoint_conf)
         self._staging, self._staged = None, [None, None]
+        self._stream, self._stream_key = None, None
+        self.network_batch = BATCH     # frames per keypoint_model call (the reference feeds the network 4 at a time, :20)
+        # host threads filling the page-locked staging buffers: one frame per task; a single core moves 4-10 GB/s, the PCIe
+        # link 55, so the copy-in is spread over the cores this process may run on (at most 16)
+        self.copy_threads = max(2, min(16, len(os.sched_getaffinity(0))))
+        self.profile = False           # time H2D / kernels / D2H of every chunk with CUDA events (last_stats)
         self.always_propagate = False  # route every clip through PropagatedPath (tests)
         self.piece_frames = 2048       # sparse cadence: frames resident in HBM at a time (12.7 GB of 1080p frames + 5.6 GB of pyramids)
         self.last_stats = {}
@@ -184,13 +226,19 @@ class CoordinateModel:
         return self._detect_objects(frame)
 
     @torch.no_grad()
-    def _heatmaps_dev(self, dev_frames: torch.Tensor) -> torch.Tensor:
-        """K1 + the attached network on frames that already are in HBM ((n, H, W, 3) uint8)."""
+    def _heatmaps_of(self, x: torch.Tensor) -> torch.Tensor:
+        """The attached network on a preprocessed (n, 3, 540, 960) tensor, ``network_batch`` frames per call."""
         if self.keypoint_model is None:
             raise RuntimeError("no keypoint network attached: pass keypoint_model=<callable tensor -> heatmaps>")
-        x = self.path.engine.preprocess(dev_frames.contiguous())
-        outs = [self.keypoint_model(x[i:i + BATCH]) for i in range(0, x.shape[0], BATCH)]
-        return torch.cat(outs).to(torch.float32).contiguous()
+        b = max(1, int(self.network_batch))
+        outs = [self.keypoint_model(x[i:i + b]) for i in range(0, x.shape[0], b)]
+        hm = outs[0] if len(outs) == 1 else torch.cat(outs)
+        return hm.to(torch.float32).contiguous()
+
+    @torch.no_grad()
+    def _heatmaps_dev(self, dev_frames: torch.Tensor) -> torch.Tensor:
+        """K1 + the attached network on frames that already are in HBM ((n, H, W, 3) uint8)."""
+        return self._heatmaps_of(self.path.engine.preprocess(dev_frames.contiguous()))
 
     def _upload(self, frames: Sequence[np.ndarray], dst: torch.Tensor, group: int = 32) -> None:
         """Host frames -> dst (n, H, W, 3) on the device through two reusable page-locked staging buffers
@@ -228,7 +276,12 @@ class CoordinateModel:
 
     def get_coordinates(self, frames, fps: int, num_homography: int = 1, num_keypoint_detection: int = 1,
                         verbose: bool = True, calibration: bool = False) -> dict:
-        """coordinate_model.py:188-417."""
+        """coordinate_model.py:188-417.
+
+        With a keypoint interval of 1 the clip streams through eagle_b200.streaming.DenseStream: page-locked staging
+        filled by a thread pool, H2D, kernels and the packed D2H on three streams, dict assembly (C extension) in a worker
+        thread, the homography cadence carried from chunk to chunk in device memory.  ``last_stats`` has the host-side
+        split (detector, staging, assembly seconds and the bytes moved)."""
         if len(frames) == 0:
             return {}
         homography_interval = max(1, int(fps / max(1, num_homography)))
@@ -236,32 +289,28 @@ class CoordinateModel:
         if keypoint_interval != 1 or calibration or self.always_propagate:
             return self._get_coordinates_propagated(frames, fps, homography_interval, keypoint_interval, calibration)
         height, width = frames[0].shape[:2]
-        # cadence state crosses chunk boundaries through carry_in; chunks keep memory bounded
-        all_obj = [self.detect_objects(f) for f in frames]
-        # the select kernel needs the whole clip's statuses, so fit per chunk first, then select+project once
-        e = self.path.engine
-        kps, fits = [], []
-        for s in range(0, len(frames), self.chunk):
-            hm = self._heatmaps(frames[s:s + self.chunk])
-            kp = e.decode(hm, width, height, self.keypoint_conf)
-            e.synthesize(kp)
-            kps.append(kp)
-            fits.append(e.fit(kp))
-        cat = lambda xs: torch.cat(xs) if len(xs) > 1 else xs[0]
-        if int(torch.stack([(k.count[:, 1] < 4).any() for k in kps]).any().item()):
+        # chunks hold whole cadence segments, so the cadence of a chunk needs one number from its predecessor
+        chunk = max(homography_interval, self.chunk // homography_interval * homography_interval)
+        key = (height, width, chunk)
+        if self._stream is None or self._stream_key != key:
+            if self._stream is not None:
+                self._stream.close()
+            from .streaming import DenseStream
+            self._stream, self._stream_key = DenseStream(self.path.engine, height, width, chunk, copy_threads=self.copy_threads), key
+
+        def assemble(objs, first, a, out):
+            assemble_frames(objs, fps, first, a["xy"], a["order"], a["count"], None, a["inlier_mask"], a["status"], a["attempted"],
+                            a["h_index"], a["coords_i"], a["in_bounds"], a["bounds"], out=out)
+
+        stats = {}
+        with torch.no_grad():
+            res, all_obj, aborted = self._stream.run(frames, self.detect_objects, self._heatmaps_of, fps, homography_interval,
+                                                     self.keypoint_conf, assemble, stats=stats, profile=self.profile)
+        self.last_stats = stats
+        if aborted:
             # a frame decoded < 4 landmarks: the reference brings optical flow in (:287-311)
             return self._get_coordinates_propagated(frames, fps, homography_interval, keypoint_interval, calibration, all_obj)
-        status = cat([f.status for f in fits]); Hs = cat([f.H for f in fits])
-        h_index, attempted = e.select(status, homography_interval)
-        max_pts = max(1, max(sum(len(v) for v in o.values()) for o in all_obj))
-        foot_h, count_h = objects_to_arrays(all_obj, max_pts)
-        proj = e.project(Hs, torch.from_numpy(foot_h).to(self.device), torch.from_numpy(count_h).to(self.device), width, height,
-                         h_index=h_index)
-        c = lambda t: t.cpu().numpy()
-        return assemble_frames(all_obj, fps, 0, c(cat([k.xy for k in kps])), c(cat([k.order for k in kps])),
-                               c(cat([k.count for k in kps])), c(cat([f.used_mask for f in fits])),
-                               c(cat([f.inlier_mask for f in fits])), c(status), c(attempted), c(h_index), c(proj.coords_i),
-                               c(proj.in_bounds), c(proj.bounds))
+        return res
 
     def _get_coordinates_propagated(self, frames, fps: int, homography_interval: int, keypoint_interval: int, calibration: bool,
                                     all_obj=None) -> dict:
@@ -302,10 +351,10 @@ class CoordinateModel:
             stats["pieces"] += 1
         out = finalize(e, pieces)
         self.last_stats = stats
-        max_pts = max(1, max(sum(len(v) for v in o.values()) for o in all_obj))
-        foot_h, count_h = objects_to_arrays(all_obj, max_pts)
+        foot_h, count_h = objects_to_arrays(all_obj, max(1, max_objects(all_obj)))
         proj = e.project(out["H"], torch.from_numpy(foot_h).to(self.device), torch.from_numpy(count_h).to(self.device), width, height,
                          h_index=out["h_index"])
-        c = lambda t: t.cpu().numpy()
-        return assemble_frames(all_obj, fps, 0, c(out["xy"]), c(out["order"]), c(out["count"]), None, None, None, None, c(out["h_index"]),
-                               c(proj.coords_i), c(proj.in_bounds), c(proj.bounds), kp_src=c(out["src"]))
+        from .sharding import download
+        xy_h, order_h, count_h, hi_h, ci_h, ib_h, bd_h, src_h = download([out["xy"], out["order"], out["count"], out["h_index"], proj.coords_i,
+                                                                          proj.in_bounds, proj.bounds, out["src"]])
+        return assemble_frames(all_obj, fps, 0, xy_h, order_h, count_h, None, None, None, None, hi_h, ci_h, ib_h, bd_h, kp_src=src_h)

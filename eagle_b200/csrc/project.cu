@@ -83,8 +83,12 @@ __global__ void __launch_bounds__(128) project_kernel(const double* __restrict__
 // One CTA; each thread scans a contiguous slice, slice maxima are combined by a block scan.
 constexpr int kSelThreads = 1024;
 
+// `base` = clip index of status[0] (a multiple of interval) -- h_index holds CLIP rows, so a clip can be processed chunk
+// by chunk; the row valid before the chunk comes from carry_in or, when carry_ptr is given, from device memory (the
+// previous chunk's carry_out: no host round trip between chunks).
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const int32_t* __restrict__ status, int F, int interval,
-                                                             int carry_in, int32_t* h_index, uint8_t* attempted) {
+                                                             int carry_in, int32_t* h_index, uint8_t* attempted, int base = 0,
+                                                             const int32_t* carry_ptr = nullptr, int32_t* carry_out = nullptr) {
     __shared__ int s_max[kSelThreads];
     const int tid = threadIdx.x;
     const int per = (F + kSelThreads - 1) / kSelThreads;
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const int32_t* __re
         bool earlier = false;
         for (int j = b; j < i && !earlier; ++j) earlier = status[j] == EGL_FIT_OK;
         attempted[i] = !earlier;
-        const int ev = (!earlier && status[i] == EGL_FIT_OK) ? i : -1;
+        const int ev = (!earlier && status[i] == EGL_FIT_OK) ? base + i : -1;
         run = max(run, ev);
         h_index[i] = run;  // local running max, fixed up below
     }
@@ -110,8 +114,13 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const int32_t* __re
         s_max[tid] = v;
         __syncthreads();
     }
+    if (carry_ptr) carry_in = *carry_ptr;
     const int before = max(tid > 0 ? s_max[tid - 1] : -1, carry_in);
     for (int i = lo; i < hi; ++i) h_index[i] = max(h_index[i], before);
+    if (carry_out) {  // every thread has read *carry_ptr before anyone overwrites it (carry_out may alias carry_ptr)
+        __syncthreads();
+        if (tid == kSelThreads - 1) *carry_out = max(s_max[tid], carry_in);
+    }
 }
 
 }  // namespace egl
@@ -126,6 +135,19 @@ extern "C" int egl_select_homography(const int32_t* status, int F, int interval,
     if (F == 0) return 0;
     select_kernel<<<1, kSelThreads, 0, (cudaStream_t)stream>>>(status, F, interval, carry_in, h_index, attempted);
     return cuda_status(cudaGetLastError(), "egl_select_homography: kernel launch");
+}
+
+extern "C" int egl_select_homography_chunk(const int32_t* status, int F, int interval, int first_frame, const int32_t* carry_in,
+                                           int32_t* carry_out, int32_t* h_index, uint8_t* attempted, void* stream) {
+    if (F == 0) return 0;
+    EGL_REQUIRE(status && h_index && attempted, EGL_ERR_NULL, "egl_select_homography_chunk: null pointer");
+    EGL_REQUIRE(F >= 0 && interval >= 1 && first_frame >= 0, EGL_ERR_SHAPE, "egl_select_homography_chunk: bad arguments");
+    EGL_REQUIRE(first_frame % interval == 0, EGL_ERR_SHAPE,
+                "egl_select_homography_chunk: a chunk must start on a multiple of the homography interval (first_frame=%d interval=%d)",
+                first_frame, interval);
+    select_kernel<<<1, kSelThreads, 0, (cudaStream_t)stream>>>(status, F, interval, -1, h_index, attempted, first_frame, carry_in,
+                                                               carry_out);
+    return cuda_status(cudaGetLastError(), "egl_select_homography_chunk: kernel launch");
 }
 
 extern "C" int egl_project_points(const double* H, const int32_t* h_index, const float* pts, const int32_t* npts, int F, int P,

@@ -249,6 +249,22 @@ class GeometryEngine:
                                                 _stream()), "egl_select_homography")
         return h_index, attempted
 
+    def select_chunk(self, status: torch.Tensor, interval: int, first_frame: int, carry: torch.Tensor,
+                     h_index: torch.Tensor | None = None, attempted: torch.Tensor | None = None):
+        """The cadence for one chunk of a clip: ``status`` belongs to clip frames first_frame.. (first_frame a multiple
+        of interval); ``carry`` is a 1-element int32 device tensor holding the clip row of H valid before the chunk
+        (-1 = none), updated in place.  h_index holds clip rows."""
+        F = status.numel()
+        _require(carry.dtype == torch.int32 and carry.numel() == 1 and carry.is_cuda, "select_chunk: carry must be a 1-element int32 CUDA tensor")
+        if h_index is None:
+            h_index = torch.empty(F, dtype=torch.int32, device=status.device)
+        if attempted is None:
+            attempted = torch.empty(F, dtype=torch.uint8, device=status.device)
+        with torch.cuda.device(status.device):
+            N.check(N.lib.egl_select_homography_chunk(_ptr(status), F, int(interval), int(first_frame), _ptr(carry), _ptr(carry),
+                                                      _ptr(h_index), _ptr(attempted), _stream()), "egl_select_homography_chunk")
+        return h_index, attempted
+
     # -- K4 ---------------------------------------------------------------------------------
     def alloc_projection(self, F: int, P: int) -> Projection:
         dev = self.device

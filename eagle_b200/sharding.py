@@ -20,11 +20,18 @@ def frame_range(n_frames: int, rank: int, world: int) -> tuple[int, int]:
     return n_frames * rank // world, n_frames * (rank + 1) // world
 
 
+def _row_bytes(t: torch.Tensor) -> int:
+    per = t.element_size()
+    for d in t.shape[1:]:
+        per *= int(d)
+    return per
+
+
 def pack_results(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
     """Concatenate per-frame result arrays (F, ...) of any dtypes into one (F, bytes) uint8 record
     tensor so that a single collective moves everything."""
     F = tensors[0].shape[0]
-    cols = [t.contiguous().view(F, -1).view(torch.uint8) for t in tensors]
+    cols = [t.contiguous().view(torch.uint8).view(F, _row_bytes(t)) for t in tensors]
     return torch.cat(cols, dim=1)
 
 
@@ -36,9 +43,19 @@ def unpack_results(records: torch.Tensor, like: Sequence[torch.Tensor]) -> list[
         per = t.element_size()
         for d in t.shape[1:]:
             per *= int(d)
-        out.append(records[:, o:o + per].contiguous().view(t.dtype).view((F,) + tuple(t.shape[1:])))
+        # clone(contiguous_format), not contiguous(): a one-row slice counts as contiguous while keeping the record stride
+        col = records[:, o:o + per].clone(memory_format=torch.contiguous_format)
+        out.append(col.view(t.dtype).view((F,) + tuple(t.shape[1:])))
         o += per
     return out
+
+
+def download(tensors: Sequence[torch.Tensor]) -> list:
+    """Device tensors (F, ...) -> numpy arrays through ONE packed device-to-host copy (instead of one per tensor)."""
+    if tensors[0].shape[0] == 0:
+        return [t.cpu().numpy() for t in tensors]
+    rec = pack_results(tensors).cpu()
+    return [t.numpy() for t in unpack_results(rec, tensors)]
 
 
 def gather_to_rank0(records: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor | None:
@@ -64,40 +81,80 @@ def gather_to_rank0(records: torch.Tensor, counts: Sequence[int], group=None) ->
     return None
 
 
-def run_sharded(path, heatmaps_local: torch.Tensor, objects_local: Sequence[dict], width: int, height: int, fps: int,
-                homography_interval: int = 1, group=None):
+class FewLandmarksError(RuntimeError):
+    """A frame decoded fewer than four landmarks: the reference rescues it by optical flow from its neighbours
+    (coordinate_model.py:287-311), which the per-frame sharded path cannot do.  Use run_sharded_propagated with
+    keypoint_interval=1 (or CoordinateModel.get_coordinates, which reroutes by itself)."""
+
+
+def run_sharded(path, heatmaps_local, objects_local: Sequence[dict], width: int, height: int, fps: int,
+                homography_interval: int = 1, group=None, *, objects_on_rank0: Sequence[dict] | None = None, assemble: bool = True,
+                frames_local=None):
     """The geometry path for one clip sharded by contiguous frame range over the ranks of ``group``.
 
-    Every rank calls this with ITS frames' heatmaps (F_r,57,h,w on its GPU) and detector dicts, in rank
-    order of the clip.  The bandwidth- and compute-heavy kernels (decode, synthesis, RANSAC + refit) run
-    on each rank's range; the small per-frame results are gathered to rank 0, which evaluates the
-    homography cadence over the WHOLE clip (it carries state across shard boundaries exactly as the
-    reference's sequential loop does), projects and assembles the reference-format dict.  Returns that
-    dict on rank 0 and None elsewhere.  Works with NCCL (GPU tensors) and with gloo (records staged
-    through the host, used by the single-GPU tests)."""
-    import numpy as np
+    Every rank calls this with ITS frames' heatmaps and detector dicts, in rank order of the clip.  ``heatmaps_local``
+    is one (F_r,57,h,w) CUDA tensor or an iterable of such tensors (consecutive chunks of the rank's range: a full
+    match does not fit in HBM at once, so the caller streams chunks through fixed buffers); ``frames_local``, if given,
+    is the matching tensor / iterable of (n,H,W,3) uint8 frames, which then go through K1 as well (the network input
+    is produced and dropped: the network is not part of this path).  The bandwidth- and compute-heavy kernels (decode,
+    synthesis, RANSAC + refit) run on each rank's range; the small per-frame results are gathered to rank 0, which
+    evaluates the homography cadence over the WHOLE clip (it carries state across shard boundaries exactly as the
+    reference's sequential loop does), projects and assembles the reference-format dict.  Returns that dict on rank 0
+    and None elsewhere (``assemble=False``: the per-frame arrays instead of the dict).  ``objects_on_rank0``: the whole
+    clip's detections when rank 0 already holds them (skips the pickled gather of the dicts).
 
+    Precondition (checked, FewLandmarksError on every rank): every frame decodes at least four landmarks.
+    Works with NCCL (GPU tensors) and with gloo (records staged through the host, used by the single-GPU tests)."""
+    from .boxes import max_objects, objects_to_arrays
     from .coordinate_model import assemble_frames
-    from .boxes import objects_to_arrays
+    from .engine import FitResult, KeypointSet
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     e = path.engine
-    F_r = heatmaps_local.shape[0]
-    # per-rank frame counts and the clip-wide maximum object count (host-side, tiny)
-    local_meta = (F_r, max([1] + [sum(len(v) for v in o.values()) for o in objects_local]))
+    objects_local = objects_local if type(objects_local) is list else list(objects_local)
+    chunks = [heatmaps_local] if torch.is_tensor(heatmaps_local) else heatmaps_local
+    fchunks = None if frames_local is None else ([frames_local] if torch.is_tensor(frames_local) else frames_local)
+    kps, fits = [], []
+    x = None
+    fit_iter = iter(fchunks) if fchunks is not None else None
+    for hm in chunks:
+        if fit_iter is not None:
+            fr = next(fit_iter)
+            if x is None or x.shape[0] < fr.shape[0]:
+                x = torch.empty((fr.shape[0], 3, 540, 960), dtype=torch.float32, device=e.device)
+            e.preprocess(fr, out=x[:fr.shape[0]])
+        kp = e.decode(hm, width, height, path.keypoint_conf)
+        if path.synthesis:
+            e.synthesize(kp)
+        kps.append(kp)
+        fits.append(e.fit(kp, mode=path.fit_mode, K=path.max_iters, thr=path.thr))
+    cat = lambda xs: torch.cat(xs) if len(xs) > 1 else xs[0]
+    kp = KeypointSet(None, None, cat([k.xy for k in kps]), cat([k.order for k in kps]), cat([k.count for k in kps]))
+    fit = FitResult(cat([f.H for f in fits]), cat([f.used_mask for f in fits]), cat([f.inlier_mask for f in fits]),
+                    cat([f.status for f in fits]), None)
+    F_r = kp.xy.shape[0]
+    if len(objects_local) != F_r:
+        raise ValueError(f"rank {rank}: {F_r} frames of heatmaps but {len(objects_local)} detection dicts")
+    # the foot points are packed while the kernels above still run (nothing has synchronised yet)
+    P_local = max(1, max_objects(objects_local))
+    foot_h, cnt_h = objects_to_arrays(objects_local, P_local)
+    # per-rank frame counts, the clip-wide maximum object count and the < 4 landmarks flag (host-side, tiny)
+    few = bool((kp.count[:, 1] < 4).any().item()) if F_r else False
+    local_meta = (F_r, P_local, few)
     metas = [None] * world
     if world > 1:
         dist.all_gather_object(metas, local_meta, group=group)
     else:
         metas = [local_meta]
+    if any(m[2] for m in metas):
+        raise FewLandmarksError("a frame of the clip decoded fewer than four landmarks; the per-frame sharded path does not apply "
+                                f"(ranks affected: {[r for r, m in enumerate(metas) if m[2]]})")
     counts = [m[0] for m in metas]
     P = max(m[1] for m in metas)
-    kp = e.decode(heatmaps_local, width, height, path.keypoint_conf)
-    if path.synthesis:
-        e.synthesize(kp)
-    fit = e.fit(kp, mode=path.fit_mode, K=path.max_iters, thr=path.thr)
-    foot_h, cnt_h = objects_to_arrays(list(objects_local), P)
+    if P > P_local:   # another rank saw a busier frame: same record width everywhere
+        import numpy as np
+        foot_h = np.concatenate([foot_h, np.zeros((F_r, P - P_local, 2), np.float32)], axis=1)
     foot = torch.from_numpy(foot_h).to(e.device); cnt = torch.from_numpy(cnt_h).to(e.device)
     like = [kp.xy, kp.order, kp.count, fit.H, fit.used_mask, fit.inlier_mask, fit.status, foot, cnt]
     rec = pack_results(like)
@@ -105,21 +162,26 @@ def run_sharded(path, heatmaps_local: torch.Tensor, objects_local: Sequence[dict
     if backend == "gloo":
         rec = rec.cpu()
     all_rec = gather_to_rank0(rec, counts, group) if world > 1 else rec
-    objs_all = [None] * world
-    if world > 1:
-        dist.gather_object(list(objects_local), objs_all if rank == 0 else None, dst=0, group=group)
-    else:
-        objs_all = [list(objects_local)]
+    objs_all = None
+    if assemble and objects_on_rank0 is None:
+        objs_all = [None] * world
+        if world > 1:
+            dist.gather_object(objects_local, objs_all if rank == 0 else None, dst=0, group=group)
+        else:
+            objs_all = [objects_local]
     if rank != 0:
         return None
     all_rec = all_rec.to(e.device)
     xy, order, count, H, used, inl, status, foot_a, cnt_a = unpack_results(all_rec, like)
     h_index, attempted = e.select(status.contiguous(), homography_interval)
     proj = e.project(H.contiguous(), foot_a.contiguous(), cnt_a.contiguous(), width, height, h_index=h_index)
-    objects_per_frame = [o for part in objs_all for o in part]
-    c = lambda t: t.cpu().numpy()
-    return assemble_frames(objects_per_frame, fps, 0, c(xy), c(order), c(count), c(used), c(inl), c(status), c(attempted),
-                           c(h_index), c(proj.coords_i), c(proj.in_bounds), c(proj.bounds))
+    arrays = download([xy, order, count, used, inl, status, attempted, h_index, proj.coords_i, proj.in_bounds, proj.bounds])
+    if not assemble:
+        return arrays
+    objects_per_frame = list(objects_on_rank0) if objects_on_rank0 is not None else [o for part in objs_all for o in part]
+    if len(objects_per_frame) != sum(counts):
+        raise ValueError(f"{sum(counts)} frames in the clip but {len(objects_per_frame)} detection dicts on rank 0")
+    return assemble_frames(objects_per_frame, fps, 0, *arrays)
 
 
 def chain_range(n_frames: int, keypoint_interval: int, rank: int, world: int) -> tuple[int, int]:
@@ -201,8 +263,8 @@ def run_sharded_propagated(engine, frames_local: torch.Tensor, head_heatmaps_loc
                                "status": status.contiguous(), "inlier_mask": inl}])
     proj = engine.project(whole["H"], foot_a.contiguous(), cnt_a.contiguous(), width, height, h_index=whole["h_index"])
     objects_per_frame = [o for part in objs_all for o in part]
-    c = lambda t: t.cpu().numpy()
-    res = assemble_frames(objects_per_frame, fps, 0, c(xy), c(order), c(count), None, None, None, None, c(whole["h_index"]),
-                          c(proj.coords_i), c(proj.in_bounds), c(proj.bounds), kp_src=c(src))
+    xy_h, order_h, count_h, hi_h, ci_h, ib_h, bd_h, src_h = download([xy, order, count, whole["h_index"], proj.coords_i, proj.in_bounds,
+                                                                      proj.bounds, src])
+    res = assemble_frames(objects_per_frame, fps, 0, xy_h, order_h, count_h, None, None, None, None, hi_h, ci_h, ib_h, bd_h, kp_src=src_h)
     run_sharded_propagated.last_stats = [m[2] for m in metas]
     return res

@@ -156,6 +156,18 @@ int egl_select_homography(const int32_t *status, int F, int interval, int carry_
                           uint8_t *attempted, void *stream);
 
 /*
+ * The same cadence, one chunk of a clip at a time (so that a long clip streams through fixed buffers and every
+ * chunk can be projected and handed to the host while the next is still being decoded).
+ *   status      [F] int32: the chunk's fit statuses; the chunk starts at clip frame first_frame, which must be a
+ *               multiple of interval (cadence segments then never straddle a chunk boundary)
+ *   carry_in    device pointer to the CLIP row of H valid before this chunk (-1 = none), or NULL = none
+ *   carry_out   device pointer that receives the row valid after this chunk (may alias carry_in), or NULL
+ *   h_index     [F] int32 out: CLIP row of H for every frame of the chunk (H is indexed by clip frame)
+ */
+int egl_select_homography_chunk(const int32_t *status, int F, int interval, int first_frame, const int32_t *carry_in,
+                                int32_t *carry_out, int32_t *h_index, uint8_t *attempted, void *stream);
+
+/*
  * K4  projection of all foot points of every frame + visible-pitch boundaries.
  * Replaces the per-object cv2.perspectiveTransform loop (coordinate_model.py:369-392), the corner
  * projection and find_x_at_y (:396-414, :32-44).
