@@ -274,7 +274,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     F = args.frames
     lo, hi = frame_range(F * world, rank, world)
     assert hi - lo == F
@@ -496,14 +497,15 @@ def main():
 
         match_once(False)
         barrier()
-        m_steps = 0
         tm = time.perf_counter()
-        while True:
+        match_once(False)
+        barrier()
+        # run_sharded holds collectives, so every rank must go round the same number of times: the count comes from
+        # one agreed estimate, not from each rank's own clock
+        m_steps = max(2, int(MIN_TIMED_S / max_over_ranks(time.perf_counter() - tm)) + 1)
+        tm = time.perf_counter()
+        for _ in range(m_steps):
             match_once(False)
-            torch.cuda.synchronize()
-            m_steps += 1
-            if time.perf_counter() - tm >= MIN_TIMED_S:
-                break
         barrier()
         m_dt = max_over_ranks((time.perf_counter() - tm) / m_steps)
         barrier()

@@ -31,6 +31,7 @@ _vp, _i, _d, _sz, _u64 = C.c_void_p, C.c_int, C.c_double, C.c_size_t, C.c_uint64
 lib.egl_version.restype = _i
 lib.egl_last_error.restype = C.c_char_p
 lib.egl_sm_count.restype = _i
+lib.egl_build_flags.restype = _i
 lib.egl_preprocess_u8.argtypes = [_vp, _i, _i, _i, _sz, _sz, _vp, _vp]
 lib.egl_decode_heatmaps.argtypes = [_vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]
 lib.egl_decode_logits.argtypes = [_vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]
@@ -57,7 +58,7 @@ for _name in ("egl_preprocess_u8", "egl_decode_heatmaps", "egl_decode_logits", "
               "egl_select_homography", "egl_select_homography_chunk", "egl_project_points"):
     getattr(lib, _name).restype = _i
 
-EXPORTS = ("egl_version", "egl_last_error", "egl_sm_count", "egl_preprocess_u8", "egl_decode_heatmaps", "egl_decode_logits",
+EXPORTS = ("egl_version", "egl_last_error", "egl_sm_count", "egl_build_flags", "egl_preprocess_u8", "egl_decode_heatmaps", "egl_decode_logits",
            "egl_synthesize_keypoints", "egl_fit_homography", "egl_select_homography", "egl_project_points", "egl_pyramid_bytes",
            "egl_gray_pyramid", "egl_track_keypoints", "egl_filter_flow", "egl_merge_keypoints", "egl_calibrate_keypoints",
            "egl_fit_homography_masked", "egl_commit_fit", "egl_refine_keypoints", "egl_fit_homography_subpixel",

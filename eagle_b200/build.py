@@ -60,6 +60,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     objs = []
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
     common = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + ARCH
+    if os.environ.get("EGL_BENCH_VARIANTS") == "1":   # A/B kernels + EGL_*_VARIANT switches (tools/sweep.py, tools/sanitize.sh)
+        common += ["-DEGL_BENCH_VARIANTS"]
     if verbose:
         common += ["-Xptxas", "-v"]
     procs = []

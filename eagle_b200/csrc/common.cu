@@ -26,6 +26,14 @@ extern "C" int egl_version(void) { return EGL_ABI_VERSION; }
 
 extern "C" const char* egl_last_error(void) { return egl::g_err; }
 
+extern "C" int egl_build_flags(void) {
+#ifdef EGL_BENCH_VARIANTS
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 extern "C" int egl_sm_count(void) {
     static thread_local int cached_dev = -1, cached = 0;
     int dev = 0;

@@ -14,7 +14,7 @@
 //   argmax_kernel<6,512,1>   one CTA per SM, 6 x 32 KB ring                           5.07 TB/s
 // Staging through shared memory buys nothing when nothing is reused -- it adds a shared-memory round
 // trip and a hand-off per chunk -- so the register-streaming kernel is the default and the TMA rings
-// stay selectable (EGL_DECODE_VARIANT) for measurement.  All layouts share the scan: per float4 a
+// stay selectable (EGL_DECODE_VARIANT) for measurement in builds with -DEGL_BENCH_VARIANTS; the shipped library holds one kernel per job.  All layouts share the scan: per float4 a
 // 4-way max, the first lane equal to it and a predicated update (strict '>' keeps the earliest index,
 // i.e. np.argmax's first-maximum rule); NaNs are routed to an exact cold path.
 //   * postprocess_kernel -- one warp per frame over the 57 (index, score) pairs: confidence
@@ -45,6 +45,7 @@ __device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
     return v > bv || (v == bv && i < bi);
 }
 
+#ifdef EGL_BENCH_VARIANTS  // shared-memory staging layouts, measured and kept for A/B runs (-DEGL_BENCH_VARIANTS)
 template <int kStages, int kDecThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kDecThreads, kMinBlocks) argmax_kernel(DecodeArgs a) {
     constexpr int kDecWarps = kDecThreads / 32;
@@ -239,6 +240,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) argmax_warp_ring_kernel(Decode
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
     }
 }
+
+#endif  // EGL_BENCH_VARIANTS
 
 // Alternative without the TMA ring (kept for A/B measurements, EGL_DECODE_VARIANT=ldg): one CTA per
 // map, 256 threads, 8 independent 128-bit streaming loads in flight per thread.
@@ -522,10 +525,12 @@ static int decode_impl(const float* hm, int F, int hm_h, int hm_w, int img_w, in
     a.kp_score = kp_score;
     int sms = egl_sm_count();
     if (sms <= 0) return -1;
+    int rc = 0;
+    bool launched = false;
+#ifdef EGL_BENCH_VARIANTS
     // Launch variants (EGL_DECODE_VARIANT, measurement switch; default 4 = register-streaming kernel).
     static const char* variant_env = getenv("EGL_DECODE_VARIANT");
     const int variant = (variant_env && !from_logits) ? atoi(variant_env) : 4;  // the ring variants take heatmaps only
-    int rc = 0;
     auto launch_ring = [&](auto kernel, int stages, int threads, int ctas_per_sm, int chunk_div) -> int {
         DecodeArgs b = a;
         b.chunks_per_map = (a.map_f4 + kChunkF4Max / chunk_div - 1) / (kChunkF4Max / chunk_div);
@@ -553,6 +558,7 @@ static int decode_impl(const float* hm, int F, int hm_h, int hm_w, int img_w, in
         kernel<<<(unsigned)grid, warps * 32, smem, s>>>(b);
         return 0;
     };
+    launched = true;
     switch (variant) {
         case 1: rc = launch_ring(argmax_kernel<12, 512, 1>, 12, 512, 1, 2); break;   // 12 x 16 KB
         case 2: rc = launch_ring(argmax_kernel<3, 256, 2>, 3, 256, 2, 1); break;    // 2 CTAs/SM, 3 x 32 KB each
@@ -565,12 +571,14 @@ static int decode_impl(const float* hm, int F, int hm_h, int hm_w, int img_w, in
         case 10: rc = launch_ring(argmax_kernel<2, 256, 3>, 2, 256, 3, 1); break;         // 3 CTAs/SM, 2 x 32 KB each
         case 11: rc = launch_ring(argmax_kernel<3, 128, 4>, 3, 128, 4, 2); break;         // 4 CTAs/SM, 3 x 16 KB each
         case 0: rc = launch_ring(argmax_kernel<6, 512, 1>, 6, 512, 1, 1); break;    // 6 x 32 KB, 1 CTA/SM
-        default:  // register streaming
-            if (from_logits) argmax_logits_kernel<<<(unsigned)a.total_maps, 256, 0, s>>>(a);
-            else argmax_ldg_kernel<<<(unsigned)a.total_maps, 256, 0, s>>>(a);
-            break;
+        default: launched = false; break;
     }
     if (rc) return rc;
+#endif
+    if (!launched) {  // register streaming: one CTA per (frame, channel) map
+        if (from_logits) argmax_logits_kernel<<<(unsigned)a.total_maps, 256, 0, s>>>(a);
+        else argmax_ldg_kernel<<<(unsigned)a.total_maps, 256, 0, s>>>(a);
+    }
     rc = cuda_status(cudaGetLastError(), "egl_decode_heatmaps: argmax kernel launch");
     if (rc) return rc;
     postprocess_kernel<<<(F + kPostWarps - 1) / kPostWarps, kPostWarps * 32, 0, s>>>(kp_flat, kp_score, F, hm_h, hm_w, img_w, img_h, keypoint_conf, kp_xy,

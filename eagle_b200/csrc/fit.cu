@@ -1005,10 +1005,13 @@ static int fit_impl(const char* who, const int32_t* kp_xy, const uint8_t* kp_ord
     // Same algorithm, two parallelisations: one warp per frame has the lower latency (0.28 ms for a
     // 2250-frame clip, a single wave), one thread per frame -- the host-checkable scalar code of
     // geometry_core.cuh -- the higher throughput once there are more frames than resident warps
-    // (measured cross-over ~10-12 k frames: 50 k frames 2.2 ms vs 3.9 ms).  EGL_REFIT_VARIANT = 1 / 2
-    // forces the thread / warp kernel (used by the cross-check test).
+    // (measured cross-over ~10-12 k frames: 50 k frames 2.2 ms vs 3.9 ms).  In builds with
+    // -DEGL_BENCH_VARIANTS, EGL_REFIT_VARIANT = 1 / 2 forces the thread / warp kernel.
+    int refit_variant = 0;
+#ifdef EGL_BENCH_VARIANTS
     static const char* refit_env = getenv("EGL_REFIT_VARIANT");
-    const int refit_variant = refit_env ? atoi(refit_env) : 0;
+    refit_variant = refit_env ? atoi(refit_env) : 0;
+#endif
     if (refit_variant == 1 || (refit_variant == 0 && F > 12288))
         refit_kernel<<<(F + kRefitThreads - 1) / kRefitThreads, kRefitThreads, 0, s>>>(a);
     else

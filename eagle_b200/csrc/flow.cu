@@ -501,6 +501,7 @@ __global__ void __launch_bounds__(kTrackWarps * 32) track_kernel(TrackArgs a) {
 // The same tracker as one thread per point: lk_track_point of flow_core.cuh, the scalar statement that the
 // CPU suite compiles for the host and holds against live cv2.  EGL_TRACK_VARIANT=1 selects it (cross-check
 // of the warp kernel above; ~20x slower).
+#ifdef EGL_BENCH_VARIANTS
 __global__ void __launch_bounds__(64) track_thread_kernel(TrackArgs a) {
     const int p = blockIdx.x, j = threadIdx.x;
     if (j >= min(a.kp_count[2 * p], kMaxPts)) return;
@@ -514,6 +515,7 @@ __global__ void __launch_bounds__(64) track_thread_kernel(TrackArgs a) {
     a.out_pts[((size_t)p * kMaxPts + ch) * 2 + 1] = out[1];
     a.out_status[(size_t)p * kMaxPts + ch] = (uint8_t)status;
 }
+#endif  // EGL_BENCH_VARIANTS
 
 // ------------------------------------------------------------------------------------------------
 // the reference's filters on the tracked points (coordinate_model.py:438-478): one warp per frame pair
@@ -737,9 +739,12 @@ extern "C" int egl_gray_pyramid(const uint8_t* frames, int F, int H, int W, size
                 "egl_gray_pyramid: bad shape (F=%d H=%d W=%d max_level=%d)", F, H, W, max_level);
     const PyrLayout L = pyramid_layout(H, W, max_level);
     cudaStream_t s = (cudaStream_t)stream;
+    bool general_only = false, unfused = false;
+#ifdef EGL_BENCH_VARIANTS
     static const char* env = getenv("EGL_PYRAMID_VARIANT");  // measurement switch: 1 = general per-byte kernels only, 2 = unfused fast kernels
-    const bool general_only = env && atoi(env) == 1;
-    const bool unfused = env && atoi(env) == 2;
+    general_only = env && atoi(env) == 1;
+    unfused = env && atoi(env) == 2;
+#endif
     const bool fast_gray = !general_only && W % 16 == 0 && row_stride % 16 == 0 && frame_stride % 16 == 0 &&
                            ((uintptr_t)frames & 15) == 0 && ((uintptr_t)pyr & 15) == 0;
     // One pass over all frames per level: splitting the clip into L2-sized groups (so that pyrDown would find
@@ -790,11 +795,14 @@ extern "C" int egl_track_keypoints(const uint8_t* pyr, int H, int W, int max_lev
     a.eps2 = e * e;
     a.min_eig = 1e-4;
     a.out_pts = new_pts; a.out_status = status;
+#ifdef EGL_BENCH_VARIANTS
     static const char* env = getenv("EGL_TRACK_VARIANT");  // 1 = one thread per point (the host-checkable scalar code)
-    if (env && atoi(env) == 1)
+    if (env && atoi(env) == 1) {
         track_thread_kernel<<<n, 64, 0, (cudaStream_t)stream>>>(a);
-    else
-        track_kernel<<<dim3(kMaxPts / kTrackWarps, n), kTrackWarps * 32, 0, (cudaStream_t)stream>>>(a);
+        return cuda_status(cudaGetLastError(), "egl_track_keypoints: kernel launch");
+    }
+#endif
+    track_kernel<<<dim3(kMaxPts / kTrackWarps, n), kTrackWarps * 32, 0, (cudaStream_t)stream>>>(a);
     return cuda_status(cudaGetLastError(), "egl_track_keypoints: kernel launch");
 }
 

@@ -177,15 +177,20 @@ extern "C" int egl_preprocess_u8(const uint8_t* frames, int F, int H, int W, siz
     const double scale_x = 1. / ((double)kOutW / (double)W);
     const double scale_y = 1. / ((double)kOutH / (double)H);
     // even integer multiple of the output size -> rounded mean of four (see kMean4)
+    bool mean4 = (W % kOutW == 0) && (H % kOutH == 0) && (W / kOutW == H / kOutH) && ((W / kOutW) % 2 == 0);
+#ifdef EGL_BENCH_VARIANTS
     static const char* mean4_env = getenv("EGL_PREPROCESS_MEAN4");  // measurement switch: 0 forces the general recipe
-    const bool mean4 = (W % kOutW == 0) && (H % kOutH == 0) && (W / kOutW == H / kOutH) && ((W / kOutW) % 2 == 0) &&
-                       !(mean4_env && atoi(mean4_env) == 0);
+    if (mean4_env && atoi(mean4_env) == 0) mean4 = false;
+#endif
     const double arg_x = mean4 ? (double)(W / kOutW / 2) : scale_x, arg_y = mean4 ? (double)(H / kOutH / 2) : scale_y;
     // output rows per CTA: 4 unless the row slots of a CTA would exceed ~100 KB of shared memory
-    static const char* rows_env = getenv("EGL_PREPROCESS_ROWS");
-    int R = rows_env ? atoi(rows_env) : 4;
+    int R = 4;
+#ifdef EGL_BENCH_VARIANTS
+    static const char* rows_env = getenv("EGL_PREPROCESS_ROWS");  // measurement switch: rows per CTA (1, 2, 3, 4, 6)
+    if (rows_env) R = atoi(rows_env);
     if (R != 1 && R != 2 && R != 3 && R != 4 && R != 6) R = 4;
     if (mean4 && R == 3) R = 2;
+#endif
     while (R > 1 && (size_t)2 * R * row_pad > 100 * 1024) R = (R == 6) ? 4 : (R == 3 ? 2 : R / 2);
     const size_t smem = (size_t)2 * R * row_pad;
     EGL_REQUIRE(smem <= 200 * 1024, EGL_ERR_SHAPE, "egl_preprocess_u8: frame too wide (%d px)", W);
@@ -205,15 +210,19 @@ extern "C" int egl_preprocess_u8(const uint8_t* frames, int F, int H, int W, siz
         switch (R) {
             case 1: rc = launch(preprocess_kernel<1, true>, 1); break;
             case 2: rc = launch(preprocess_kernel<2, true>, 2); break;
+#ifdef EGL_BENCH_VARIANTS
             case 6: rc = launch(preprocess_kernel<6, true>, 6); break;
+#endif
             default: rc = launch(preprocess_kernel<4, true>, 4); break;
         }
     } else {
         switch (R) {
             case 1: rc = launch(preprocess_kernel<1, false>, 1); break;
             case 2: rc = launch(preprocess_kernel<2, false>, 2); break;
+#ifdef EGL_BENCH_VARIANTS
             case 3: rc = launch(preprocess_kernel<3, false>, 3); break;
             case 6: rc = launch(preprocess_kernel<6, false>, 6); break;
+#endif
             default: rc = launch(preprocess_kernel<4, false>, 4); break;
         }
     }

@@ -13,6 +13,7 @@ namespace egl {
 
 #include "line_families.inc"
 
+#ifdef EGL_BENCH_VARIANTS
 __global__ void __launch_bounds__(64) synthesize_kernel(int32_t* kp_xy, uint8_t* kp_order, int32_t* kp_count, int F,
                                                         int max_new) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -34,6 +35,7 @@ __global__ void __launch_bounds__(64) synthesize_kernel(int32_t* kp_xy, uint8_t*
     }
     kp_count[2 * f] = total < EGL_ORDER_STRIDE ? total : EGL_ORDER_STRIDE;
 }
+#endif  // EGL_BENCH_VARIANTS
 
 // Warp-per-frame version (the product kernel): lanes are line families for the fits (19 world-y
 // families, then 19 world-x families) and x-families for the crossings of each y-family; a ballot
@@ -98,11 +100,14 @@ extern "C" int egl_synthesize_keypoints(int32_t* kp_xy, uint8_t* kp_order, int32
     EGL_REQUIRE(kp_xy && kp_order && kp_count, EGL_ERR_NULL, "egl_synthesize_keypoints: null pointer");
     EGL_REQUIRE(F >= 0 && max_new >= 0, EGL_ERR_SHAPE, "egl_synthesize_keypoints: bad arguments");
     if (F == 0 || max_new == 0) return 0;
+#ifdef EGL_BENCH_VARIANTS
     static const char* env = getenv("EGL_SYNTH_VARIANT");  // measurement switch: 1 = one thread per frame (host-checkable code)
-    if (env && atoi(env) == 1)
+    if (env && atoi(env) == 1) {
         synthesize_kernel<<<(F + 63) / 64, 64, 0, (cudaStream_t)stream>>>(kp_xy, kp_order, kp_count, F, max_new);
-    else
-        synthesize_warp_kernel<<<(F + kSynWarps - 1) / kSynWarps, kSynWarps * 32, 0, (cudaStream_t)stream>>>(kp_xy, kp_order, kp_count,
+        return cuda_status(cudaGetLastError(), "egl_synthesize_keypoints: kernel launch");
+    }
+#endif
+    synthesize_warp_kernel<<<(F + kSynWarps - 1) / kSynWarps, kSynWarps * 32, 0, (cudaStream_t)stream>>>(kp_xy, kp_order, kp_count,
                                                                                                              F, max_new);
     return cuda_status(cudaGetLastError(), "egl_synthesize_keypoints: kernel launch");
 }

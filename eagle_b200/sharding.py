@@ -31,6 +31,8 @@ def pack_results(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
     """Concatenate per-frame result arrays (F, ...) of any dtypes into one (F, bytes) uint8 record
     tensor so that a single collective moves everything."""
     F = tensors[0].shape[0]
+    if F == 0:   # an idle rank still takes part in the gather, with zero rows of the right width
+        return torch.empty((0, sum(_row_bytes(t) for t in tensors)), dtype=torch.uint8, device=tensors[0].device)
     cols = [t.contiguous().view(torch.uint8).view(F, _row_bytes(t)) for t in tensors]
     return torch.cat(cols, dim=1)
 
@@ -186,9 +188,15 @@ def run_sharded(path, heatmaps_local, objects_local: Sequence[dict], width: int,
 
 def chain_range(n_frames: int, keypoint_interval: int, rank: int, world: int) -> tuple[int, int]:
     """Frame range [lo, hi) of ``rank`` when the clip is cut between chains (a chain = one network frame and the
-    frames propagated from it): boundaries are multiples of the keypoint interval."""
+    frames propagated from it): boundaries are multiples of the keypoint interval.  The chains are dealt out so
+    that the LOW ranks are never empty (a clip of fewer chains than ranks leaves the high ranks idle): rank 0
+    assembles the result and every non-empty rank's predecessor holds the frame before its first."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
     nc = (n_frames + keypoint_interval - 1) // keypoint_interval
-    c0, c1 = frame_range(nc, rank, world)
+    base, rem = divmod(nc, world)
+    c0 = rank * base + min(rank, rem)
+    c1 = c0 + base + (1 if rank < rem else 0)
     return min(c0 * keypoint_interval, n_frames), min(c1 * keypoint_interval, n_frames)
 
 
@@ -213,7 +221,31 @@ def run_sharded_propagated(engine, frames_local: torch.Tensor, head_heatmaps_loc
     dev = engine.device
     height, width = frames_local.shape[1], frames_local.shape[2]
     prop = PropagatedPath(engine, keypoint_conf)
-    prop.start(frames_local, head_heatmaps_local, detect, keypoint_interval, homography_interval, calibration, first_frame=first_frame)
+    # a rank past the end of a short clip (chain_range leaves the high ranks empty) only passes the boundary state on
+    n_local = frames_local.shape[0] - (1 if first_frame > 0 else 0) if frames_local is not None else 0
+    idle = n_local <= 0
+    if idle and rank == 0:
+        raise ValueError("run_sharded_propagated: rank 0 holds no frames (empty clip)")
+    if not idle:
+        from .propagation import FirstPieceTooShort
+        try:
+            # rank 0's forward scan for the first usable frame (:290-297) may not leave its own range: if it would have
+            # to, the clip cannot be sharded this way and every rank is told so (instead of a silently different dict)
+            prop.start(frames_local, head_heatmaps_local, detect, keypoint_interval, homography_interval, calibration,
+                       first_frame=first_frame, clip_continues=rank < world - 1)
+            short = False
+        except FirstPieceTooShort:
+            short = True
+    else:
+        short = False
+    if world > 1:
+        flags = [None] * world
+        dist.all_gather_object(flags, short, group=group)
+        short = any(flags)
+    if short:
+        raise FirstPieceTooShort("frame 0 has fewer than four landmarks and no frame of rank 0's range has four: the reference's "
+                                 "forward scan (coordinate_model.py:290-297) would continue into the next rank's frames; "
+                                 "run the clip on fewer ranks or through CoordinateModel.get_coordinates")
 
     def carry_like():
         return [torch.zeros((1, 57, 2), dtype=torch.int32, device=dev), torch.zeros((1, 64), dtype=torch.uint8, device=dev),
@@ -227,13 +259,20 @@ def run_sharded_propagated(engine, frames_local: torch.Tensor, head_heatmaps_loc
         dist.recv(buf, src=rank - 1, group=group)
         xy, order, count, src, retry = unpack_results(buf.to(dev), carry_like())
         carry = {"retry": int(retry.item()), "kp": KeypointSet(None, None, xy, order, count, src)}
-    prop.repair(carry)
+    if not idle:
+        prop.repair(carry)
     if rank < world - 1:
-        co = prop.carry_out
+        co = carry if idle else prop.carry_out
         msg = pack_results([co["kp"].xy, co["kp"].order, co["kp"].count, co["kp"].src,
                             torch.tensor([[co["retry"]]], dtype=torch.int32, device=dev)])
         dist.send(msg.cpu() if backend == "gloo" else msg, dst=rank + 1, group=group)
-    out = prop.outputs()
+    if idle:
+        z = lambda *shape, dtype: torch.zeros(shape, dtype=dtype, device=dev)
+        out = {"xy": z(0, 57, 2, dtype=torch.int32), "order": z(0, 64, dtype=torch.uint8), "count": z(0, 2, dtype=torch.int32),
+               "src": z(0, 64, dtype=torch.uint8), "H": z(0, 9, dtype=torch.float64), "fit_ok": z(0, dtype=torch.uint8),
+               "status": z(0, dtype=torch.int32), "inlier_mask": z(0, dtype=torch.int64)}
+    else:
+        out = prop.outputs()
 
     F_r = out["xy"].shape[0]
     local_meta = (F_r, max([1] + [sum(len(v) for v in o.values()) for o in objects_local]), dict(prop.stats))

@@ -9,6 +9,8 @@ CPU baseline, the benchmark's pool of landmark layouts); bench.py adds per-frame
 """
 from __future__ import annotations
 
+from typing import Sequence
+
 import numpy as np
 
 from .pitch import NUM_LANDMARKS, OFF_PLANE, PITCH_LENGTH_M, PITCH_WIDTH_M, WORLD_XYZ
@@ -68,6 +70,16 @@ def render_heatmaps(px: np.ndarray, vis: np.ndarray, width: int, height: int, rn
         hm[ch] += g.astype(np.float32)
     np.clip(hm, 0.0, 1.0, out=hm)
     return hm
+
+
+def blank_heatmaps(heatmaps: np.ndarray, frames: Sequence[int]) -> None:
+    """Replace the given frames' heatmaps, in place, by four sharp peaks on the cross-bar channels (pitch.OFF_PLANE).
+    Such a frame still decodes four landmarks (so there is no optical-flow rescue, coordinate_model.py:287) but has no
+    on-plane correspondence at all: its homography fit fails (:350-352) and the reference retries on the next frame."""
+    for f in frames:
+        heatmaps[f] = 0.0
+        for j, c in enumerate(OFF_PLANE):
+            heatmaps[f, c, 20 + 10 * j, 30 + 15 * j] = 0.9
 
 
 def sample_objects(cam: np.ndarray, width: int, height: int, rng: np.random.Generator,

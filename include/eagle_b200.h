@@ -60,6 +60,10 @@ const char *egl_last_error(void);
 /* Number of SMs of the current device (grid sizing is a multiple of it). */
 int egl_sm_count(void);
 
+/* Bit 0: the library was built with -DEGL_BENCH_VARIANTS and holds the alternative kernels / EGL_*_VARIANT
+ * environment switches used for A/B measurements.  The shipped build returns 0: one kernel per job. */
+int egl_build_flags(void);
+
 /*
  * K1  uint8 BGR frames -> normalised float32 RGB planes for the keypoint network.
  * Replaces cv2.cvtColor(BGR2RGB) + A.Resize(540,960) + A.Normalize() + ToTensorV2 + .float()

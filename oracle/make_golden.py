@@ -33,12 +33,12 @@ def cadence_fixture(name, n_frames, width, height, seed, fps, num_homography, bl
     """Homography cadence (interval fps/num_homography, every frame a keypoint frame) incl. frames
     whose heatmaps are blanked so that the fit fails and the reference retries on the next frame."""
     clip = synthetic.make_clip(n_frames, width, height, seed=seed, with_frames=True, ghost_prob=0.05)
-    for b in blank:
-        clip["heatmaps"][b, 3:] = 0.0   # leaves channels 0-2 (two of them off-plane): < 4 usable landmarks
+    synthetic.blank_heatmaps(clip["heatmaps"], blank)
     res, rec = ref_harness.run_reference(clip["frames"], clip["heatmaps"], clip["objects"], fps=fps,
                                          num_homography=num_homography, num_keypoint_detection=fps)
     np.savez_compressed(os.path.join(GOLDEN, name), n_frames=n_frames, width=width, height=height, seed=seed, fps=fps,
-                        num_homography=num_homography, blank=np.array(blank, np.int32), heatmaps_sha256=sha(clip["heatmaps"]),
+                        num_homography=num_homography, blank=np.array(blank, np.int32),
+                        cv2_version=cv2.__version__, heatmaps_sha256=sha(clip["heatmaps"]),
                         result_json=json.dumps(res, default=float, sort_keys=True), n_fits=len(rec.fits))
     print(name, "frames", n_frames, "fits", len(rec.fits))
 
@@ -204,6 +204,9 @@ def main():
     clip_fixture("ref_clip_720p.npz", 8, 1280, 720, seed=7, ghost_prob=0.05)
     clip_fixture("ref_clip_1080p.npz", 6, 1920, 1080, seed=8, ghost_prob=0.10)
     cadence_fixture("ref_cadence_720p.npz", 17, 1280, 720, seed=9, fps=5, num_homography=1, blank=[])
+    # the reference itself goes through retry-after-failure: frame 0 and the scheduled frame 5 fail, so do the retries
+    # on 6; 11 is a failed frame the cadence never asks for
+    cadence_fixture("ref_cadence_retry_720p.npz", 17, 1280, 720, seed=9, fps=5, num_homography=1, blank=[0, 5, 6, 11])
     flow_fixture("ref_flow_360p.npz", 26, 640, 360, seed=31, fps=24, num_homography=1, num_keypoint_detection=3, pan_px=2.0)
     decode_fixture()
     find_homography_fixture()

@@ -30,3 +30,18 @@ def pytest_sessionstart(session):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+CADENCE_GOLDENS = ("ref_cadence_720p.npz", "ref_cadence_retry_720p.npz")
+
+
+def cadence_clip(golden_path, with_frames=False):
+    """The clip a cadence golden was minted from (oracle/make_golden.py::cadence_fixture): seeded synthetic clip, the
+    frames listed in ``blank`` replaced by four off-plane peaks so that their fit fails and the reference retries."""
+    import numpy as np
+    from eagle_b200 import synthetic
+    g = np.load(golden_path)
+    clip = synthetic.make_clip(int(g["n_frames"]), int(g["width"]), int(g["height"]), seed=int(g["seed"]), with_frames=with_frames,
+                               ghost_prob=0.05)
+    synthetic.blank_heatmaps(clip["heatmaps"], [int(b) for b in g["blank"]])
+    return g, clip

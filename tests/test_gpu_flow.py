@@ -116,7 +116,11 @@ def test_tracker_bit_exact_vs_cv2_and_oracle(engine):
 def test_tracker_warp_and_thread_kernels_agree():
     """EGL_TRACK_VARIANT=1 runs lk_track_point (csrc/flow_core.cuh, the scalar statement the CPU suite compiles for
     the host and compares with live cv2) one thread per point; the default warp kernel has to produce the same
-    bits.  Subprocesses, because the switch is read once per process."""
+    bits.  Subprocesses, because the switch is read once per process.  The thread kernel only exists in builds with
+    -DEGL_BENCH_VARIANTS (EGL_BENCH_VARIANTS=1 python -m eagle_b200.build --force; tools/variants_check.sh runs it)."""
+    from eagle_b200 import _native
+    if not (_native.lib.egl_build_flags() & 1):
+        pytest.skip("libeagle_b200.so was built without -DEGL_BENCH_VARIANTS: the one-thread-per-point tracker is not in it")
     import subprocess
     import sys
     import tempfile
@@ -430,8 +434,8 @@ def _sharded_flow_worker(rank, world, port, scenario, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         eng = GeometryEngine("cuda:0")
-        n, k, h, fps = 14, 4, 8, 8
-        if scenario == "plain":
+        n, k, h, fps = (5 if scenario == "short" else 14), 4, 8, 8
+        if scenario in ("plain", "short"):
             clip = synthetic.make_flow_clip(n, W, H, seed=110, pan_px=2.0)
         else:  # blank head + 3-landmark head on shard boundaries, retry flag crossing, fallback frame
             clip = synthetic.make_flow_clip(n, W, H, seed=22, pan_px=2.0)
@@ -440,8 +444,10 @@ def _sharded_flow_worker(rank, world, port, scenario, q):
         halo = 1 if lo > 0 else 0
         dev_frames = torch.from_numpy(np.ascontiguousarray(clip["frames"][lo - halo:hi])).cuda()
         net = _Net(eng, clip["frames"], clip["heatmaps"])
-        x_heads = eng.preprocess(dev_frames[halo::k].contiguous())
-        heads = net(x_heads).contiguous()
+        if hi > lo:
+            heads = net(eng.preprocess(dev_frames[halo::k].contiguous())).contiguous()
+        else:   # a rank past the end of a short clip holds only its predecessor's last frame
+            heads = torch.zeros((0, 57, 135, 240), device="cuda")
         detect = lambda i: net(eng.preprocess(dev_frames[halo + i - lo:halo + i - lo + 1].contiguous())).contiguous()
         res = run_sharded_propagated(eng, dev_frames, heads, detect, clip["objects"][lo:hi], fps, k, h, first_frame=lo)
         if rank == 0:
@@ -451,7 +457,7 @@ def _sharded_flow_worker(rank, world, port, scenario, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,scenario", [(2, "plain"), (3, "rescues")])
+@pytest.mark.parametrize("world,scenario", [(2, "plain"), (3, "rescues"), (3, "short")])
 def test_sparse_cadence_sharded_between_chains(world, scenario):
     """Chains shard over ranks (here the ranks share cuda:0 and talk over gloo; NCCL on a multi-GPU box): the
     parallel passes run at once, the boundary state is handed from rank to rank, rank 0 assembles the dict."""

@@ -148,7 +148,7 @@ def test_fit_and_projection_match_oracle(w, h, seed, ghost):
         assert status[i] == 0
         want_mask = sum(1 << c for c, m in zip(chans, t["mask"].ravel()) if m)
         assert int(inl[i]) == want_mask, f"frame {i}: inlier mask differs from cv2"
-        if int(t["mask"].sum()) >= 6:
+        if int(t["mask"].sum()) >= 5:   # exactly-4-inlier fits: test_four_inlier_fits_are_a_counted_carve_out
             worst_h = max(worst_h, float(np.max(np.abs(Hs[i] - t["H"]) / np.abs(t["H"]))))
         raw = np.array(t["proj_raw"])
         worst_p = max(worst_p, float(np.max(np.abs(pf[i, :len(raw)] - raw))))
@@ -196,7 +196,7 @@ def test_find_homography_golden_cases(engine, golden_dir):
             continue
         assert status[i] == 0, i
         assert int(inl[i]) == sum(1 << int(c) for c, m in zip(ch, g["mask"][i, :n]) if m), i
-        if int(g["mask"][i, :n].sum()) >= 6:
+        if int(g["mask"][i, :n].sum()) >= 5:   # exactly-4-inlier fits: test_four_inlier_fits_are_a_counted_carve_out
             worst = max(worst, float(np.max(np.abs(Hs[i] - g["H"][i]) / np.abs(g["H"][i]))))
     assert worst < H_REL_TOL, worst
 
@@ -320,15 +320,114 @@ def test_fixed_k_bit_exact_against_c_mirror(engine, use_table):
     assert worst < 1e-6, worst
 
 
-def test_drop_in_get_coordinates_with_cadence(golden_dir):
+def test_fixed_k_against_cv2_arithmetic_on_the_same_tables(engine):
+    """North star: "landmark indices and inlier masks bit-exact when both implementations are fed the same seeded
+    hypothesis set".  The other implementation here is OpenCV's own arithmetic -- oracle/homography.py's restated
+    RANSACPointSetRegistrator (double-precision normalised DLT per sample, float reprojection errors, first strictly
+    better hypothesis wins), driven by the SAME explicit table with the adaptive stop switched off -- not the mirror
+    of the kernel's FP32 recipe.  Reported: how often the two pick the same hypothesis; asserted: the final inlier mask
+    is identical and the refined H agrees within 1e-4 on every frame."""
+    from eagle_b200 import _native as N
+    from eagle_b200.pitch import WORLD_XY_F32
+    from oracle import homography
+    F, K = 24, 512
+    kp, xy, on, flags = _stress_kp(F, 5)
+    rng = np.random.default_rng(9)
+    hyp = np.stack([np.stack([rng.choice(53, 4, replace=False) for _ in range(K)]) for _ in range(F)]).astype(np.uint8)
+    fit = engine.fit(kp, mode=N.FIT_FIXED_K, K=K, hyp=torch.from_numpy(hyp).cuda())
+    info = fit.info.cpu().numpy(); status = fit.status.cpu().numpy(); inl = fit.inlier_mask.cpu().numpy()
+    Hs = fit.H.cpu().numpy().reshape(-1, 3, 3)
+    same_winner = 0
+    worst = 0.0
+    for f in range(F):
+        img = xy[f, on].astype(np.float32); wor = WORLD_XY_F32[on]
+        Hc, mc, ci = homography.find_homography_restated(img, wor, 5.0, hyp_table=hyp[f], adaptive=False, return_info=True)
+        assert Hc is not None and status[f] == 0
+        same_winner += int(info[f, 2] == ci["best_hyp"])
+        assert int(inl[f]) == sum(1 << c for c, b in zip(on, mc.ravel()) if b), f"frame {f}: final inlier mask differs from cv2 arithmetic"
+        worst = max(worst, float(np.max(np.abs(Hs[f] - Hc) / np.abs(Hc))))
+    print(f"fixed-K vs cv2 arithmetic on the same tables: same winning hypothesis on {same_winner}/{F} frames, worst relative H error {worst:.2e}")
+    assert same_winner >= F - 2, same_winner   # a different winner needs two hypotheses within FP32 rounding of a tie
+    assert worst < H_REL_TOL, worst
+
+
+def test_four_inlier_fits_are_a_counted_carve_out(engine):
+    """The H tolerance (1e-4 relative) is asserted for every fit OpenCV ends with five or more inliers on.  A fit that
+    ends on exactly FOUR inliers (of more than four correspondences) is refined by LM on a system with one equation per
+    unknown: J^T J is numerically singular and cv2's own eigen back-substitution divides by rounding noise, so no
+    independent arithmetic reproduces its digits.  Those fits are counted here, not skipped: the mask must still be
+    identical, at most 3 % of them may leave the tolerance, and even then the four inlier landmarks must map to the
+    same pitch position within 0.25 m.  (CPU calibration of the same code, 3000 sets: 0.7 % outside, worst 0.04 m.)"""
+    cv2 = pytest.importorskip("cv2")
+    from eagle_b200 import synthetic
+    from eagle_b200.engine import KeypointSet
+    from eagle_b200.pitch import OFF_PLANE, WORLD_XYZ
+    on = np.array([i for i in range(57) if i not in OFF_PLANE])
+    rng = np.random.default_rng(3)
+    sets = []
+    while len(sets) < 1500:
+        W, Himg = [(1280, 720), (1920, 1080), (960, 540)][len(sets) % 3]
+        cam = synthetic.sample_cameras(1, W, Himg, rng)[0]
+        px, vis = synthetic.landmark_pixels(cam, W, Himg)
+        sel = on[vis[on]]
+        if len(sel) < 5:
+            continue
+        good = rng.choice(sel, int(rng.integers(4, 6)), replace=False)
+        bad = rng.choice(np.setdiff1d(on, good), int(rng.integers(1, 12)), replace=False)
+        pts = {int(c): px[c] + rng.normal(0, 0.7, 2) for c in good}
+        pts.update({int(c): rng.uniform([0, 0], [W, Himg]) for c in bad})
+        chs = sorted(pts)
+        sets.append((chs, np.rint(np.array([pts[c] for c in chs])).astype(np.int32)))
+    T = len(sets)
+    xy = np.zeros((T, 57, 2), np.int32); order = np.full((T, 64), 255, np.uint8); count = np.zeros((T, 2), np.int32)
+    for i, (chs, ip) in enumerate(sets):
+        xy[i, chs] = ip; order[i, :len(chs)] = chs; count[i] = len(chs)
+    kp = KeypointSet(None, None, torch.from_numpy(xy).cuda(), torch.from_numpy(order).cuda(), torch.from_numpy(count).cuda())
+    fit = engine.fit(kp)
+    Hs = fit.H.cpu().numpy().reshape(-1, 3, 3); status = fit.status.cpu().numpy(); inl = fit.inlier_mask.cpu().numpy()
+
+    def proj(Hm, p):
+        q = np.c_[p, np.ones(len(p))] @ Hm.T
+        return q[:, :2] / q[:, 2:3]
+
+    four = five = outside = 0
+    worst5 = worst_m = 0.0
+    for i, (chs, ip) in enumerate(sets):
+        a = ip.astype(np.float32)
+        H, m = cv2.findHomography(a, WORLD_XYZ[chs, :2].astype(np.float32), cv2.RANSAC, 5.0)
+        if H is None:
+            assert status[i] != 0, i
+            continue
+        k = int(m.sum())
+        if k not in (4, 5) or len(chs) == 4:
+            continue
+        assert status[i] == 0 and int(inl[i]) == sum(1 << int(c) for c, mm in zip(chs, m.ravel()) if mm), i
+        rel = float(np.max(np.abs(Hs[i] - H) / np.abs(H)))
+        if k == 5:
+            five += 1
+            worst5 = max(worst5, rel)
+        else:
+            four += 1
+            outside += rel >= H_REL_TOL
+            pin = a[m.ravel() > 0]
+            worst_m = max(worst_m, float(np.max(np.abs(proj(Hs[i], pin) - proj(H, pin)))))
+    print(f"5-inlier fits {five} (worst rel H {worst5:.2e}); 4-inlier fits {four}, {outside} outside 1e-4, worst inlier displacement {worst_m:.3g} m")
+    assert five > 300 and four > 100
+    assert worst5 < H_REL_TOL, worst5
+    assert outside <= 0.03 * four and worst_m < 0.25, (outside, four, worst_m)
+
+
+@pytest.mark.parametrize("name", ["ref_cadence_720p.npz", "ref_cadence_retry_720p.npz"])
+def test_drop_in_get_coordinates_with_cadence(golden_dir, name):
     """The reference-shaped front end (frames in, dict out; K1 -> network stand-in -> K2..K4) with the
     reference's homography cadence (fps=5, num_homography=1), against the dict the UNMODIFIED reference
-    produced for the same clip (tests/golden/ref_cadence_720p.npz)."""
+    produced for the same clip (tests/golden/ref_cadence_720p.npz; in ref_cadence_retry_720p.npz the reference
+    itself goes through retry-after-failure: frames 0, 5, 6 and 11 cannot be fitted)."""
+    from conftest import cadence_clip
     from eagle_b200 import synthetic
     from eagle_b200.coordinate_model import CoordinateModel, GeometryPath
-    g = np.load(os.path.join(golden_dir, "ref_cadence_720p.npz"))
+    g, clip = cadence_clip(os.path.join(golden_dir, name), with_frames=True)
     n, w, h = int(g["n_frames"]), int(g["width"]), int(g["height"])
-    clip = synthetic.make_clip(n, w, h, seed=int(g["seed"]), with_frames=True, ghost_prob=0.05)
     assert sha(clip["heatmaps"]) == str(g["heatmaps_sha256"])
     hm = torch.from_numpy(clip["heatmaps"]).cuda()
     state = {"i": 0, "seen": 0}
@@ -349,34 +448,24 @@ def test_drop_in_get_coordinates_with_cadence(golden_dir):
     assert json.dumps(got2, default=float, sort_keys=True) == str(g["result_json"])
 
 
-def test_refit_thread_and_warp_kernels_agree():
-    """EGL_REFIT_VARIANT=1 (one thread per frame, the host-checkable scalar code) and =2 (one warp per
-    frame) are the same algorithm: identical masks, H equal to rounding.  Run in subprocesses because the
-    switch is read once per process."""
-    import subprocess
-    import sys
-    code = r'''
-import sys, numpy as np, torch
-sys.path.insert(0, %r)
-from eagle_b200 import synthetic
-from eagle_b200.coordinate_model import GeometryPath
-clip = synthetic.make_clip(12, 1920, 1080, seed=77, ghost_prob=0.1)
-p = GeometryPath("cuda:0")
-kp, fit, hi, at, pr = p.run_device(torch.from_numpy(clip["heatmaps"]).cuda(), torch.zeros((12, 1, 2)).cuda(),
-                                   torch.zeros(12, dtype=torch.int32).cuda(), 1920, 1080)
-np.save(sys.argv[1], np.concatenate([fit.H.cpu().numpy().ravel(), fit.inlier_mask.cpu().numpy().astype(np.float64)]))
-''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    import tempfile
-    outs = []
-    for variant in ("1", "2"):
-        f = tempfile.NamedTemporaryFile(suffix=".npy", delete=False).name
-        subprocess.check_call([sys.executable, "-c", code, f], env=dict(os.environ, EGL_REFIT_VARIANT=variant))
-        outs.append(np.load(f)); os.unlink(f)
-    a, b = outs
-    assert np.array_equal(a[-12:], b[-12:])                      # masks
-    # H: the LM minimum is flat to ~1e-8 (cost changes < 1e-15 there), so two summation orders agree to that
-    assert np.max(np.abs(a[:-12] - b[:-12]) / np.abs(a[:-12])) < 1e-6
-
+def test_refit_thread_and_warp_kernels_agree(engine):
+    """The refit exists twice -- one thread per frame (the host-checkable scalar code, chosen above 12 288 frames per call)
+    and one warp per frame (below) -- and is the same algorithm: identical masks, H equal to rounding.  The kernels are
+    selected the way production selects them, by batch size: the same 12 frames alone and tiled to 12 300."""
+    from eagle_b200 import synthetic
+    from eagle_b200.engine import KeypointSet
+    clip = synthetic.make_clip(12, 1920, 1080, seed=77, ghost_prob=0.1)
+    kp = engine.decode(torch.from_numpy(clip["heatmaps"]).cuda(), 1920, 1080)
+    engine.synthesize(kp)
+    small = engine.fit(kp)
+    reps = 1025
+    big_kp = KeypointSet(None, None, kp.xy.repeat(reps, 1, 1), kp.order.repeat(reps, 1), kp.count.repeat(reps, 1))
+    big = engine.fit(big_kp)
+    assert big_kp.n_frames > 12288
+    for r in (0, 1, reps - 1):
+        sl = slice(12 * r, 12 * r + 12)
+        assert torch.equal(big.status[sl], small.status) and torch.equal(big.inlier_mask[sl], small.inlier_mask)
+        assert float(((big.H[sl] - small.H).abs() / small.H.abs().clamp_min(1e-300)).max()) < 1e-9
 
 def _sharded_worker(rank, world, port, golden_path, out_q):
     import torch.distributed as dist
@@ -385,9 +474,9 @@ def _sharded_worker(rank, world, port, golden_path, out_q):
     from eagle_b200.sharding import frame_range, run_sharded
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    g = np.load(golden_path)
+    from conftest import cadence_clip
+    g, clip = cadence_clip(golden_path)
     n, w, h = int(g["n_frames"]), int(g["width"]), int(g["height"])
-    clip = synthetic.make_clip(n, w, h, seed=int(g["seed"]), ghost_prob=0.05)
     lo, hi = frame_range(n, rank, world)
     path = GeometryPath("cuda:0")
     res = run_sharded(path, torch.from_numpy(clip["heatmaps"][lo:hi]).cuda(), clip["objects"][lo:hi], w, h, fps=int(g["fps"]),
@@ -397,8 +486,8 @@ def _sharded_worker(rank, world, port, golden_path, out_q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_clip_equals_reference_dict(golden_dir, world):
+@pytest.mark.parametrize("world,name", [(2, "ref_cadence_720p.npz"), (3, "ref_cadence_720p.npz"), (3, "ref_cadence_retry_720p.npz")])
+def test_sharded_clip_equals_reference_dict(golden_dir, world, name):
     """Frame-range sharding (here: ranks share cuda:0 and gather over gloo; NCCL on a multi-GPU box):
     the shard boundaries (17 frames over 2 / 3 ranks) do not align with the homography interval (5), so
     the cadence state has to be carried across shards on rank 0 -- the result must still be the dict the
@@ -408,7 +497,7 @@ def test_sharded_clip_equals_reference_dict(golden_dir, world):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, os.path.join(golden_dir, "ref_cadence_720p.npz"), q))
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, os.path.join(golden_dir, name), q))
              for r in range(world)]
     for p in procs:
         p.start()

@@ -156,16 +156,20 @@ def test_empty_and_few_point_frames():
     assert res[0]["Keypoints"] == {} and len(res[1]["Keypoints"]) == 3
 
 
-def test_homography_cadence_matches_reference(golden_dir):
-    """fps=5, num_homography=1 -> fit on frames 0,5,10,15 only; the rest reuse H (reference run)."""
-    g = np.load(os.path.join(golden_dir, "ref_cadence_720p.npz"))
-    clip = synthetic.make_clip(int(g["n_frames"]), int(g["width"]), int(g["height"]), seed=int(g["seed"]), ghost_prob=0.05)
+@pytest.mark.parametrize("name", ["ref_cadence_720p.npz", "ref_cadence_retry_720p.npz"])
+def test_homography_cadence_matches_reference(golden_dir, name):
+    """fps=5, num_homography=1 -> fit on frames 0,5,10,15 only; the rest reuse H (reference run).  In the second
+    fixture frames 0, 5 and 6 cannot be fitted, so the reference itself retries on 1 and on 6, 7 (:350-352, 366-367)."""
+    from conftest import cadence_clip
+    g, clip = cadence_clip(os.path.join(golden_dir, name))
     assert sha(clip["heatmaps"]) == str(g["heatmaps_sha256"])
     trace = []
     res = pipeline.get_coordinates(clip["heatmaps"], clip["objects"], clip["width"], clip["height"], fps=int(g["fps"]),
                                    num_homography=int(g["num_homography"]), trace=trace)
     assert json.dumps(res, default=float, sort_keys=True) == str(g["result_json"])
     assert sum(t["H"] is not None for t in trace) == int(g["n_fits"]) == 4
+    if len(g["blank"]):
+        assert res[0]["Boundaries"] == [None] * 4 and [i for i, t in enumerate(trace) if t["H"] is not None] == [1, 7, 10, 15]
 
 
 def test_rho_lmeds_fallbacks_never_rescue_a_failed_ransac():

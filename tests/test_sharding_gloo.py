@@ -75,3 +75,6 @@ def test_chain_range_cuts_between_chains():
                     assert lo == prev and lo <= hi <= n and (lo % k == 0 or lo == n)
                     prev = hi
                 assert prev == n
+                # a short clip leaves the HIGH ranks idle, never rank 0 (which assembles) nor a rank between two busy ones
+                sizes = [chain_range(n, k, r, world)[1] - chain_range(n, k, r, world)[0] for r in range(world)]
+                assert sizes[0] > 0 and all(a > 0 or b == 0 for a, b in zip(sizes, sizes[1:]))
