@@ -491,9 +491,12 @@ def main():
             for s in range(0, Fm, F):
                 yield t[:min(F, Fm - s)]
 
+        mstats = {}
+
         def match_once(assemble):
-            return run_sharded(path, chunks(hm), objs_local, W, H, 25, 25, objects_on_rank0=objs_all, assemble=assemble,
-                               frames_local=chunks(frames))
+            mstats.clear()
+            return run_sharded(path, chunks(hm), objs_local, W, H, 25, 25, gather_objects=False, objects_on_rank0=objs_all, assemble=assemble,
+                               frames_local=chunks(frames), stats=mstats)
 
         match_once(False)
         barrier()
@@ -523,6 +526,7 @@ def main():
                       "with_dict_on_rank0": {"value": M / md_dt, "unit": "frames/s", "s_per_match": md_dt,
                                              "note": "same, plus one D2H of every result and the reference-format dict of all frames "
                                                      "assembled on rank 0 (detections already on rank 0)"},
+                      "rank0_host_split_s": dict(mstats),
                       "timing": "wall clock around run_sharded incl. the gather, barrier + synchronize on both sides, max over ranks"}
         del objs_local, objs_all
 

@@ -52,12 +52,23 @@ def unpack_results(records: torch.Tensor, like: Sequence[torch.Tensor]) -> list[
     return out
 
 
+_PINNED = {}
+
+
 def download(tensors: Sequence[torch.Tensor]) -> list:
-    """Device tensors (F, ...) -> numpy arrays through ONE packed device-to-host copy (instead of one per tensor)."""
-    if tensors[0].shape[0] == 0:
+    """Device tensors (F, ...) -> numpy arrays through ONE packed device-to-host copy (instead of one per tensor), staged
+    in a reusable page-locked buffer (a pageable destination halves the copy rate and costs an allocation per call)."""
+    if tensors[0].shape[0] == 0 or not tensors[0].is_cuda:
         return [t.cpu().numpy() for t in tensors]
-    rec = pack_results(tensors).cpu()
-    return [t.numpy() for t in unpack_results(rec, tensors)]
+    rec = pack_results(tensors)
+    n = rec.numel()
+    buf = _PINNED.get("buf")
+    if buf is None or buf.numel() < n:
+        buf = _PINNED["buf"] = torch.empty(max(n, 1 << 20), dtype=torch.uint8, pin_memory=True)
+    host = buf[:n].view(rec.shape)
+    host.copy_(rec, non_blocking=True)
+    torch.cuda.current_stream(rec.device).synchronize()
+    return [t.numpy() for t in unpack_results(host, tensors)]
 
 
 def gather_to_rank0(records: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor | None:
@@ -90,8 +101,9 @@ class FewLandmarksError(RuntimeError):
 
 
 def run_sharded(path, heatmaps_local, objects_local: Sequence[dict], width: int, height: int, fps: int,
-                homography_interval: int = 1, group=None, *, objects_on_rank0: Sequence[dict] | None = None, assemble: bool = True,
-                frames_local=None):
+                homography_interval: int = 1, group=None, *, gather_objects: bool = True,
+                objects_on_rank0: Sequence[dict] | None = None, assemble: bool = True, frames_local=None,
+                stats: dict | None = None):
     """The geometry path for one clip sharded by contiguous frame range over the ranks of ``group``.
 
     Every rank calls this with ITS frames' heatmaps and detector dicts, in rank order of the clip.  ``heatmaps_local``
@@ -102,14 +114,24 @@ def run_sharded(path, heatmaps_local, objects_local: Sequence[dict], width: int,
     synthesis, RANSAC + refit) run on each rank's range; the small per-frame results are gathered to rank 0, which
     evaluates the homography cadence over the WHOLE clip (it carries state across shard boundaries exactly as the
     reference's sequential loop does), projects and assembles the reference-format dict.  Returns that dict on rank 0
-    and None elsewhere (``assemble=False``: the per-frame arrays instead of the dict).  ``objects_on_rank0``: the whole
-    clip's detections when rank 0 already holds them (skips the pickled gather of the dicts).
+    and None elsewhere (``assemble=False``: the per-frame arrays instead of the dict).  ``gather_objects=False`` (the same
+    on EVERY rank) skips the pickled gather of the detection dicts; rank 0 then passes the whole clip's detections as
+    ``objects_on_rank0`` (e.g. the detector ran there).
 
     Precondition (checked, FewLandmarksError on every rank): every frame decodes at least four landmarks.
     Works with NCCL (GPU tensors) and with gloo (records staged through the host, used by the single-GPU tests)."""
     from .boxes import max_objects, objects_to_arrays
     from .coordinate_model import assemble_frames
     from .engine import FitResult, KeypointSet
+
+    import time
+    t_mark = [time.perf_counter()]
+
+    def lap(name):   # wall-clock split for ``stats`` (host view: kernels are asynchronous until the first sync)
+        if stats is not None:
+            now = time.perf_counter()
+            stats[name] = stats.get(name, 0.0) + now - t_mark[0]
+            t_mark[0] = now
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -138,11 +160,14 @@ def run_sharded(path, heatmaps_local, objects_local: Sequence[dict], width: int,
     F_r = kp.xy.shape[0]
     if len(objects_local) != F_r:
         raise ValueError(f"rank {rank}: {F_r} frames of heatmaps but {len(objects_local)} detection dicts")
+    lap("enqueue_s")
     # the foot points are packed while the kernels above still run (nothing has synchronised yet)
     P_local = max(1, max_objects(objects_local))
     foot_h, cnt_h = objects_to_arrays(objects_local, P_local)
     # per-rank frame counts, the clip-wide maximum object count and the < 4 landmarks flag (host-side, tiny)
+    lap("pack_foot_s")
     few = bool((kp.count[:, 1] < 4).any().item()) if F_r else False
+    lap("wait_kernels_s")
     local_meta = (F_r, P_local, few)
     metas = [None] * world
     if world > 1:
@@ -164,8 +189,9 @@ def run_sharded(path, heatmaps_local, objects_local: Sequence[dict], width: int,
     if backend == "gloo":
         rec = rec.cpu()
     all_rec = gather_to_rank0(rec, counts, group) if world > 1 else rec
+    lap("gather_s")
     objs_all = None
-    if assemble and objects_on_rank0 is None:
+    if assemble and gather_objects:
         objs_all = [None] * world
         if world > 1:
             dist.gather_object(objects_local, objs_all if rank == 0 else None, dst=0, group=group)
@@ -178,12 +204,20 @@ def run_sharded(path, heatmaps_local, objects_local: Sequence[dict], width: int,
     h_index, attempted = e.select(status.contiguous(), homography_interval)
     proj = e.project(H.contiguous(), foot_a.contiguous(), cnt_a.contiguous(), width, height, h_index=h_index)
     arrays = download([xy, order, count, used, inl, status, attempted, h_index, proj.coords_i, proj.in_bounds, proj.bounds])
+    lap("rank0_cadence_project_download_s")
     if not assemble:
         return arrays
-    objects_per_frame = list(objects_on_rank0) if objects_on_rank0 is not None else [o for part in objs_all for o in part]
+    if gather_objects:
+        objects_per_frame = [o for part in objs_all for o in part]
+    elif objects_on_rank0 is None:
+        raise ValueError("run_sharded(gather_objects=False) needs the clip's detections as objects_on_rank0 on rank 0")
+    else:
+        objects_per_frame = list(objects_on_rank0)
     if len(objects_per_frame) != sum(counts):
         raise ValueError(f"{sum(counts)} frames in the clip but {len(objects_per_frame)} detection dicts on rank 0")
-    return assemble_frames(objects_per_frame, fps, 0, *arrays)
+    res = assemble_frames(objects_per_frame, fps, 0, *arrays)
+    lap("assemble_s")
+    return res
 
 
 def chain_range(n_frames: int, keypoint_interval: int, rank: int, world: int) -> tuple[int, int]:
