@@ -53,22 +53,31 @@ def unpack_results(records: torch.Tensor, like: Sequence[torch.Tensor]) -> list[
 
 
 _PINNED = {}
+_NP_DTYPE = {torch.uint8: "uint8", torch.int32: "int32", torch.int64: "int64", torch.float32: "float32", torch.float64: "float64",
+             torch.int8: "int8", torch.int16: "int16", torch.bool: "bool"}
 
 
 def download(tensors: Sequence[torch.Tensor]) -> list:
-    """Device tensors (F, ...) -> numpy arrays through ONE packed device-to-host copy (instead of one per tensor), staged
-    in a reusable page-locked buffer (a pageable destination halves the copy rate and costs an allocation per call)."""
+    """Device tensors (F, ...) -> numpy arrays through ONE device-to-host copy (instead of one per tensor): the tensors are
+    laid end to end on the device (planar, so that every array is one contiguous block on the host and no strided
+    unpacking is needed there), copied into a reusable page-locked buffer, and copied out of it as owned arrays."""
+    import numpy as np
     if tensors[0].shape[0] == 0 or not tensors[0].is_cuda:
         return [t.cpu().numpy() for t in tensors]
-    rec = pack_results(tensors)
-    n = rec.numel()
+    flat = torch.cat([t.contiguous().view(torch.uint8).reshape(-1) for t in tensors])
+    n = flat.numel()
     buf = _PINNED.get("buf")
     if buf is None or buf.numel() < n:
         buf = _PINNED["buf"] = torch.empty(max(n, 1 << 20), dtype=torch.uint8, pin_memory=True)
-    host = buf[:n].view(rec.shape)
-    host.copy_(rec, non_blocking=True)
-    torch.cuda.current_stream(rec.device).synchronize()
-    return [t.numpy() for t in unpack_results(host, tensors)]
+    buf[:n].copy_(flat, non_blocking=True)
+    torch.cuda.current_stream(flat.device).synchronize()
+    host = buf.numpy()
+    out, o = [], 0
+    for t in tensors:
+        nb = t.numel() * t.element_size()
+        out.append(np.array(host[o:o + nb], copy=True).view(_NP_DTYPE[t.dtype]).reshape(tuple(t.shape)))
+        o += nb
+    return out
 
 
 def gather_to_rank0(records: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor | None:
@@ -127,8 +136,10 @@ def run_sharded(path, heatmaps_local, objects_local: Sequence[dict], width: int,
     import time
     t_mark = [time.perf_counter()]
 
-    def lap(name):   # wall-clock split for ``stats`` (host view: kernels are asynchronous until the first sync)
+    def lap(name, sync=False):   # wall-clock split for ``stats``; sync=True charges the device work enqueued so far to this lap
         if stats is not None:
+            if sync and torch.cuda.is_available():
+                torch.cuda.synchronize()
             now = time.perf_counter()
             stats[name] = stats.get(name, 0.0) + now - t_mark[0]
             t_mark[0] = now
@@ -189,7 +200,7 @@ def run_sharded(path, heatmaps_local, objects_local: Sequence[dict], width: int,
     if backend == "gloo":
         rec = rec.cpu()
     all_rec = gather_to_rank0(rec, counts, group) if world > 1 else rec
-    lap("gather_s")
+    lap("gather_s", sync=True)
     objs_all = None
     if assemble and gather_objects:
         objs_all = [None] * world
@@ -203,8 +214,9 @@ def run_sharded(path, heatmaps_local, objects_local: Sequence[dict], width: int,
     xy, order, count, H, used, inl, status, foot_a, cnt_a = unpack_results(all_rec, like)
     h_index, attempted = e.select(status.contiguous(), homography_interval)
     proj = e.project(H.contiguous(), foot_a.contiguous(), cnt_a.contiguous(), width, height, h_index=h_index)
+    lap("rank0_cadence_project_s", sync=True)
     arrays = download([xy, order, count, used, inl, status, attempted, h_index, proj.coords_i, proj.in_bounds, proj.bounds])
-    lap("rank0_cadence_project_download_s")
+    lap("rank0_download_s")
     if not assemble:
         return arrays
     if gather_objects:
