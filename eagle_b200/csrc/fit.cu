@@ -596,53 +596,51 @@ struct RefitShared {
     double xs[9], rs[9], ds[9];  // parameter vector / right-hand side / LM scaling staged for lane-indexed access
 };
 
-// Gauss-Jordan elimination with partial pivoting of an n x n system held as an augmented n x (n+1)
-// array (row stride S = n+1) in shared memory, all 32 lanes working: lane l owns elements l, l+32, ...;
-// step k picks the largest remaining entry of column k (every lane scans the <= 10 candidates itself, so
-// the choice is uniform without shuffles; lowest row on ties, like the scalar gauss_solve), swaps rows,
-// and clears column k in every other row.  Same pivot order as the one-thread-per-frame code, which is
-// what keeps the two kernels -- and cv2 -- together on poorly conditioned fits.  x[0..n) in shared
-// memory.  Returns false (uniformly) on a zero / non-finite pivot.
+// Gauss-Jordan elimination with partial pivoting of an n x n system, rows in REGISTERS: lane r < n holds row r of
+// the augmented n x (n+1) array.  Step k picks the largest remaining |entry| of column k (three warp reductions on
+// the bit pattern -- non-negative doubles order like unsigned integers -- with the lowest row position on ties, like
+// the scalar gauss_solve), broadcasts the pivot row by shuffles and clears column k in every other row.  Rows are
+// not moved when they are "swapped": each lane tracks the position its row would have, which is all the pivot
+// order and the result need.  Same pivot order and the same operations per element as the one-thread-per-frame
+// code, which is what keeps the two kernels -- and cv2 -- together on poorly conditioned fits.  x[0..n) goes to
+// shared memory.  Returns false (uniformly) on a zero / non-finite pivot.  (The shared-memory version this
+// replaces spent two thirds of its instructions on element indices, barriers and the lane id.)
 template <int n>
-__device__ bool warp_pivot_solve(double* aug, double* x) {
-    constexpr int S = n + 1, E = n * S, Q = (E + 31) / 32;
-    const int lane = threadIdx.x & 31;
-    int er[Q], ej[Q];
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-        const int e = lane + 32 * q;
-        er[q] = e < E ? e / S : -1;
-        ej[q] = e % S;
-    }
+__device__ __forceinline__ bool warp_row_solve(double (&row)[n + 1], double* x, int lane) {
+    const bool is_row = lane < n;
+    int pos = lane;
+    double diag = 1.0;   // this row's pivot element, once it has been the pivot row
+    // The row is shifted left by one element per step, so the current column is always row[0]: the loop body has
+    // static register indices without being unrolled n times (the unrolled form was instruction-fetch bound).
+#pragma unroll 1
     for (int k = 0; k < n; ++k) {
-        int piv = k;
-        double best = fabs(aug[k * S + k]);
-        for (int r = k + 1; r < n; ++r) {
-            const double v = fabs(aug[r * S + k]);
-            if (v > best) { best = v; piv = r; }
-        }
+        const bool eligible = is_row && pos >= k;
+        const unsigned long long bits = eligible ? (unsigned long long)__double_as_longlong(fabs(row[0])) : 0ull;
+        const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+        const unsigned mhi = __reduce_max_sync(kFull, hi);
+        bool cand = eligible && hi == mhi;
+        const unsigned mlo = __reduce_max_sync(kFull, cand ? lo : 0u);
+        cand = cand && lo == mlo;
+        const unsigned ppos = __reduce_min_sync(kFull, cand ? (unsigned)pos : 99u);
+        const bool is_piv = cand && (unsigned)pos == ppos;
+        const double best = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
         if (!(best > 0.0) || !isfinite(best)) return false;
-        __syncwarp();
-        if (piv != k && lane < S) {  // lanes are columns for the swap
-            const double t = aug[k * S + lane];
-            aug[k * S + lane] = aug[piv * S + lane];
-            aug[piv * S + lane] = t;
-        }
-        __syncwarp();
-        const double inv = 1.0 / aug[k * S + k];
-        double nv[Q];
-        bool upd[Q];
+        const int blane = __ffs(__ballot_sync(kFull, is_piv)) - 1;
+        if (pos == k) pos = (int)ppos;      // the row that sat at position k takes the pivot row's place ...
+        else if (is_piv) pos = k;           // ... and the pivot row moves to position k
+        const double inv = 1.0 / shfl_f64(row[0], blane);
+        const double f = row[0] * inv;
+        if (is_piv) diag = row[0];
+        const bool upd = is_row && !is_piv;
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            upd[q] = er[q] >= 0 && er[q] != k && ej[q] > k;
-            if (upd[q]) nv[q] = aug[er[q] * S + ej[q]] - (aug[er[q] * S + k] * inv) * aug[k * S + ej[q]];
+        for (int j = 1; j <= n; ++j) {
+            const double pj = shfl_f64(row[j], blane);
+            row[j - 1] = upd ? row[j] - f * pj : row[j];   // eliminate and shift; columns already used carry zeros along
         }
-#pragma unroll
-        for (int q = 0; q < Q; ++q)
-            if (upd[q]) aug[er[q] * S + ej[q]] = nv[q];
-        __syncwarp();
+        row[n] = 0.0;
     }
-    if (lane < n) x[lane] = aug[lane * S + n] / aug[lane * S + lane];
+    // after n shifts the right-hand side sits in row[0]
+    if (is_row) x[pos] = row[0] / diag;
     __syncwarp();
     return true;
 }
@@ -761,13 +759,11 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
             double y_l = lane < 9 ? 1.0 / (1.37 + lane) : 0.0;  // lane i < 9 holds y[i]
             double prev = 1e300;
             for (int it = 0; it < 48 && have_ls; ++it) {
-                for (int t = lane; t < 81; t += 32) {
-                    const int r = t / 9, c = t % 9;
-                    sh.aug[r * 10 + c] = sh.A[t] + (r == c ? sigma : 0.0);
-                }
-                if (lane < 9) sh.aug[lane * 10 + 9] = y_l;
-                __syncwarp();
-                if (!warp_pivot_solve<9>(sh.aug, sh.vec)) { have_ls = false; break; }
+                double row[10];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) row[c] = lane < 9 ? sh.A[lane * 9 + c] + (lane == c ? sigma : 0.0) : 0.0;
+                row[9] = y_l;
+                if (!warp_row_solve<9>(row, sh.vec, lane)) { have_ls = false; break; }
                 double z = lane < 9 ? sh.vec[lane] : 0.0;
                 const double nrm = warp_sum_f64(z * z);
                 // sign: component of largest magnitude positive (lowest index on ties)
@@ -866,15 +862,12 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
             const double sc = dmx / sqrt(xn);
             stage(sh.xs, x);
             stage(sh.rs, rhs);
-            for (int t = lane; t < 81; t += 32) sh.aug[(t / 9) * 11 + (t % 9)] = sh.A[t];
-            if (lane < 9) {
-                sh.aug[lane * 11 + 9] = sc * sh.xs[lane];
-                sh.aug[lane * 11 + 10] = sh.rs[lane];
-                sh.aug[9 * 11 + lane] = sc * sh.xs[lane];
-            }
-            if (lane == 0) { sh.aug[9 * 11 + 9] = 0.0; sh.aug[9 * 11 + 10] = 0.0; }
-            __syncwarp();
-            return warp_pivot_solve<10>(sh.aug, sh.vec);
+            double row[11];
+#pragma unroll
+            for (int c = 0; c < 9; ++c) row[c] = lane < 9 ? sh.A[lane * 9 + c] : (lane == 9 ? sc * sh.xs[c] : 0.0);
+            row[9] = lane < 9 ? sc * sh.xs[lane] : 0.0;
+            row[10] = lane < 9 ? sh.rs[lane] : 0.0;
+            return warp_row_solve<10>(row, sh.vec, lane);
         };
         linearise(x);
 #pragma unroll
@@ -887,13 +880,11 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
             bool ok;
             if (lambda > 0) {
                 stage(sh.rs, v);
-                for (int t = lane; t < 81; t += 32) {
-                    const int r = t / 9, c = t % 9;
-                    sh.aug[r * 10 + c] = sh.A[t] + (r == c ? lambda * sh.ds[r] : 0.0);
-                }
-                if (lane < 9) sh.aug[lane * 10 + 9] = sh.rs[lane];
-                __syncwarp();
-                ok = warp_pivot_solve<9>(sh.aug, sh.vec);
+                double row[10];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) row[c] = lane < 9 ? sh.A[lane * 9 + c] + (lane == c ? lambda * sh.ds[c] : 0.0) : 0.0;
+                row[9] = lane < 9 ? sh.rs[lane] : 0.0;
+                ok = warp_row_solve<9>(row, sh.vec, lane);
             } else {
                 ok = solve_gauge(v);
             }
