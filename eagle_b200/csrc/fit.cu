@@ -12,6 +12,10 @@
 //                       solved by block elimination entirely in FP32 registers, all N points scored
 //                       by the same thread with a division-free test (13 FP32 ops per point);
 //                       block-wide arg-max (ties -> lowest hypothesis index).  FP32-ALU bound.
+//   cascade_kernel      (mode EGL_FIT_CV2_COMPAT) the rest of the reference's cascade, `for method in [cv2.RANSAC,
+//                       cv2.RHO, cv2.LMEDS]` (:354-357), for the frames the RANSAC leg left without a model: one thread
+//                       per such frame runs OpenCV's RHO estimator and, if that fails too, LMedS (cascade_core.cuh);
+//                       every other thread exits on its status word.
 //   refit_warp_kernel   one warp per frame, FP64: OpenCV's tail of findHomography -- normalised DLT on
 //                       the inliers (smallest eigenvector of the 9x9 normal matrix), <= 10
 //                       Levenberg-Marquardt iterations over nine parameters, mask recomputed from the
@@ -23,6 +27,7 @@
 
 #include "common.cuh"
 #include "geometry_core.cuh"
+#include "cascade_core.cuh"
 
 namespace egl {
 
@@ -969,6 +974,45 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The RHO and LMEDS legs of coordinate_model.py:354-357 for frames whose RANSAC leg returned no model.
+// Rare frames (RANSAC gives up only when no sample passes checkSubset or no model reaches 4 inliers), both
+// estimators are sequential by construction (every sample depends on the SPRT / iteration bounds the
+// previous one left), so: one thread per frame, scalar code shared with the host build.
+//   status -> EGL_FIT_OK, H / inlier_mask / info[1] as for the RANSAC leg, info[2] = EGL_FIT_LEG_RHO / _LMEDS
+// ------------------------------------------------------------------------------------------------
+constexpr int kCascadeThreads = 128;
+
+__global__ void __launch_bounds__(kCascadeThreads) cascade_kernel(FitArgs a) {
+    const int f = blockIdx.x * kCascadeThreads + threadIdx.x;
+    if (f >= a.F || a.status[f] != EGL_FIT_NO_MODEL) return;
+    float sx[kMaxPts], sy[kMaxPts], dx[kMaxPts], dy[kMaxPts];
+    uint8_t ch[kMaxPts];
+    const int N = gather_points_thread(a, f, sx, sy, dx, dy, ch);
+    if (N <= 4) return;  // findHomography solves exactly four points without a robust method: every leg fails alike
+    double H[9];
+    uint64_t pm = 0;
+    float Hf[9];
+    int leg = EGL_FIT_LEG_RHO;
+    int count = rho_fit(sx, sy, dx, dy, N, Hf, &pm);
+    if (count > 0) {
+        for (int i = 0; i < 9; ++i) H[i] = (double)Hf[i];
+    } else {
+        double scratch[192];
+        leg = EGL_FIT_LEG_LMEDS;
+        count = lmeds_fit(sx, sy, dx, dy, N, a.confidence, H, &pm, scratch);
+        if (count < 0) return;
+    }
+    uint64_t cm = 0;
+    for (int i = 0; i < N; ++i)
+        if ((pm >> i) & 1ull) cm |= 1ull << ch[i];
+    for (int i = 0; i < 9; ++i) a.H[(size_t)f * 9 + i] = H[i];
+    a.inlier_mask[f] = cm;
+    a.status[f] = EGL_FIT_OK;
+    a.info[4 * f + 1] = count;
+    a.info[4 * f + 2] = leg;
+}
+
 }  // namespace egl
 
 using namespace egl;
@@ -1007,7 +1051,10 @@ static int fit_impl(const char* who, const int32_t* kp_xy, const uint8_t* kp_ord
         refit_kernel<<<(F + kRefitThreads - 1) / kRefitThreads, kRefitThreads, 0, s>>>(a);
     else
         refit_warp_kernel<<<(F + kRefitWarps - 1) / kRefitWarps, kRefitWarps * 32, 0, s>>>(a);
-    return cuda_status(cudaGetLastError(), "egl_fit_homography: refit kernel launch");
+    rc = cuda_status(cudaGetLastError(), "egl_fit_homography: refit kernel launch");
+    if (rc || mode != EGL_FIT_CV2_COMPAT) return rc;
+    cascade_kernel<<<(F + kCascadeThreads - 1) / kCascadeThreads, kCascadeThreads, 0, s>>>(a);
+    return cuda_status(cudaGetLastError(), "egl_fit_homography: cascade kernel launch");
 }
 
 extern "C" int egl_fit_homography(const int32_t* kp_xy, const uint8_t* kp_order, const int32_t* kp_count, int F, int mode,

@@ -212,6 +212,103 @@ EGL_HD_NOINLINE bool smallest_eigvec9(const double* A, double* aug, double* h) {
     return true;
 }
 
+// cv::eigen for a symmetric 9x9 (core/lapack.cpp JacobiImpl_, the path an OpenCV build without Eigen takes): classical
+// Jacobi with the max-off-diagonal pivot found through per-row / per-column index caches, OpenCV's own hypot, rotations
+// in its order, eigenvalues sorted descending by selection.  Bit-identical to cv2.eigen on the host build
+// (tests/test_host_core.py); used where the smallest eigenvalue of the DLT normal matrix is not isolated (LMEDS refits on
+// an inlier band that holds no common model), so that the vector picked from the near-degenerate subspace is OpenCV's.
+// A (81, destroyed), W (9), V (81: rows = eigenvectors).
+EGL_HD double cv_hypot(double a, double b) {
+    a = fabs(a);
+    b = fabs(b);
+    if (a > b) {
+        b /= a;
+        return dmul(a, sqrt(dadd(1.0, dmul(b, b))));
+    }
+    if (b > 0) {
+        a /= b;
+        return dmul(b, sqrt(dadd(1.0, dmul(a, a))));
+    }
+    return 0.0;
+}
+EGL_HD_NOINLINE void cv_jacobi9(double* A, double* W, double* V) {
+    constexpr int n = 9;
+    int indR[n], indC[n];
+    for (int i = 0; i < n * n; ++i) V[i] = 0.0;
+    for (int i = 0; i < n; ++i) V[i * n + i] = 1.0;
+    auto row_max = [&](int k) {
+        int m = k + 1;
+        double mv = fabs(A[k * n + m]);
+        for (int i = k + 2; i < n; ++i) {
+            const double val = fabs(A[k * n + i]);
+            if (mv < val) { mv = val; m = i; }
+        }
+        indR[k] = m;
+    };
+    auto col_max = [&](int k) {
+        int m = 0;
+        double mv = fabs(A[k]);
+        for (int i = 1; i < k; ++i) {
+            const double val = fabs(A[i * n + k]);
+            if (mv < val) { mv = val; m = i; }
+        }
+        indC[k] = m;
+    };
+    for (int k = 0; k < n; ++k) {
+        W[k] = A[k * n + k];
+        if (k < n - 1) row_max(k);
+        if (k > 0) col_max(k);
+    }
+    for (int iters = 0; iters < n * n * 30; ++iters) {
+        int k = 0;
+        double mv = fabs(A[indR[0]]);
+        for (int i = 1; i < n - 1; ++i) {
+            const double val = fabs(A[i * n + indR[i]]);
+            if (mv < val) { mv = val; k = i; }
+        }
+        int l = indR[k];
+        for (int i = 1; i < n; ++i) {
+            const double val = fabs(A[indC[i] * n + i]);
+            if (mv < val) { mv = val; k = indC[i]; l = i; }
+        }
+        const double p = A[k * n + l];
+        if (fabs(p) <= DBL_EPSILON) break;
+        const double y = dmul(dsub(W[l], W[k]), 0.5);
+        double t = dadd(fabs(y), cv_hypot(p, y));
+        double s = cv_hypot(p, t);
+        const double c = t / s;
+        s = p / s;
+        t = dmul(p / t, p);
+        if (y < 0) { s = -s; t = -t; }
+        A[k * n + l] = 0;
+        W[k] = dsub(W[k], t);
+        W[l] = dadd(W[l], t);
+        auto rotate = [&](double& v0, double& v1) {
+            const double a0 = v0, b0 = v1;
+            v0 = dsub(dmul(a0, c), dmul(b0, s));
+            v1 = dadd(dmul(a0, s), dmul(b0, c));
+        };
+        for (int i = 0; i < k; ++i) rotate(A[i * n + k], A[i * n + l]);
+        for (int i = k + 1; i < l; ++i) rotate(A[k * n + i], A[i * n + l]);
+        for (int i = l + 1; i < n; ++i) rotate(A[k * n + i], A[l * n + i]);
+        for (int i = 0; i < n; ++i) rotate(V[k * n + i], V[l * n + i]);
+        for (int j = 0; j < 2; ++j) {
+            const int idx = j == 0 ? k : l;
+            if (idx < n - 1) row_max(idx);
+            if (idx > 0) col_max(idx);
+        }
+    }
+    for (int k = 0; k < n - 1; ++k) {
+        int m = k;
+        for (int i = k + 1; i < n; ++i)
+            if (W[m] < W[i]) m = i;
+        if (k != m) {
+            double tmp = W[m]; W[m] = W[k]; W[k] = tmp;
+            for (int i = 0; i < n; ++i) { tmp = V[m * n + i]; V[m * n + i] = V[k * n + i]; V[k * n + i] = tmp; }
+        }
+    }
+}
+
 // Minimum-norm solution of the singular symmetric system A d = v whose null vector is x (the
 // 9-parameter homography cost is scale invariant, so J x = 0): solved through the bordered system
 // [[A, s*x],[s*x^T, 0]] [d; mu] = [v; 0].  This is what cv::solve(..., DECOMP_EIG) returns for such
@@ -241,7 +338,8 @@ EGL_HD_NOINLINE bool solve_gauge_fixed9(const double* A, const double* x, const 
 // Accumulates the 9x9 normal matrix with the block structure
 //     LtL = sum_i (b b^T) (x) [[1,0,-x],[0,1,-y],[-x,-y,x^2+y^2]],  b = (X, Y, 1) normalised.
 EGL_HD_NOINLINE bool dlt_normal_matrix(const float* sx, const float* sy, const float* dx, const float* dy,
-                                       const uint8_t* idx, int n, double* LtL, double* norm /*[8]: cM,cm,sM,sm*/) {
+                                       const uint8_t* idx, int n, double* LtL, double* norm /*[8]: cM,cm,sM,sm*/,
+                                       bool exact = false) {
     double cMx = 0, cMy = 0, cmx = 0, cmy = 0;
     for (int i = 0; i < n; ++i) {
         const int j = idx ? idx[i] : i;
@@ -267,12 +365,18 @@ EGL_HD_NOINLINE bool dlt_normal_matrix(const float* sx, const float* sy, const f
     for (int i = 0; i < 81; ++i) LtL[i] = 0.0;
     for (int i = 0; i < n; ++i) {
         const int j = idx ? idx[i] : i;
-        const double x = (dx[j] - cmx) * smx, y = (dy[j] - cmy) * smy;
-        const double X = (sx[j] - cMx) * sMx, Y = (sy[j] - cMy) * sMy;
-        const double Lx[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x};
-        const double Ly[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
-        for (int a = 0; a < 9; ++a)
-            for (int b = a; b < 9; ++b) LtL[a * 9 + b] += Lx[a] * Lx[b] + Ly[a] * Ly[b];
+        const double x = dmul(dx[j] - cmx, smx), y = dmul(dy[j] - cmy, smy);
+        const double X = dmul(sx[j] - cMx, sMx), Y = dmul(sy[j] - cMy, sMy);
+        const double Lx[9] = {X, Y, 1, 0, 0, 0, dmul(-x, X), dmul(-x, Y), -x};
+        const double Ly[9] = {0, 0, 0, X, Y, 1, dmul(-y, X), dmul(-y, Y), -y};
+        if (exact) {  // no contraction: the library's x86 build rounds every product and sum
+            for (int a = 0; a < 9; ++a)
+                for (int b = a; b < 9; ++b)
+                    LtL[a * 9 + b] = dadd(LtL[a * 9 + b], dadd(dmul(Lx[a], Lx[b]), dmul(Ly[a], Ly[b])));
+        } else {
+            for (int a = 0; a < 9; ++a)
+                for (int b = a; b < 9; ++b) LtL[a * 9 + b] += Lx[a] * Lx[b] + Ly[a] * Ly[b];
+        }
     }
     for (int a = 0; a < 9; ++a)
         for (int b = 0; b < a; ++b) LtL[a * 9 + b] = LtL[b * 9 + a];
@@ -302,13 +406,16 @@ EGL_HD void dlt_denormalise(const double* h0, const double* norm, double* H) {
 
 // runKernel on the points selected by idx[0..n).  scratch: 81 + 90 doubles.
 EGL_HD_NOINLINE bool run_kernel_ls(const float* sx, const float* sy, const float* dx, const float* dy,
-                                   const uint8_t* idx, int n, double* H, double* scratch) {
+                                   const uint8_t* idx, int n, double* H, double* scratch, bool exact = false) {
     double* LtL = scratch;
     double* aug = scratch + 81;
     double norm[8];
-    if (!dlt_normal_matrix(sx, sy, dx, dy, idx, n, LtL, norm)) return false;
+    if (!dlt_normal_matrix(sx, sy, dx, dy, idx, n, LtL, norm, exact)) return false;
     double h0[9];
-    if (!smallest_eigvec9(LtL, aug, h0)) return false;
+    if (exact) {  // OpenCV's own eigen-decomposition (see cv_jacobi9); aug has room for the 81 vectors + 9 values
+        cv_jacobi9(LtL, aug + 81, aug);
+        for (int i = 0; i < 9; ++i) h0[i] = aug[8 * 9 + i];
+    } else if (!smallest_eigvec9(LtL, aug, h0)) return false;
     dlt_denormalise(h0, norm, H);
     for (int i = 0; i < 9; ++i)
         if (!isfinite(H[i])) return false;
@@ -542,8 +649,8 @@ EGL_HD_NOINLINE void eig_threshold_solve9(const double* Ain, const double* b, do
 constexpr int kLmExactMaxPoints = 9;
 
 EGL_HD_NOINLINE int lm_refine(double* H, const float* sx, const float* sy, const float* dx, const float* dy,
-                              const uint8_t* idx, int n, double* scratch) {
-    const bool exact_small = n <= kLmExactMaxPoints;
+                              const uint8_t* idx, int n, double* scratch, bool always_exact = false) {
+    const bool exact_small = always_exact || n <= kLmExactMaxPoints;
     double* A = scratch;         // J^T J
     double* aug = scratch + 81;  // 10 x 11 augmented system
     double x[9], xd[9], v[9], d[9], D[9];
@@ -556,7 +663,12 @@ EGL_HD_NOINLINE int lm_refine(double* H, const float* sx, const float* sy, const
     int iter = 0;
     for (;;) {
         bool ok;
-        if (lambda > 0) {
+        if (lambda > 0 && always_exact) {  // cv::solve(DECOMP_EIG) on the damped system as well (see lmeds_fit)
+            for (int i = 0; i < 81; ++i) aug[i] = A[i];
+            for (int i = 0; i < 9; ++i) aug[i * 9 + i] += lambda * D[i];
+            eig_threshold_solve9(aug, v, d, nullptr);
+            ok = true;
+        } else if (lambda > 0) {
             for (int i = 0; i < 9; ++i) {
                 for (int j = 0; j < 9; ++j) aug[i * 10 + j] = A[i * 9 + j];
                 aug[i * 10 + i] += lambda * D[i];
@@ -646,15 +758,16 @@ EGL_HD int inlier_mask_f32(const double* H, const float* sx, const float* sy, co
 // The tail of cv2.findHomography after RANSAC picked `H` (best model) with inlier list mask:
 // runKernel on the inliers, LM polish, mask recomputed from the refined H.  scratch >= 192 doubles.
 EGL_HD_NOINLINE int refit_on_inliers(double* H, const float* sx, const float* sy, const float* dx, const float* dy, int n,
-                                     uint64_t ransac_mask, float thr_sq, uint64_t* final_mask, double* scratch) {
+                                     uint64_t ransac_mask, float thr_sq, uint64_t* final_mask, double* scratch,
+                                     bool always_exact = false) {
     uint8_t idx[64];
     int m = 0;
     for (int i = 0; i < n; ++i)
         if ((ransac_mask >> i) & 1) idx[m++] = (uint8_t)i;
     double Hk[9];
-    if (run_kernel_ls(sx, sy, dx, dy, idx, m, Hk, scratch))
+    if (run_kernel_ls(sx, sy, dx, dy, idx, m, Hk, scratch, always_exact))
         for (int i = 0; i < 9; ++i) H[i] = Hk[i];
-    lm_refine(H, sx, sy, dx, dy, idx, m, scratch);
+    lm_refine(H, sx, sy, dx, dy, idx, m, scratch, always_exact);
     return inlier_mask_f32(H, sx, sy, dx, dy, n, thr_sq, final_mask);
 }
 

@@ -42,13 +42,17 @@ extern "C" {
 /* status[] values written by egl_fit_homography */
 #define EGL_FIT_OK 0         /* H, masks valid */
 #define EGL_FIT_FEW_POINTS 1 /* < 4 on-plane landmarks: reference sets compute_homography=True (:350-352) */
-#define EGL_FIT_NO_MODEL 2   /* RANSAC found no model (cv2.findHomography returned None, :363-367) */
+#define EGL_FIT_NO_MODEL 2   /* no leg of the cascade found a model (cv2.findHomography returned None three times, :363-367) */
 #define EGL_FIT_SKIPPED 3    /* egl_fit_homography_masked: the cadence did not ask for a fit on this frame */
 
 /* kp_src[] values: which Python type the reference holds a keypoint value in (it reaches the JSON) */
 #define EGL_KP_PY_INT 0    /* tuple of int: decoded (:248) or synthesised (:179) */
 #define EGL_KP_NUMPY_INT 1 /* tuple of numpy int64: optical flow (:476) or calibration (:553) */
 #define EGL_KP_FLOAT 2     /* list of float: inlier of a successful fit (:361) */
+
+/* info[2] of a frame whose H comes from a later leg of `for method in [cv2.RANSAC, cv2.RHO, cv2.LMEDS]` (:354) */
+#define EGL_FIT_LEG_RHO (-2)
+#define EGL_FIT_LEG_LMEDS (-3)
 
 /* fit modes */
 #define EGL_FIT_CV2_COMPAT 1 /* OpenCV's RNG, sampling, adaptive stopping: picks the model cv2 picks */
@@ -133,7 +137,9 @@ int egl_synthesize_keypoints(int32_t *kp_xy, uint8_t *kp_order, int32_t *kp_coun
  * Replaces the correspondence gather (coordinate_model.py:335-349: on-plane channels of kp_order,
  * in order) and cv2.findHomography(img_pts, world_pts, cv2.RANSAC, 5.0) (:354-357), including
  * OpenCV's least-squares refit on the inliers, Levenberg-Marquardt polish and the final mask
- * recomputed from the refined H.
+ * recomputed from the refined H.  In mode EGL_FIT_CV2_COMPAT a frame the RANSAC leg leaves without a model goes
+ * through the rest of the reference's cascade, cv2.findHomography(..., cv2.RHO, None) and then
+ * (..., cv2.LMEDS, None) (:354-357); info[2] says which leg produced H.
  *   mode EGL_FIT_CV2_COMPAT: K = iteration cap (2000 = OpenCV's default), hyp/seed ignored.
  *   mode EGL_FIT_FIXED_K:    K hypotheses per frame; hyp = [F][K][4] uint8 indices into the frame's
  *                            point list, or NULL to draw them from the counter-based generator (seed).
@@ -141,7 +147,7 @@ int egl_synthesize_keypoints(int32_t *kp_xy, uint8_t *kp_order, int32_t *kp_coun
  *   H         [F][9] float64 row-major, H[8] == 1 (unchanged when status != EGL_FIT_OK)
  *   used_mask / inlier_mask [F] uint64, bit = channel
  *   status    [F] int32 (EGL_FIT_*)
- *   info      [F][4] int32 {points used, inliers, winning hypothesis index, hypotheses evaluated}
+ *   info      [F][4] int32 {points used, inliers, winning hypothesis index (or EGL_FIT_LEG_*), hypotheses evaluated}
  */
 int egl_fit_homography(const int32_t *kp_xy, const uint8_t *kp_order, const int32_t *kp_count, int F, int mode,
                        int K, const uint8_t *hyp, uint64_t seed, double thr, double confidence, double *H,

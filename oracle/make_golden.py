@@ -168,6 +168,44 @@ def find_homography_fixture():
     print("find_homography_cv2", len(cases), "none:", int(np.isnan(H_a[:, 0, 0]).sum()))
 
 
+def cascade_fixture(want=((-1, 120), (0, 40), (1, 100), (2, 100))):
+    """The whole cascade of coordinate_model.py:354-357 on live cv2 for point sets on which the RANSAC leg returns None
+    (families of tools/cascade_census.py: outlier-heavy camera views, points on one or two pitch lines, garbage,
+    near-collinear / repeated / tiny-spread pixels) plus a few ordinary ones: which leg answered (want = how many sets
+    per answering leg, -1 = none did), its H and mask."""
+    from tools.cascade_census import FAMILIES, _world, make_set
+    world, on = _world()
+    rng = np.random.default_rng(2024)
+    want, have = dict(want), {k: 0 for k, _ in want}
+    cases, t = [], 0
+    while any(have[k] < want[k] for k in want):
+        fam = FAMILIES[t % len(FAMILIES)]; t += 1
+        img, wor, sel = make_set(rng, fam, world, on, return_sel=True)
+        if len(img) < 5:
+            continue
+        leg, Hm, mask = -1, None, None
+        for k, (method, thr) in enumerate(((cv2.RANSAC, 5.0), (cv2.RHO, None), (cv2.LMEDS, None))):
+            Hm, mask = cv2.findHomography(img, wor, method, thr)
+            if Hm is not None:
+                leg = k
+                break
+        if have[leg] >= want[leg]:
+            continue
+        have[leg] += 1
+        cases.append((sel, img, leg, Hm, mask))
+    nmax = 16
+    T = len(cases)
+    sel_a = np.full((T, nmax), -1, np.int32); img_a = np.zeros((T, nmax, 2), np.float32); n_a = np.zeros(T, np.int32)
+    H_a = np.full((T, 3, 3), np.nan); m_a = np.zeros((T, nmax), np.uint8); leg_a = np.zeros(T, np.int32)
+    for i, (sel, img, leg, Hm, mask) in enumerate(cases):
+        n = len(sel); n_a[i] = n; sel_a[i, :n] = sel; img_a[i, :n] = img; leg_a[i] = leg
+        if Hm is not None:
+            H_a[i] = Hm; m_a[i, :n] = mask.ravel()
+    np.savez_compressed(os.path.join(GOLDEN, "cascade_cv2.npz"), n=n_a, channels=sel_a, img_pts=img_a, leg=leg_a, H=H_a, mask=m_a,
+                        cv2_version=cv2.__version__)
+    print("cascade_cv2", T, "by leg (-1 none, 0 RANSAC, 1 RHO, 2 LMEDS):", {int(k): int((leg_a == k).sum()) for k in np.unique(leg_a)})
+
+
 def resize_fixture():
     """Checksums of the live cv2.resize(..., (960,540), INTER_LINEAR) output on seeded frames."""
     out = {}
@@ -210,6 +248,7 @@ def main():
     flow_fixture("ref_flow_360p.npz", 26, 640, 360, seed=31, fps=24, num_homography=1, num_keypoint_detection=3, pan_px=2.0)
     decode_fixture()
     find_homography_fixture()
+    cascade_fixture()
     resize_fixture()
 
 

@@ -996,7 +996,7 @@ def find_homography_lmeds(img_pts, world_pts, thresh=None, max_iters=2000, confi
     min_median, best = float("inf"), None
     for it in range(niters):
         found = False
-        for _ in range(10000):
+        for _ in range(1000):   # getSubset default maxAttempts (the RANSAC leg passes 10000)
             idx = hg.draw_subset(rng, count)
             if hg.check_subset(src[idx], dst[idx]):
                 found = True

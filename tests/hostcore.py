@@ -14,6 +14,7 @@ SRC = os.path.join(HERE, "native", "host_check.cpp")
 LIB = os.path.join(HERE, "native", "libhostcheck.so")
 CORE = os.path.join(os.path.dirname(HERE), "eagle_b200", "csrc", "geometry_core.cuh")
 FLOW_CORE = os.path.join(os.path.dirname(HERE), "eagle_b200", "csrc", "flow_core.cuh")
+CASCADE_CORE = [os.path.join(os.path.dirname(HERE), "eagle_b200", "csrc", n) for n in ("cascade_core.cuh", "rho_hfunc.inc", "rho_lmstep.inc")]
 
 _lib = None
 
@@ -21,7 +22,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        stale = (not os.path.exists(LIB)) or any(os.path.getmtime(p) > os.path.getmtime(LIB) for p in (SRC, CORE, FLOW_CORE))
+        stale = (not os.path.exists(LIB)) or any(os.path.getmtime(p) > os.path.getmtime(LIB) for p in (SRC, CORE, FLOW_CORE, *CASCADE_CORE))
         if stale:
             subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", LIB, SRC])
         _lib = C.CDLL(LIB)
@@ -45,6 +46,27 @@ def fit_cv2(img_pts, world_pts, thr=5.0, confidence=0.995, max_iters=2000):
                           C.c_double(thr), C.c_double(confidence), max_iters, _p(H, C.c_double), C.byref(mask), _p(info, C.c_int32))
     m = np.array([(mask.value >> i) & 1 for i in range(len(sx))], np.uint8)
     return st, H.reshape(3, 3), m, info
+
+
+def fit_rho(img_pts, world_pts):
+    """cascade_core.cuh rho_fit -> (inlier count (0 = no model), H float32 3x3, mask)."""
+    sx, sy, dx, dy = split(img_pts, world_pts)
+    H = np.zeros(9, np.float32); mask = C.c_uint64(0)
+    n = lib().hc_fit_rho(_p(sx, C.c_float), _p(sy, C.c_float), _p(dx, C.c_float), _p(dy, C.c_float), len(sx), _p(H, C.c_float),
+                         C.byref(mask))
+    m = np.array([(mask.value >> i) & 1 for i in range(len(sx))], np.uint8)
+    return n, H.reshape(3, 3), m
+
+
+def fit_lmeds(img_pts, world_pts, confidence=0.995):
+    """cascade_core.cuh lmeds_fit -> (final inlier count (0 = no model), H 3x3, mask)."""
+    sx, sy, dx, dy = split(img_pts, world_pts)
+    H = np.zeros(9); mask = C.c_uint64(0); band = C.c_uint64(0)
+    n = lib().hc_fit_lmeds(_p(sx, C.c_float), _p(sy, C.c_float), _p(dx, C.c_float), _p(dy, C.c_float), len(sx),
+                           C.c_double(confidence), _p(H, C.c_double), C.byref(mask), C.byref(band))
+    m = np.array([(mask.value >> i) & 1 for i in range(len(sx))], np.uint8)
+    fit_lmeds.band = np.array([(band.value >> i) & 1 for i in range(len(sx))], np.uint8)
+    return n, H.reshape(3, 3), m
 
 
 def fixedk_stage(img_pts, world_pts, K, hyp=None, seed=0, frame=0, thr=5.0):

@@ -7,6 +7,7 @@
 #include "../../include/eagle_b200.h"
 #include "../../eagle_b200/csrc/geometry_core.cuh"
 #include "../../eagle_b200/csrc/flow_core.cuh"
+#include "../../eagle_b200/csrc/cascade_core.cuh"
 #include <vector>
 
 namespace egl {
@@ -109,6 +110,34 @@ int hc_refit(double* H, const float* sx, const float* sy, const float* dx, const
              double thr, uint64_t* final_mask) {
     double scratch[192];
     return refit_on_inliers(H, sx, sy, dx, dy, N, ransac_mask, (float)(thr * thr), final_mask, scratch);
+}
+
+// the RHO / LMEDS legs of the cascade (cascade_core.cuh) for one point list
+int hc_fit_rho(const float* sx, const float* sy, const float* dx, const float* dy, int N, float* H, uint64_t* mask) {
+    return rho_fit(sx, sy, dx, dy, N, H, mask);
+}
+int hc_fit_lmeds(const float* sx, const float* sy, const float* dx, const float* dy, int N, double confidence, double* H,
+                 uint64_t* mask, uint64_t* band_mask) {
+    double scratch[192];
+    return lmeds_fit(sx, sy, dx, dy, N, confidence, H, mask, scratch, band_mask);
+}
+void hc_cv_jacobi9(double* A, double* W, double* V) { cv_jacobi9(A, W, V); }
+int hc_run_kernel_ls(const float* sx, const float* sy, const float* dx, const float* dy, int N, double* H) {
+    double scratch[192];
+    uint8_t idx[64];
+    for (int i = 0; i < N; ++i) idx[i] = (uint8_t)i;
+    return run_kernel_ls(sx, sy, dx, dy, idx, N, H, scratch);
+}
+int hc_lm_refine(double* H, const float* sx, const float* sy, const float* dx, const float* dy, int N, int always_exact) {
+    double scratch[192];
+    uint8_t idx[64];
+    for (int i = 0; i < N; ++i) idx[i] = (uint8_t)i;
+    return lm_refine(H, sx, sy, dx, dy, idx, N, scratch, always_exact != 0);
+}
+int hc_refit_exact(double* H, const float* sx, const float* sy, const float* dx, const float* dy, int N, uint64_t ransac_mask,
+                   double thr, uint64_t* final_mask) {
+    double scratch[192];
+    return refit_on_inliers(H, sx, sy, dx, dy, N, ransac_mask, (float)(thr * thr), final_mask, scratch, true);
 }
 
 int hc_dlt4_f64(const float* sx, const float* sy, const float* dx, const float* dy, double* H) { return dlt4_f64(sx, sy, dx, dy, H); }

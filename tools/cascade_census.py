@@ -46,8 +46,8 @@ def _camera(rng, W=1920, H=1080):
     return P[:, [0, 1, 3]]
 
 
-def make_set(rng, family, world, on):
-    """-> (img (n,2) float32, wor (n,2) float32); integer pixel positions like the reference's keypoints."""
+def make_set(rng, family, world, on, return_sel=False):
+    """-> (img (n,2) float32, wor (n,2) float32[, landmark indices]); integer pixel positions like the reference's keypoints."""
     lines_x = {}
     lines_y = {}
     for i in on:
@@ -93,7 +93,8 @@ def make_set(rng, family, world, on):
         img[flip, 0] = 1920 - img[flip, 0]
     elif family == "tiny_spread":
         img = rng.uniform(0, (1920, 1080), 2) + rng.integers(-3, 4, (n, 2))
-    return np.floor(np.clip(img, -4000, 6000)).astype(np.float32), wor.astype(np.float32)
+    img = np.floor(np.clip(img, -4000, 6000)).astype(np.float32)
+    return (img, wor.astype(np.float32), sel) if return_sel else (img, wor.astype(np.float32))
 
 
 def worker(args):
