@@ -323,7 +323,62 @@ __device__ __forceinline__ float warp_tree_sum_f32(float lo, float hi) {  // tre
     return t;
 }
 
-__global__ void __launch_bounds__(kFixedThreads, 6) ransac_fixedk_kernel(FitArgs a, float inv_thr, double thr) {
+// Per-frame input of the hypothesis kernel, written by fixedk_prepare_kernel: the gathered correspondences, their
+// normalised form (X', x', Y', y') and the normalisation.  2.1 KB per frame in a stream-ordered scratch allocation.
+struct FixedKPrep {
+    float4 ps[kMaxPts];
+    float sx[kMaxPts], sy[kMaxPts], dx[kMaxPts], dy[kMaxPts];
+    uint8_t ch[kMaxPts];
+    FixedKNorm nm;
+    int N, ok;
+    unsigned long long used;
+};
+
+// Gather + normalise, one warp per frame.  This is a chain of dependent global loads (count -> order -> positions) and
+// shuffle reductions: inside the hypothesis kernel it kept three of a CTA's four warps waiting for ~10 % of the CTA's
+// life; here thousands of frames are in flight at once and the latency disappears behind them.
+constexpr int kPrepWarps = 8;
+__global__ void __launch_bounds__(kPrepWarps * 32) fixedk_prepare_kernel(FitArgs a, float inv_thr, FixedKPrep* prep) {
+    __shared__ PointList s_pl[kPrepWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * kPrepWarps + warp;
+    if (f >= a.F || fit_skipped(a, f)) return;
+    PointList& pl = s_pl[warp];
+    FixedKPrep& o = prep[f];
+    uint64_t used;
+    const int n = gather_points_warp(a, f, pl, &used);
+    // fixedk_normalise, lanes as the partial sums of the tree order
+    const bool v0 = lane < n, v1 = lane + 32 < n;
+    const float X0 = v0 ? pl.sx[lane] : 0.f, X1 = v1 ? pl.sx[lane + 32] : 0.f;
+    const float Y0 = v0 ? pl.sy[lane] : 0.f, Y1 = v1 ? pl.sy[lane + 32] : 0.f;
+    const float x0 = v0 ? pl.dx[lane] : 0.f, x1 = v1 ? pl.dx[lane + 32] : 0.f;
+    const float y0 = v0 ? pl.dy[lane] : 0.f, y1 = v1 ? pl.dy[lane + 32] : 0.f;
+    const float fn = (float)n;
+    FixedKNorm nm;
+    nm.cX = fdiv(warp_tree_sum_f32(X0, X1), fn); nm.cY = fdiv(warp_tree_sum_f32(Y0, Y1), fn);
+    nm.cx = fdiv(warp_tree_sum_f32(x0, x1), fn); nm.cy = fdiv(warp_tree_sum_f32(y0, y1), fn);
+    const float aX = warp_tree_sum_f32(v0 ? fabsf(fsub(X0, nm.cX)) : 0.f, v1 ? fabsf(fsub(X1, nm.cX)) : 0.f);
+    const float aY = warp_tree_sum_f32(v0 ? fabsf(fsub(Y0, nm.cY)) : 0.f, v1 ? fabsf(fsub(Y1, nm.cY)) : 0.f);
+    nm.sX = fdiv(fn, aX); nm.sY = fdiv(fn, aY); nm.rt = inv_thr;
+    if (lane == 0) {
+        o.N = n;
+        o.used = used;
+        o.ok = n >= 4 && aX > 0.f && aY > 0.f;
+        o.nm = nm;
+    }
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int i = pass * 32 + lane;
+        if (i >= n) continue;
+        float q[4];
+        fixedk_normalise_point(nm, pl.sx[i], pl.sy[i], pl.dx[i], pl.dy[i], q);
+        o.ps[i] = make_float4(q[0], q[2], q[1], q[3]);
+        o.sx[i] = pl.sx[i]; o.sy[i] = pl.sy[i]; o.dx[i] = pl.dx[i]; o.dy[i] = pl.dy[i];
+        o.ch[i] = pl.ch[i];
+    }
+}
+
+__global__ void __launch_bounds__(kFixedThreads, 6) ransac_fixedk_kernel(FitArgs a, float inv_thr, double thr, const FixedKPrep* prep) {
     __shared__ PointList s_pl;
     // normalised points as (X', x', Y', y') -- image/pitch pairs for the sample test -- replicated into the eight
     // 16-byte columns of a 128-byte row: lane l gathers from column l & 7, so the eight lanes of a quarter warp never
@@ -337,7 +392,7 @@ __global__ void __launch_bounds__(kFixedThreads, 6) ransac_fixedk_kernel(FitArgs
     __shared__ uint32_t s_pi[kFixedWarps * 64];          // what the warps had left over, pooled
     __shared__ int s_ph[kFixedWarps * 64];
     __shared__ FixedKNorm s_nm;
-    __shared__ int s_N, s_ok, s_pool;
+    __shared__ int s_N, s_pool;
     __shared__ unsigned long long s_used;
     const int f = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -345,48 +400,31 @@ __global__ void __launch_bounds__(kFixedThreads, 6) ransac_fixedk_kernel(FitArgs
         if (tid == 0) park_skipped(a, f);
         return;
     }
-    if (warp == 0) {
-        uint64_t used;
-        const int n = gather_points_warp(a, f, s_pl, &used);
-        // fixedk_normalise, lanes as the partial sums of the tree order
-        const bool v0 = lane < n, v1 = lane + 32 < n;
-        const float X0 = v0 ? s_pl.sx[lane] : 0.f, X1 = v1 ? s_pl.sx[lane + 32] : 0.f;
-        const float Y0 = v0 ? s_pl.sy[lane] : 0.f, Y1 = v1 ? s_pl.sy[lane + 32] : 0.f;
-        const float x0 = v0 ? s_pl.dx[lane] : 0.f, x1 = v1 ? s_pl.dx[lane + 32] : 0.f;
-        const float y0 = v0 ? s_pl.dy[lane] : 0.f, y1 = v1 ? s_pl.dy[lane + 32] : 0.f;
-        const float fn = (float)n;
-        FixedKNorm nm;
-        nm.cX = fdiv(warp_tree_sum_f32(X0, X1), fn); nm.cY = fdiv(warp_tree_sum_f32(Y0, Y1), fn);
-        nm.cx = fdiv(warp_tree_sum_f32(x0, x1), fn); nm.cy = fdiv(warp_tree_sum_f32(y0, y1), fn);
-        const float aX = warp_tree_sum_f32(v0 ? fabsf(fsub(X0, nm.cX)) : 0.f, v1 ? fabsf(fsub(X1, nm.cX)) : 0.f);
-        const float aY = warp_tree_sum_f32(v0 ? fabsf(fsub(Y0, nm.cY)) : 0.f, v1 ? fabsf(fsub(Y1, nm.cY)) : 0.f);
-        nm.sX = fdiv(fn, aX); nm.sY = fdiv(fn, aY); nm.rt = inv_thr;
-        if (lane == 0) {
-            s_N = n;
-            s_used = used;
-            s_ok = n >= 4 && aX > 0.f && aY > 0.f;
-            s_nm = nm;
-            s_pool = 0;
-        }
-    }
-    __syncthreads();
-    const int N = s_N;
-    if (N < 4 || !s_ok) {
-        if (tid == 0) park(a, f, N < 4 ? EGL_FIT_FEW_POINTS : EGL_FIT_NO_MODEL, N, 0, -1, 0, nullptr, 0, s_used);
+    const FixedKPrep& in = prep[f];
+    const int N = in.N;
+    if (N < 4 || !in.ok) {
+        if (tid == 0) park(a, f, N < 4 ? EGL_FIT_FEW_POINTS : EGL_FIT_NO_MODEL, N, 0, -1, 0, nullptr, 0, in.used);
         return;
     }
+    if (tid == 0) {
+        s_N = N;
+        s_used = in.used;
+        s_nm = in.nm;
+        s_pool = 0;
+    }
     const int N4 = (N + 3) & ~3;
-    for (int e = tid; e < N4 * 8; e += kFixedThreads) {
-        const int i = e >> 3, col = e & 7;
+    for (int i = tid; i < N4; i += kFixedThreads) {
         if (i < N) {
-            float o[4];
-            fixedk_normalise_point(s_nm, s_pl.sx[i], s_pl.sy[i], s_pl.dx[i], s_pl.dy[i], o);
-            s_ps[i][col] = make_float4(o[0], o[2], o[1], o[3]);
-            if (col == 0) s_bc[i][0] = make_float4(o[0], o[0], o[1], o[1]);
-            if (col == 1) s_bc[i][1] = make_float4(-o[2], -o[2], -o[3], -o[3]);
-        } else if (col < 2) {  // padding rows: NaN residuals are never counted
-            const float q = col ? __int_as_float(0x7fffffff) : 0.f;
-            s_bc[i][col] = make_float4(q, q, q, q);
+            const float4 q = in.ps[i];  // (X', x', Y', y')
+#pragma unroll
+            for (int col = 0; col < 8; ++col) s_ps[i][col] = q;
+            s_bc[i][0] = make_float4(q.x, q.x, q.z, q.z);
+            s_bc[i][1] = make_float4(-q.y, -q.y, -q.w, -q.w);
+            s_pl.sx[i] = in.sx[i]; s_pl.sy[i] = in.sy[i]; s_pl.dx[i] = in.dx[i]; s_pl.dy[i] = in.dy[i];
+        } else {  // padding rows: NaN residuals are never counted
+            const float q = __int_as_float(0x7fffffff);
+            s_bc[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            s_bc[i][1] = make_float4(q, q, q, q);
         }
     }
     __syncthreads();
@@ -1033,7 +1071,13 @@ static int fit_impl(const char* who, const int32_t* kp_xy, const uint8_t* kp_ord
     if (mode == EGL_FIT_CV2_COMPAT) {
         ransac_cv2_kernel<<<(F + kCv2Warps - 1) / kCv2Warps, kCv2Warps * 32, 0, s>>>(a);
     } else {
-        ransac_fixedk_kernel<<<F, kFixedThreads, 0, s>>>(a, (float)(1.0 / thr), thr);
+        // scratch for the prepared frames: stream-ordered, so the free below only takes effect after the kernels
+        FixedKPrep* prep = nullptr;
+        int rc0 = cuda_status(cudaMallocAsync((void**)&prep, sizeof(FixedKPrep) * (size_t)F, s), "egl_fit_homography: scratch allocation");
+        if (rc0) return rc0;
+        fixedk_prepare_kernel<<<(F + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, 0, s>>>(a, (float)(1.0 / thr), prep);
+        ransac_fixedk_kernel<<<F, kFixedThreads, 0, s>>>(a, (float)(1.0 / thr), thr, prep);
+        cudaFreeAsync(prep, s);
     }
     int rc = cuda_status(cudaGetLastError(), "egl_fit_homography: hypothesis kernel launch");
     if (rc) return rc;

@@ -197,3 +197,24 @@ def test_rho_lmeds_fallbacks_do_not_rescue_fully_degenerate_sets():
         assert (Hr is None) == (Hc is None)
         n_none += Hr is None
     assert n_none > 60
+
+
+def test_goldens_belong_to_this_opencv(golden_dir):
+    """Parity is claimed against the OpenCV the goldens were minted with (4.13.0, the cv2 of this image; the reference's
+    uv.lock pins 4.11.0.86, which is not installable offline -- tests/golden/README.md).  Fixtures that carry the version
+    must match the cv2 the tests run against; the others (minted before the stamp existed) are re-checked live by
+    tests/test_oracle_vs_reference.py whenever /root/reference is mounted."""
+    import glob
+    stamped = 0
+    for path in sorted(glob.glob(os.path.join(golden_dir, "*"))):
+        if path.endswith(".npz"):
+            g = np.load(path)
+            v = str(g["cv2_version"]) if "cv2_version" in g else None
+        elif path.endswith(".json"):
+            v = json.load(open(path)).get("cv2_version")
+        else:
+            continue
+        if v is not None:
+            stamped += 1
+            assert v == cv2.__version__, (path, v)
+    assert stamped >= 4
