@@ -21,6 +21,7 @@
 namespace egl {
 
 constexpr int kMaxPtsCascade = 64;  // = kMaxPts (common.cuh), which the host build does not include
+constexpr int kLmedsMaxIters = 64;
 
 // ---- RHO_HEST_REFC::fastSeed / fastRandom -------------------------------------------------------------------------
 struct XorShift128Plus {
@@ -347,23 +348,24 @@ EGL_HD int lmeds_key(float e) {
 #endif
 }
 
-// LMeDSPointSetRegistrator::run + the common tail of findHomography.  N >= 5.  Returns the final inlier count (which may
-// be 0: cv2 still returns the refined H then), or -1 when the leg returns no model; H (double, h33 = 1) and *mask as for
-// the RANSAC leg.  scratch >= 192 doubles.
-EGL_HD_NOINLINE int lmeds_fit(const float* sx, const float* sy, const float* dx, const float* dy, int N, double confidence,
-                              double* H, uint64_t* mask, double* scratch, uint64_t* band_mask = nullptr) {
+// LMeDSPointSetRegistrator::run + the common tail of findHomography, in three pieces so that cascade_kernel can rate the
+// samples on the lanes of a warp (the sample SEQUENCE is a walk of cv::RNG, the rating of a sample depends on nothing
+// else) while the host build and lmeds_fit() below run them one after the other.
+//
+// 1. the sample sequence: up to `niters` (55 at OpenCV's defaults) accepted 4-subsets; -1 = the leg fails at once
+EGL_HD_NOINLINE int lmeds_draw_samples(const float* sx, const float* sy, const float* dx, const float* dy, int N, double confidence,
+                                       uint8_t (*smp)[4]) {
     CvRng rng{~0ull};
     int niters = ransac_update_num_iters(confidence, 0.45, 4, 2000);
     if (niters < 3) niters = 3;
-    double min_median = DBL_MAX;
-    double best[9];
-    bool have = false;
+    if (niters > kLmedsMaxIters) niters = kLmedsMaxIters;
+    int n_smp = 0;
     for (int iter = 0; iter < niters; ++iter) {
         int idx[4];
-        float qx[4], qy[4], rx[4], ry[4];
         bool found = false;
         for (int attempt = 0; attempt < 1000 && !found; ++attempt) {  // getSubset default maxAttempts (the RANSAC leg passes 10000)
             draw_subset(rng, N, idx);
+            float qx[4], qy[4], rx[4], ry[4];
             for (int k = 0; k < 4; ++k) {
                 qx[k] = sx[idx[k]];
                 qy[k] = sy[idx[k]];
@@ -376,38 +378,53 @@ EGL_HD_NOINLINE int lmeds_fit(const float* sx, const float* sy, const float* dx,
             if (iter == 0) return -1;
             break;
         }
-        double Hm[9];
-        if (!run_kernel_ls(qx, qy, rx, ry, nullptr, 4, Hm, scratch, true)) continue;  // runKernel as OpenCV runs it: the median decides by a rounding
-        float Hf[8];
-        for (int i = 0; i < 8; ++i) Hf[i] = (float)Hm[i];
-        int key[kMaxPtsCascade];
-        float err[kMaxPtsCascade];
-        for (int i = 0; i < N; ++i) {
-            err[i] = reproj_err_f32(Hf, sx[i], sy[i], dx[i], dy[i]);
-            key[i] = lmeds_key(err[i]);
+        for (int k = 0; k < 4; ++k) smp[n_smp][k] = (uint8_t)idx[k];
+        ++n_smp;
+    }
+    return n_smp;
+}
+
+// 2. one sample: runKernel as OpenCV runs it (normal matrix + its Jacobi eigen-decomposition: the median decides by a
+//    rounding) and element N/2 of the sorted float errors (std::nth_element on the int view).  false = no model.
+EGL_HD_NOINLINE bool lmeds_rate_sample(const float* sx, const float* sy, const float* dx, const float* dy, int N, const uint8_t* smp4,
+                                       double* Hm, double* median, double* scratch) {
+    float qx[4], qy[4], rx[4], ry[4];
+    for (int k = 0; k < 4; ++k) {
+        qx[k] = sx[smp4[k]];
+        qy[k] = sy[smp4[k]];
+        rx[k] = dx[smp4[k]];
+        ry[k] = dy[smp4[k]];
+    }
+    if (!run_kernel_ls(qx, qy, rx, ry, nullptr, 4, Hm, scratch, true)) return false;
+    float Hf[8];
+    for (int i = 0; i < 8; ++i) Hf[i] = (float)Hm[i];
+    int key[kMaxPtsCascade];
+    float err[kMaxPtsCascade];
+    for (int i = 0; i < N; ++i) {
+        err[i] = reproj_err_f32(Hf, sx[i], sy[i], dx[i], dy[i]);
+        key[i] = lmeds_key(err[i]);
+    }
+    const int want = N / 2;
+    float med = 0.f;
+    for (int i = 0; i < N; ++i) {
+        int less = 0, equal = 0;
+        for (int j = 0; j < N; ++j) {
+            less += key[j] < key[i];
+            equal += key[j] == key[i];
         }
-        // element N/2 of the sorted keys
-        const int want = N / 2;
-        float med = 0.f;
-        for (int i = 0; i < N; ++i) {
-            int less = 0, equal = 0;
-            for (int j = 0; j < N; ++j) {
-                less += key[j] < key[i];
-                equal += key[j] == key[i];
-            }
-            if (less <= want && want < less + equal) {
-                med = err[i];
-                break;
-            }
-        }
-        const double median = (double)med;
-        if (median < min_median) {
-            min_median = median;
-            for (int i = 0; i < 9; ++i) best[i] = Hm[i];
-            have = true;
+        if (less <= want && want < less + equal) {
+            med = err[i];
+            break;
         }
     }
-    if (!have) return -1;
+    *median = (double)med;
+    return true;
+}
+
+// 3. from the model of the smallest median: inlier band, refit on the band, final mask at the default threshold 3.
+//    Returns the final inlier count (may be 0: cv2 still returns the refined H), or -1 when the band holds < 4 points.
+EGL_HD_NOINLINE int lmeds_finish(const float* sx, const float* sy, const float* dx, const float* dy, int N, const double* best,
+                                 double min_median, double* H, uint64_t* mask, double* scratch, uint64_t* band_mask = nullptr) {
     double sigma = dmul(dmul(dmul(2.5, 1.4826), dadd(1.0, 5.0 / (double)(N - 4))), sqrt(min_median));
     if (!(sigma > 0.001)) sigma = 0.001;   // MAX(sigma, 0.001); a NaN sigma also ends up here, as MAX's `a > b ? a : b` does
     uint64_t pm;
@@ -416,8 +433,31 @@ EGL_HD_NOINLINE int lmeds_fit(const float* sx, const float* sy, const float* dx,
     if (good < 4) return -1;
     for (int i = 0; i < 9; ++i) H[i] = best[i];
     // the band may hold points that fit no common model, so the LM system has no margin over OpenCV's eigenvalue
-    // threshold at any set size: always solve the undamped steps the way cv::solve(DECOMP_EIG) does
+    // threshold at any set size: always solve the LM steps the way cv::solve(DECOMP_EIG) does
     return refit_on_inliers(H, sx, sy, dx, dy, N, pm, 9.0f, mask, scratch, true);
+}
+
+// The whole leg on one thread.  N >= 5.  Returns the final inlier count or -1 (no model); H (double, h33 = 1) and *mask
+// as for the RANSAC leg.  scratch >= 192 doubles.
+EGL_HD_NOINLINE int lmeds_fit(const float* sx, const float* sy, const float* dx, const float* dy, int N, double confidence,
+                              double* H, uint64_t* mask, double* scratch, uint64_t* band_mask = nullptr) {
+    uint8_t smp[kLmedsMaxIters][4];
+    const int n_smp = lmeds_draw_samples(sx, sy, dx, dy, N, confidence, smp);
+    if (n_smp < 0) return -1;
+    double min_median = DBL_MAX;
+    double best[9];
+    bool have = false;
+    for (int t = 0; t < n_smp; ++t) {
+        double Hm[9], median;
+        if (!lmeds_rate_sample(sx, sy, dx, dy, N, smp[t], Hm, &median, scratch)) continue;
+        if (median < min_median) {  // the first sample of the smallest median wins
+            min_median = median;
+            for (int i = 0; i < 9; ++i) best[i] = Hm[i];
+            have = true;
+        }
+    }
+    if (!have) return -1;
+    return lmeds_finish(sx, sy, dx, dy, N, best, min_median, H, mask, scratch, band_mask);
 }
 
 }  // namespace egl

@@ -13,9 +13,10 @@
 //                       by the same thread with a division-free test (13 FP32 ops per point);
 //                       block-wide arg-max (ties -> lowest hypothesis index).  FP32-ALU bound.
 //   cascade_kernel      (mode EGL_FIT_CV2_COMPAT) the rest of the reference's cascade, `for method in [cv2.RANSAC,
-//                       cv2.RHO, cv2.LMEDS]` (:354-357), for the frames the RANSAC leg left without a model: one thread
-//                       per such frame runs OpenCV's RHO estimator and, if that fails too, LMedS (cascade_core.cuh);
-//                       every other thread exits on its status word.
+//                       cv2.RHO, cv2.LMEDS]` (:354-357), for the frames the RANSAC leg left without a model: one warp
+//                       per such frame runs OpenCV's RHO estimator (lane 0: the algorithm is a chain) and, if that
+//                       fails too, LMedS with the samples rated on the 32 lanes (cascade_core.cuh); every other warp
+//                       exits on its status word.
 //   refit_warp_kernel   one warp per frame, FP64: OpenCV's tail of findHomography -- normalised DLT on
 //                       the inliers (smallest eigenvector of the 9x9 normal matrix), <= 10
 //                       Levenberg-Marquardt iterations over nine parameters, mask recomputed from the
@@ -1016,34 +1017,74 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
 // The RHO and LMEDS legs of coordinate_model.py:354-357 for frames whose RANSAC leg returned no model.
 // Rare frames (RANSAC gives up only when no sample passes checkSubset or no model reaches 4 inliers), both
 // estimators are sequential by construction (every sample depends on the SPRT / iteration bounds the
-// previous one left), so: one thread per frame, scalar code shared with the host build.
+// previous one left); the scalar code is shared with the host build.
 //   status -> EGL_FIT_OK, H / inlier_mask / info[1] as for the RANSAC leg, info[2] = EGL_FIT_LEG_RHO / _LMEDS
 // ------------------------------------------------------------------------------------------------
-constexpr int kCascadeThreads = 128;
+constexpr int kCascadeWarps = 4;
 
-__global__ void __launch_bounds__(kCascadeThreads) cascade_kernel(FitArgs a) {
-    const int f = blockIdx.x * kCascadeThreads + threadIdx.x;
+__global__ void __launch_bounds__(kCascadeWarps * 32) cascade_kernel(FitArgs a) {
+    // One WARP per frame (hard frames that are neighbours in the clip must not share a warp: they would run one after
+    // the other).  RHO is a chain -- every sample depends on the SPRT state and the iteration bound the previous one
+    // left -- and runs on lane 0.  LMedS rates a fixed sample sequence: lane 0 walks cv::RNG for the sequence, all lanes
+    // rate samples (one 9x9 Jacobi eigen-decomposition each), a warp arg-min picks the first smallest median.
+    __shared__ PointList s_pl[kCascadeWarps];
+    __shared__ uint8_t s_smp[kCascadeWarps][kLmedsMaxIters][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * kCascadeWarps + warp;
     if (f >= a.F || a.status[f] != EGL_FIT_NO_MODEL) return;
-    float sx[kMaxPts], sy[kMaxPts], dx[kMaxPts], dy[kMaxPts];
-    uint8_t ch[kMaxPts];
-    const int N = gather_points_thread(a, f, sx, sy, dx, dy, ch);
+    PointList& pl = s_pl[warp];
+    uint64_t used;
+    const int N = gather_points_warp(a, f, pl, &used);
     if (N <= 4) return;  // findHomography solves exactly four points without a robust method: every leg fails alike
     double H[9];
     uint64_t pm = 0;
-    float Hf[9];
-    int leg = EGL_FIT_LEG_RHO;
-    int count = rho_fit(sx, sy, dx, dy, N, Hf, &pm);
-    if (count > 0) {
+    int leg = EGL_FIT_LEG_RHO, count = 0;
+    if (lane == 0) {
+        float Hf[9];
+        count = rho_fit(pl.sx, pl.sy, pl.dx, pl.dy, N, Hf, &pm);
         for (int i = 0; i < 9; ++i) H[i] = (double)Hf[i];
-    } else {
-        double scratch[192];
+    }
+    count = __shfl_sync(kFull, count, 0);
+    if (count <= 0) {
         leg = EGL_FIT_LEG_LMEDS;
-        count = lmeds_fit(sx, sy, dx, dy, N, a.confidence, H, &pm, scratch);
+        int n_smp = 0;
+        if (lane == 0) n_smp = lmeds_draw_samples(pl.sx, pl.sy, pl.dx, pl.dy, N, a.confidence, s_smp[warp]);
+        n_smp = __shfl_sync(kFull, n_smp, 0);
+        __syncwarp();
+        if (n_smp < 0) return;
+        double scratch[192];
+        double bm = DBL_MAX, bH[9];
+        int bt = 0x7fffffff;
+        for (int i = 0; i < 9; ++i) bH[i] = 0.0;
+        for (int t = lane; t < n_smp; t += 32) {
+            double Hm[9], med;
+            if (lmeds_rate_sample(pl.sx, pl.sy, pl.dx, pl.dy, N, s_smp[warp][t], Hm, &med, scratch) && med < bm) {
+                bm = med;
+                bt = t;
+                for (int i = 0; i < 9; ++i) bH[i] = Hm[i];
+            }
+        }
+        // `median < minMedian` in sequence order = smallest median, ties to the earliest sample
+        double wm = bm;
+        int wt = bt;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            const double om = shfl_xor_f64(wm, m);
+            const int ot = __shfl_xor_sync(kFull, wt, m);
+            if (om < wm || (om == wm && ot < wt)) { wm = om; wt = ot; }
+        }
+        if (wt == 0x7fffffff) return;  // no sample gave a model
+        const int src = wt & 31;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) bH[i] = shfl_f64(bH[i], src);
+        if (lane == 0) count = lmeds_finish(pl.sx, pl.sy, pl.dx, pl.dy, N, bH, wm, H, &pm, scratch);
+        count = __shfl_sync(kFull, count, 0);
         if (count < 0) return;
     }
+    if (lane != 0) return;
     uint64_t cm = 0;
     for (int i = 0; i < N; ++i)
-        if ((pm >> i) & 1ull) cm |= 1ull << ch[i];
+        if ((pm >> i) & 1ull) cm |= 1ull << pl.ch[i];
     for (int i = 0; i < 9; ++i) a.H[(size_t)f * 9 + i] = H[i];
     a.inlier_mask[f] = cm;
     a.status[f] = EGL_FIT_OK;
@@ -1054,6 +1095,27 @@ __global__ void __launch_bounds__(kCascadeThreads) cascade_kernel(FitArgs a) {
 }  // namespace egl
 
 using namespace egl;
+
+// Stream-ordered scratch of the fixed-K mode comes from a pool of this library's own that never returns memory to the
+// driver (release threshold = max): with the default pool every call paid a fresh 100 MB allocation (4 ms at 50 k frames).
+static cudaMemPool_t scratch_pool() {
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t p = nullptr;
+        if (cudaMemPoolCreate(&p, &props) != cudaSuccess) return nullptr;
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &keep);
+        pools[dev] = p;
+    }
+    return pools[dev];
+}
 
 static int fit_impl(const char* who, const int32_t* kp_xy, const uint8_t* kp_order, const int32_t* kp_count, int F, int mode, int K,
                     const uint8_t* hyp, uint64_t seed, double thr, double confidence, double* H, uint64_t* used_mask,
@@ -1073,7 +1135,9 @@ static int fit_impl(const char* who, const int32_t* kp_xy, const uint8_t* kp_ord
     } else {
         // scratch for the prepared frames: stream-ordered, so the free below only takes effect after the kernels
         FixedKPrep* prep = nullptr;
-        int rc0 = cuda_status(cudaMallocAsync((void**)&prep, sizeof(FixedKPrep) * (size_t)F, s), "egl_fit_homography: scratch allocation");
+        cudaMemPool_t pool = scratch_pool();
+        int rc0 = cuda_status(pool ? cudaMallocFromPoolAsync((void**)&prep, sizeof(FixedKPrep) * (size_t)F, pool, s) : cudaErrorMemoryAllocation,
+                              "egl_fit_homography: scratch allocation");
         if (rc0) return rc0;
         fixedk_prepare_kernel<<<(F + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, 0, s>>>(a, (float)(1.0 / thr), prep);
         ransac_fixedk_kernel<<<F, kFixedThreads, 0, s>>>(a, (float)(1.0 / thr), thr, prep);
@@ -1097,7 +1161,7 @@ static int fit_impl(const char* who, const int32_t* kp_xy, const uint8_t* kp_ord
         refit_warp_kernel<<<(F + kRefitWarps - 1) / kRefitWarps, kRefitWarps * 32, 0, s>>>(a);
     rc = cuda_status(cudaGetLastError(), "egl_fit_homography: refit kernel launch");
     if (rc || mode != EGL_FIT_CV2_COMPAT) return rc;
-    cascade_kernel<<<(F + kCascadeThreads - 1) / kCascadeThreads, kCascadeThreads, 0, s>>>(a);
+    cascade_kernel<<<(F + kCascadeWarps - 1) / kCascadeWarps, kCascadeWarps * 32, 0, s>>>(a);
     return cuda_status(cudaGetLastError(), "egl_fit_homography: cascade kernel launch");
 }
 
