@@ -13,7 +13,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libeagle_b200.so")
-SOURCES = ["common.cu", "preprocess.cu", "decode.cu", "synthesize.cu", "fit.cu", "project.cu", "flow.cu"]
+SOURCES = ["common.cu", "preprocess.cu", "decode.cu", "synthesize.cu", "fit.cu", "project.cu", "flow.cu", "upload.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -80,7 +80,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(f"--- nvcc {src} ---\n{out}\n")
     if failed:
         raise RuntimeError("nvcc failed; see output above")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ARCH + ["-Xcompiler", "-fPIC", "-lcudart"])
+    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ARCH + ["-Xcompiler", "-fPIC", "-lcudart", "-lpthread"])
     return LIB
 
 

@@ -209,7 +209,6 @@ class CoordinateModel:
         self._detect_objects = detect_objects
         self.chunk = chunk
         self.path = GeometryPath(device, keypoint_conf)
-        self._staging, self._staged = None, [None, None]
         self._stream, self._stream_key = None, None
         self.network_batch = BATCH     # frames per keypoint_model call (the reference feeds the network 4 at a time, :20)
         # host threads filling the page-locked staging buffers: one frame per task; a single core moves 4-10 GB/s, the PCIe
@@ -240,24 +239,12 @@ class CoordinateModel:
         """K1 + the attached network on frames that already are in HBM ((n, H, W, 3) uint8)."""
         return self._heatmaps_of(self.path.engine.preprocess(dev_frames.contiguous()))
 
-    def _upload(self, frames: Sequence[np.ndarray], dst: torch.Tensor, group: int = 32) -> None:
-        """Host frames -> dst (n, H, W, 3) on the device through two reusable page-locked staging buffers
-        (a page-locked copy of a whole piece would cost a multi-GB cudaHostAlloc per call)."""
-        n = len(frames)
-        shape = (min(group, max(n, 1)),) + tuple(dst.shape[1:])
-        if self._staging is None or tuple(self._staging[0].shape[1:]) != shape[1:] or self._staging[0].shape[0] < shape[0]:
-            self._staging = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(2)]
-            self._staged = [None, None]
-        for b, s in enumerate(range(0, n, shape[0])):
-            slot = b & 1
-            if self._staged[slot] is not None:
-                self._staged[slot].synchronize()   # the previous copy out of this buffer has finished
-            m = min(shape[0], n - s)
-            stage = self._staging[slot].numpy()
-            for j in range(m):
-                np.copyto(stage[j], frames[s + j])
-            dst[s:s + m].copy_(self._staging[slot][:m], non_blocking=True)
-            self._staged[slot] = torch.cuda.current_stream(self.device).record_event()
+    def _upload(self, frames: Sequence[np.ndarray], dst: torch.Tensor) -> None:
+        """Host frames -> dst (n, H, W, 3) on the device (egl_upload_frames: worker threads, page-locked rings, H2D per
+        slice).  Synchronous; whatever the current stream still does with dst is waited for first."""
+        part = [fr if fr.flags["C_CONTIGUOUS"] else np.ascontiguousarray(fr) for fr in frames]
+        torch.cuda.current_stream(self.device).synchronize()
+        self.path.engine.upload_frames(part, dst, threads=self.copy_threads)
 
     @torch.no_grad()
     def _heatmaps(self, frames: Sequence[np.ndarray]) -> torch.Tensor:

@@ -1,0 +1,122 @@
+// Host frames -> device memory for the reference-facing call (the reference hands get_coordinates a Python list of
+// pageable numpy frames, eagle/models/coordinate_model.py:188,221).
+//
+// A pageable buffer cannot be DMA'd: it is either copied into page-locked staging first or the driver does that itself
+// on one thread (8-10 GB/s measured).  Staging a whole chunk in a large pinned buffer makes every byte cross host DRAM
+// three times (read the frame, write the staging buffer, DMA reads it back): on the bench boxes that is the limit
+// (about 100 GB/s of DRAM traffic = 34 GB/s of frames with both legs running) long before PCIe Gen5 (55 GB/s).  Here each
+// worker thread copies 4 MiB slices into a small page-locked ring of its own and issues the H2D of every slice at once on
+// its own stream, so copy and DMA interleave at slice granularity: 44-47 GB/s from pageable frames with 8-16 threads on
+// the same boxes (tools/upload_probe.py), 39 GB/s with 4.
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace egl {
+
+constexpr int kUpMaxThreads = 32;
+constexpr int kUpSlots = 3;
+static size_t kUpSlice = 4u << 20;  // 256 KiB ... 4 MiB swept on B200 boxes: per-slice overhead loses below 2 MiB
+
+struct UploadWorker {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[kUpSlots] = {};
+    unsigned char* slot[kUpSlots] = {};
+    int device = -1;
+};
+
+struct UploadJob {
+    UploadWorker* w;
+    const void* const* frames;
+    int first, count, stride;  // this worker takes frames first, first + stride, ...
+    size_t bytes;
+    unsigned char* dst;
+    int device;
+    cudaError_t err;
+};
+
+static UploadWorker g_up[kUpMaxThreads];
+static pthread_mutex_t g_up_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static cudaError_t upload_worker_init(UploadWorker& w, int device) {
+    if (w.device == device) return cudaSuccess;
+    if (w.device >= 0) {  // the library was last used on another device: rebuild on this one
+        cudaStreamDestroy(w.stream);
+        for (int s = 0; s < kUpSlots; ++s) { cudaEventDestroy(w.ev[s]); cudaFreeHost(w.slot[s]); }
+        w = UploadWorker();
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking);
+    for (int s = 0; s < kUpSlots && e == cudaSuccess; ++s) {
+        e = cudaEventCreateWithFlags(&w.ev[s], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&w.slot[s], kUpSlice, cudaHostAllocDefault);
+    }
+    if (e == cudaSuccess) w.device = device;
+    return e;
+}
+
+static void* upload_thread(void* arg) {
+    UploadJob& j = *(UploadJob*)arg;
+    j.err = cudaSetDevice(j.device);
+    if (j.err != cudaSuccess) return nullptr;
+    UploadWorker& w = *j.w;
+    int q = 0;
+    bool used[kUpSlots] = {};
+    for (int f = j.first; f < j.count && j.err == cudaSuccess; f += j.stride) {
+        const unsigned char* src = (const unsigned char*)j.frames[f];
+        unsigned char* dst = j.dst + (size_t)f * j.bytes;
+        for (size_t o = 0; o < j.bytes && j.err == cudaSuccess; o += kUpSlice) {
+            const size_t n = j.bytes - o < kUpSlice ? j.bytes - o : kUpSlice;
+            if (used[q]) j.err = cudaEventSynchronize(w.ev[q]);  // the DMA that last read this slot has finished
+            if (j.err != cudaSuccess) break;
+            memcpy(w.slot[q], src + o, n);
+            j.err = cudaMemcpyAsync(dst + o, w.slot[q], n, cudaMemcpyHostToDevice, w.stream);
+            if (j.err == cudaSuccess) j.err = cudaEventRecord(w.ev[q], w.stream);
+            used[q] = true;
+            q = (q + 1) % kUpSlots;
+        }
+    }
+    const cudaError_t e = cudaStreamSynchronize(w.stream);
+    if (j.err == cudaSuccess) j.err = e;
+    return nullptr;
+}
+
+}  // namespace egl
+
+using namespace egl;
+
+extern "C" int egl_upload_frames(const void* const* frames, int n_frames, size_t bytes_per_frame, void* dst, int n_threads) {
+    if (n_frames == 0) return 0;
+    EGL_REQUIRE(frames && dst, EGL_ERR_NULL, "egl_upload_frames: null pointer");
+    EGL_REQUIRE(n_frames > 0 && bytes_per_frame > 0, EGL_ERR_SHAPE, "egl_upload_frames: need n_frames >= 0 and bytes_per_frame > 0");
+    for (int i = 0; i < n_frames; ++i) EGL_REQUIRE(frames[i], EGL_ERR_NULL, "egl_upload_frames: frame %d is null", i);
+#ifdef EGL_BENCH_VARIANTS
+    static const char* slice_env = getenv("EGL_UPLOAD_SLICE_KB");
+    if (slice_env && g_up[0].device < 0) kUpSlice = (size_t)atoi(slice_env) << 10;
+#endif
+    int nt = n_threads < 1 ? 1 : (n_threads > kUpMaxThreads ? kUpMaxThreads : n_threads);
+    if (nt > n_frames) nt = n_frames;
+    int device = 0;
+    int rc = cuda_status(cudaGetDevice(&device), "egl_upload_frames: cudaGetDevice");
+    if (rc) return rc;
+    pthread_mutex_lock(&g_up_lock);  // one upload at a time per process: the ring and its streams are shared state
+    UploadJob jobs[kUpMaxThreads];
+    pthread_t th[kUpMaxThreads];
+    cudaError_t err = cudaSuccess;
+    for (int k = 0; k < nt && err == cudaSuccess; ++k) err = upload_worker_init(g_up[k], device);
+    int started = 0;
+    if (err == cudaSuccess) {
+        for (int k = 0; k < nt; ++k) {
+            jobs[k] = UploadJob{&g_up[k], frames, k, n_frames, nt, bytes_per_frame, (unsigned char*)dst, device, cudaSuccess};
+            if (pthread_create(&th[k], nullptr, upload_thread, &jobs[k]) != 0) break;
+            ++started;
+        }
+        for (int k = 0; k < started; ++k) pthread_join(th[k], nullptr);
+        for (int k = 0; k < started; ++k)
+            if (jobs[k].err != cudaSuccess) err = jobs[k].err;
+        if (started < nt && err == cudaSuccess) err = cudaErrorLaunchFailure;  // a worker thread could not be created
+    }
+    pthread_mutex_unlock(&g_up_lock);
+    return cuda_status(err, "egl_upload_frames");
+}

@@ -68,6 +68,26 @@ class GeometryEngine:
         if self.device.type != "cuda":
             raise N.NativeError("GeometryEngine needs a CUDA device; there is no CPU path")
 
+    # -- host frames -> device ---------------------------------------------------------------
+    def upload_frames(self, frames, out: torch.Tensor, threads: int = 8) -> torch.Tensor:
+        """frames: sequence of n C-contiguous uint8 numpy arrays of one shape (pageable host memory, as the reference's
+        frame list holds them); out: (>= n, ...) uint8 CUDA tensor whose rows have that many bytes.  Synchronous."""
+        import ctypes as C
+        n = len(frames)
+        if n == 0:
+            return out[:0]
+        nbytes = frames[0].nbytes
+        _require(out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.shape[0] >= n and out[0].numel() == nbytes,
+                 "upload_frames: out must be a contiguous CUDA uint8 tensor with one row per frame")
+        ptrs = (C.c_void_p * n)()
+        for i, fr in enumerate(frames):
+            _require(fr.nbytes == nbytes and fr.flags["C_CONTIGUOUS"] and fr.dtype.itemsize == 1,
+                     "upload_frames: frames must be C-contiguous uint8 arrays of one size")
+            ptrs[i] = fr.ctypes.data
+        with torch.cuda.device(out.device):
+            N.check(N.lib.egl_upload_frames(ptrs, n, nbytes, _ptr(out), int(threads)), "egl_upload_frames")
+        return out[:n]
+
     # -- K1 ---------------------------------------------------------------------------------
     def preprocess(self, frames: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """frames (F, H, W, 3) uint8 BGR on the device -> (F, 3, 540, 960) float32."""

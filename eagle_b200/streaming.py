@@ -3,8 +3,9 @@
 coordinate_model.py:188-417 walks the clip frame by frame; with a keypoint interval of 1 every frame is independent up
 to the homography cadence, so the clip goes through in chunks of whole cadence segments and four things overlap:
 
-    host      detect_objects() of chunk c+1, frames of chunk c+1 copied into page-locked staging by a small thread pool
-    copy-in   H2D of chunk c+1 (frames uint8 + foot points)                                     [stream copy_in]
+    host      detect_objects() of chunk c+1 while egl_upload_frames moves the frames of chunk c+1 to the device (worker
+              threads of the library: 4 MiB slices through a small page-locked ring, H2D per slice on their own streams)
+    copy-in   foot points of chunk c+1                                                          [stream copy_in]
     kernels   K1 preprocess -> keypoint network -> K2 decode -> F1 synthesis -> K3 fit ->
               cadence (egl_select_homography_chunk, state carried in device memory) -> K4      [stream compute]
     copy-out  ONE packed record per chunk (about 1 KB per frame) into page-locked memory       [stream copy_out]
@@ -60,12 +61,12 @@ class DenseStream:
         self.copy_in = torch.cuda.Stream(dev)
         self.compute = torch.cuda.Stream(dev)
         self.copy_out = torch.cuda.Stream(dev)
-        self.pool = ThreadPoolExecutor(max_workers=max(1, copy_threads))
+        self.copy_threads = max(1, copy_threads)
+        self.pool = ThreadPoolExecutor(max_workers=1)   # runs the (GIL-free) upload call next to detect_objects
         self.P_cap = 0
         self.slots = []
         for _ in range(2):
             self.slots.append(dict(
-                h_frames=torch.empty((chunk, height, width, 3), dtype=torch.uint8, pin_memory=True),
                 d_frames=torch.empty((chunk, height, width, 3), dtype=torch.uint8, device=dev),
                 x=torch.empty((chunk, 3, N.MODEL_H, N.MODEL_W), dtype=torch.float32, device=dev),
                 kp=engine.alloc_keypoints(chunk), status=torch.zeros(chunk, dtype=torch.int32, device=dev),
@@ -97,6 +98,12 @@ class DenseStream:
 
     def close(self) -> None:
         self.pool.shutdown(wait=True)
+
+    def _upload(self, part, d_frames) -> float:
+        import time
+        t0 = time.perf_counter()
+        self.e.upload_frames(part, d_frames, threads=self.copy_threads)
+        return time.perf_counter() - t0
 
     # ---------------------------------------------------------------------------------------------
     def run(self, frames: Sequence[np.ndarray], detect_objects: Callable, heatmaps_of: Callable[[torch.Tensor], torch.Tensor],
@@ -142,7 +149,7 @@ class DenseStream:
 
         worker = threading.Thread(target=assembler, name="eagle-assemble", daemon=True)
         worker.start()
-        t_host = {"detect": 0.0, "stage": 0.0}
+        t_host = {"detect": 0.0, "stage": 0.0, "upload": 0.0}
         # frames that already live in page-locked memory (one (F,H,W,3) uint8 torch tensor) are copied from where they are
         pinned_src = torch.is_tensor(frames) and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.is_pinned()
         frames_np = frames.numpy() if pinned_src else frames
@@ -152,33 +159,34 @@ class DenseStream:
             for c, first in enumerate(range(0, F, CH)):
                 n = min(CH, F - first)
                 s = self.slots[c & 1]
-                # ---- host: staging copies run in the pool while the detector works on the same frames
-                if s["uploaded"] is not None:
-                    s["uploaded"].synchronize()          # the H2D that last read this staging buffer has finished
+                # ---- host: the upload runs in the library's worker threads while the detector works on the same frames
+                if s["computed"] is not None:
+                    s["computed"].synchronize()          # the kernels that last read this slot's device buffers have finished
                 t0 = time.perf_counter()
-                stage = s["h_frames"].numpy()
-                futs = [] if pinned_src else [self.pool.submit(np.copyto, stage[j], frames[first + j]) for j in range(n)]
+                fut = None
+                if not pinned_src:
+                    part = [fr if fr.flags["C_CONTIGUOUS"] else np.ascontiguousarray(fr) for fr in frames[first:first + n]]
+                    fut = self.pool.submit(self._upload, part, s["d_frames"])
                 objs = [detect_objects(frames_np[first + j]) for j in range(n)]
                 t1 = time.perf_counter()
                 all_obj.extend(objs)
                 P = max(1, max_objects(objs))
                 if P > self.P_cap:
-                    for f_ in futs:
-                        f_.result()
+                    if fut is not None:
+                        fut.result()
                     self._grow_points(P)
                 objects_to_arrays(objs, self.P_cap, out=(s["h_foot"].numpy()[:n], s["h_cnt"].numpy()[:n]))
-                for f_ in futs:
-                    f_.result()
+                if fut is not None:
+                    t_host["upload"] += fut.result()
                 t2 = time.perf_counter()
                 t_host["detect"] += t1 - t0
                 t_host["stage"] += t2 - t1
                 P = self.P_cap
                 # ---- copy-in
                 with torch.cuda.stream(self.copy_in):
-                    if s["computed"] is not None:
-                        self.copy_in.wait_event(s["computed"])   # the kernels that last read the device buffers have finished
                     m0 = ev(self.copy_in)
-                    s["d_frames"][:n].copy_(frames[first:first + n] if pinned_src else s["h_frames"][:n], non_blocking=True)
+                    if pinned_src:
+                        s["d_frames"][:n].copy_(frames[first:first + n], non_blocking=True)
                     s["d_foot"][:n].copy_(s["h_foot"][:n], non_blocking=True)
                     s["d_cnt"][:n].copy_(s["h_cnt"][:n], non_blocking=True)
                     m1 = ev(self.copy_in)
@@ -227,7 +235,7 @@ class DenseStream:
             stats.update(h2d_ms=sum(a.elapsed_time(b) for a, b, *_ in marks), kernels_ms=sum(m[2].elapsed_time(m[3]) for m in marks),
                          d2h_ms=sum(m[4].elapsed_time(m[5]) for m in marks))
         if stats is not None:
-            stats.update(detect_s=t_host["detect"], stage_s=t_host["stage"], assemble_s=t_asm[0], chunks=(F + CH - 1) // CH,
+            stats.update(detect_s=t_host["detect"], stage_s=t_host["stage"], upload_s=t_host["upload"], assemble_s=t_asm[0], chunks=(F + CH - 1) // CH,
                          chunk_frames=CH, h2d_bytes=F * (Hh * Ww * 3 + self.P_cap * 8 + 4), d2h_bytes=F * record_bytes(self.P_cap))
         return res, all_obj, aborted
 

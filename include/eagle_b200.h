@@ -133,6 +133,16 @@ int egl_fit_homography_subpixel(const float *kp_sub, const int32_t *kp_xy, const
 int egl_synthesize_keypoints(int32_t *kp_xy, uint8_t *kp_order, int32_t *kp_count, int F, int max_new, void *stream);
 
 /*
+ * Host frames -> device memory: the first step of get_coordinates on a list of frames (coordinate_model.py:188,221 take
+ * `frames` as a Python list of pageable HxWx3 uint8 arrays).  frames[i] = host pointer of frame i (any memory, pageable
+ * or not), every frame bytes_per_frame long; dst = device buffer of n_frames * bytes_per_frame.  n_threads worker threads
+ * copy 4 MiB slices through small page-locked rings of their own and issue the H2D of every slice at once on streams of
+ * their own, so the host copy and the DMA interleave at slice granularity.  Synchronous: returns when all
+ * frames are on the device (run it on a helper thread to overlap it with other work).  One upload at a time per process.
+ */
+int egl_upload_frames(const void *const *frames, int n_frames, size_t bytes_per_frame, void *dst, int n_threads);
+
+/*
  * K3  robust image->pitch homography per frame.
  * Replaces the correspondence gather (coordinate_model.py:335-349: on-plane channels of kp_order,
  * in order) and cv2.findHomography(img_pts, world_pts, cv2.RANSAC, 5.0) (:354-357), including
