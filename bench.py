@@ -417,7 +417,7 @@ def main():
                          "once -- the ceiling of the host-fed number when the caller's frames are ordinary (pageable) arrays"}
 
     # ---- e2e through the public API: host frames -> CoordinateModel.get_coordinates -> reference-format dict
-    from eagle_b200.coordinate_model import CoordinateModel
+    from eagle_b200.coordinate_model import CoordinateModel, upload_threads
     POOL_HOST = 256     # distinct host frames (1.6 GB), cycled to the clip length: every frame is still staged and copied
     host_pool = frames[:POOL_HOST].cpu().numpy()
     host_frames = [host_pool[i % POOL_HOST] for i in range(F)]
@@ -439,7 +439,7 @@ def main():
 
     model = CoordinateModel(keypoint_model=network, detect_objects=detector, device=dev, chunk=75)
     model.network_batch = 75
-    model.copy_threads = max(2, min(16, len(my_cores)))
+    model.copy_threads = upload_threads(len(my_cores))
 
     def api_once():
         state["i"] = 0; state["h"] = 0

@@ -196,6 +196,10 @@ class GeometryPath:
                                                                                proj.in_bounds, proj.bounds]))
 
 
+def upload_threads(cores: int) -> int:
+    return max(2, min(8, cores - 1))
+
+
 class CoordinateModel:
     """Reference-shaped front end (constructor kwargs and method names of
     eagle/models/coordinate_model.py:49,188,480,557)."""
@@ -211,9 +215,10 @@ class CoordinateModel:
         self.path = GeometryPath(device, keypoint_conf)
         self._stream, self._stream_key = None, None
         self.network_batch = BATCH     # frames per keypoint_model call (the reference feeds the network 4 at a time, :20)
-        # host threads filling the page-locked staging buffers: one frame per task; a single core moves 4-10 GB/s, the PCIe
-        # link 55, so the copy-in is spread over the cores this process may run on (at most 16)
-        self.copy_threads = max(2, min(16, len(os.sched_getaffinity(0))))
+        # worker threads of egl_upload_frames: a single core moves 6-10 GB/s into the page-locked rings, the PCIe link 55;
+        # measured on a 16-core box: 4 threads 38 GB/s, 6 -> 48, 8 -> 50, 16 -> 44 (they crowd out the assembler and the
+        # thread that enqueues the kernels), so: the cores this process may run on minus one, at most 8
+        self.copy_threads = upload_threads(len(os.sched_getaffinity(0)))
         self.profile = False           # time H2D / kernels / D2H of every chunk with CUDA events (last_stats)
         self.always_propagate = False  # route every clip through PropagatedPath (tests)
         self.piece_frames = 2048       # sparse cadence: frames resident in HBM at a time (12.7 GB of 1080p frames + 5.6 GB of pyramids)

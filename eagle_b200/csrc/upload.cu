@@ -8,6 +8,7 @@
 // worker thread copies 4 MiB slices into a small page-locked ring of its own and issues the H2D of every slice at once on
 // its own stream, so copy and DMA interleave at slice granularity: 44-47 GB/s from pageable frames with 8-16 threads on
 // the same boxes (tools/upload_probe.py), 39 GB/s with 4.
+#include <atomic>
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -30,7 +31,9 @@ struct UploadWorker {
 struct UploadJob {
     UploadWorker* w;
     const void* const* frames;
-    int first, count, stride;  // this worker takes frames first, first + stride, ...
+    std::atomic<long long>* next;  // slices are handed out one at a time, so no thread is left with a longer tail
+    long long total;
+    int per_frame;                 // slices per frame
     size_t bytes;
     unsigned char* dst;
     int device;
@@ -63,19 +66,21 @@ static void* upload_thread(void* arg) {
     UploadWorker& w = *j.w;
     int q = 0;
     bool used[kUpSlots] = {};
-    for (int f = j.first; f < j.count && j.err == cudaSuccess; f += j.stride) {
-        const unsigned char* src = (const unsigned char*)j.frames[f];
-        unsigned char* dst = j.dst + (size_t)f * j.bytes;
-        for (size_t o = 0; o < j.bytes && j.err == cudaSuccess; o += kUpSlice) {
-            const size_t n = j.bytes - o < kUpSlice ? j.bytes - o : kUpSlice;
-            if (used[q]) j.err = cudaEventSynchronize(w.ev[q]);  // the DMA that last read this slot has finished
-            if (j.err != cudaSuccess) break;
-            memcpy(w.slot[q], src + o, n);
-            j.err = cudaMemcpyAsync(dst + o, w.slot[q], n, cudaMemcpyHostToDevice, w.stream);
-            if (j.err == cudaSuccess) j.err = cudaEventRecord(w.ev[q], w.stream);
-            used[q] = true;
-            q = (q + 1) % kUpSlots;
-        }
+    for (;;) {
+        const long long t = j.next->fetch_add(1, std::memory_order_relaxed);
+        if (t >= j.total || j.err != cudaSuccess) break;
+        const long long f = t / j.per_frame;
+        const size_t o = (size_t)(t % j.per_frame) * kUpSlice;
+        const size_t n = j.bytes - o < kUpSlice ? j.bytes - o : kUpSlice;
+        const unsigned char* src = (const unsigned char*)j.frames[f] + o;
+        unsigned char* dst = j.dst + (size_t)f * j.bytes + o;
+        if (used[q]) j.err = cudaEventSynchronize(w.ev[q]);  // the DMA that last read this slot has finished
+        if (j.err != cudaSuccess) break;
+        memcpy(w.slot[q], src, n);
+        j.err = cudaMemcpyAsync(dst, w.slot[q], n, cudaMemcpyHostToDevice, w.stream);
+        if (j.err == cudaSuccess) j.err = cudaEventRecord(w.ev[q], w.stream);
+        used[q] = true;
+        q = (q + 1) % kUpSlots;
     }
     const cudaError_t e = cudaStreamSynchronize(w.stream);
     if (j.err == cudaSuccess) j.err = e;
@@ -96,7 +101,10 @@ extern "C" int egl_upload_frames(const void* const* frames, int n_frames, size_t
     if (slice_env && g_up[0].device < 0) kUpSlice = (size_t)atoi(slice_env) << 10;
 #endif
     int nt = n_threads < 1 ? 1 : (n_threads > kUpMaxThreads ? kUpMaxThreads : n_threads);
-    if (nt > n_frames) nt = n_frames;
+    const int per_frame = (int)((bytes_per_frame + kUpSlice - 1) / kUpSlice);
+    const long long total = (long long)n_frames * per_frame;
+    if (nt > total) nt = (int)total;
+    std::atomic<long long> next(0);
     int device = 0;
     int rc = cuda_status(cudaGetDevice(&device), "egl_upload_frames: cudaGetDevice");
     if (rc) return rc;
@@ -108,14 +116,14 @@ extern "C" int egl_upload_frames(const void* const* frames, int n_frames, size_t
     int started = 0;
     if (err == cudaSuccess) {
         for (int k = 0; k < nt; ++k) {
-            jobs[k] = UploadJob{&g_up[k], frames, k, n_frames, nt, bytes_per_frame, (unsigned char*)dst, device, cudaSuccess};
+            jobs[k] = UploadJob{&g_up[k], frames, &next, total, per_frame, bytes_per_frame, (unsigned char*)dst, device, cudaSuccess};
             if (pthread_create(&th[k], nullptr, upload_thread, &jobs[k]) != 0) break;
             ++started;
         }
         for (int k = 0; k < started; ++k) pthread_join(th[k], nullptr);
         for (int k = 0; k < started; ++k)
             if (jobs[k].err != cudaSuccess) err = jobs[k].err;
-        if (started < nt && err == cudaSuccess) err = cudaErrorLaunchFailure;  // a worker thread could not be created
+        if (started == 0 && err == cudaSuccess) err = cudaErrorLaunchFailure;  // no worker thread could be created (fewer than asked for is fine: the slices are shared out dynamically)
     }
     pthread_mutex_unlock(&g_up_lock);
     return cuda_status(err, "egl_upload_frames");

@@ -155,18 +155,26 @@ class DenseStream:
         frames_np = frames.numpy() if pinned_src else frames
         marks = []  # profile: (h2d start, h2d end, kernels start, kernels end, d2h start, d2h end) events per chunk
         ev = (lambda st: st.record_event(torch.cuda.Event(enable_timing=True))) if profile else (lambda st: None)
+
+        def start_upload(c):
+            """Frames of chunk c -> the device buffer of slot c & 1 (after the kernels that last read it), on the helper thread."""
+            if pinned_src:
+                return None
+            first = c * CH
+            s = self.slots[c & 1]
+            if s["computed"] is not None:
+                s["computed"].synchronize()
+            part = [fr if fr.flags["C_CONTIGUOUS"] else np.ascontiguousarray(fr) for fr in frames[first:first + CH]]
+            return self.pool.submit(self._upload, part, s["d_frames"])
+
+        fut_next = None
         try:
             for c, first in enumerate(range(0, F, CH)):
                 n = min(CH, F - first)
                 s = self.slots[c & 1]
                 # ---- host: the upload runs in the library's worker threads while the detector works on the same frames
-                if s["computed"] is not None:
-                    s["computed"].synchronize()          # the kernels that last read this slot's device buffers have finished
                 t0 = time.perf_counter()
-                fut = None
-                if not pinned_src:
-                    part = [fr if fr.flags["C_CONTIGUOUS"] else np.ascontiguousarray(fr) for fr in frames[first:first + n]]
-                    fut = self.pool.submit(self._upload, part, s["d_frames"])
+                fut = start_upload(c) if c == 0 else fut_next
                 objs = [detect_objects(frames_np[first + j]) for j in range(n)]
                 t1 = time.perf_counter()
                 all_obj.extend(objs)
@@ -175,15 +183,21 @@ class DenseStream:
                     if fut is not None:
                         fut.result()
                     self._grow_points(P)
+                if s["uploaded"] is not None:
+                    s["uploaded"].synchronize()          # the H2D that last read this slot's foot-point staging has finished
                 objects_to_arrays(objs, self.P_cap, out=(s["h_foot"].numpy()[:n], s["h_cnt"].numpy()[:n]))
                 if fut is not None:
                     t_host["upload"] += fut.result()
+                # the next chunk's upload starts before this chunk's kernels are enqueued (about a millisecond of launches)
+                fut_next = start_upload(c + 1) if first + CH < F else None
                 t2 = time.perf_counter()
                 t_host["detect"] += t1 - t0
                 t_host["stage"] += t2 - t1
                 P = self.P_cap
                 # ---- copy-in
                 with torch.cuda.stream(self.copy_in):
+                    if pinned_src and s["computed"] is not None:
+                        self.copy_in.wait_event(s["computed"])   # the kernels that last read the device buffers have finished
                     m0 = ev(self.copy_in)
                     if pinned_src:
                         s["d_frames"][:n].copy_(frames[first:first + n], non_blocking=True)
@@ -224,6 +238,11 @@ class DenseStream:
                     marks.append((m0, m1, m2, m3, m4, m5))
                 work.put((first, n, P, objs, oslot, done))
         finally:
+            if fut_next is not None and not fut_next.done():
+                try:
+                    fut_next.result()    # an upload still in flight writes into this object's buffers
+                except Exception:  # noqa: BLE001
+                    pass
             work.put(None)
             worker.join()
         torch.cuda.current_stream(dev).wait_stream(self.compute)
