@@ -387,19 +387,19 @@ def main():
     else:
         per_rank_h2d = [my_h2d]
     del h_probe, d_probe
-    # ... and the host's own copy rate into page-locked staging (what frames held in ordinary numpy arrays have to go through
-    # first), again with all ranks at once and the thread count the API will use
-    from concurrent.futures import ThreadPoolExecutor
-    n_stage, n_thr = 32, max(2, min(16, len(my_cores)))
+    # ... and the rate of the upload the API uses for frames held in ordinary (pageable) numpy arrays, again with all ranks
+    # at once and the thread count the API will use
+    from eagle_b200.coordinate_model import upload_threads
+    n_stage, n_thr = 64, upload_threads(len(my_cores))
     src_frames = [np.full((H, W, 3), i, dtype=np.uint8) for i in range(n_stage)]
-    stage_buf = torch.empty((n_stage, H, W, 3), dtype=torch.uint8, pin_memory=True).numpy()
-    with ThreadPoolExecutor(n_thr) as tp:
-        list(tp.map(lambda j: np.copyto(stage_buf[j], src_frames[j]), range(n_stage)))
-        barrier()
-        ts = time.perf_counter()
-        for _ in range(6):
-            list(tp.map(lambda j: np.copyto(stage_buf[j], src_frames[j]), range(n_stage)))
-        my_stage = 6 * n_stage * H * W * 3 / (time.perf_counter() - ts) / 1e9
+    up_dst = torch.empty((n_stage, H, W, 3), dtype=torch.uint8, device=dev)
+    eng.upload_frames(src_frames, up_dst, threads=n_thr)
+    barrier()
+    ts = time.perf_counter()
+    for _ in range(6):
+        eng.upload_frames(src_frames, up_dst, threads=n_thr)
+    my_stage = 6 * n_stage * H * W * 3 / (time.perf_counter() - ts) / 1e9
+    del up_dst
     barrier()
     if world > 1:
         t = torch.tensor([my_stage], dtype=torch.float64, device=dev)
@@ -408,13 +408,13 @@ def main():
         per_rank_stage = [float(v.item()) for v in allv]
     else:
         per_rank_stage = [my_stage]
-    del src_frames, stage_buf
+    del src_frames
     h2d_probe = {"per_rank_GBps": per_rank_h2d, "aggregate_GBps": sum(per_rank_h2d), "cores_per_rank": len(my_cores),
-                 "host_staging_per_rank_GBps": per_rank_stage, "host_staging_aggregate_GBps": sum(per_rank_stage),
-                 "host_staging_threads_per_rank": n_thr,
+                 "pageable_upload_per_rank_GBps": per_rank_stage, "pageable_upload_aggregate_GBps": sum(per_rank_stage),
+                 "pageable_upload_threads_per_rank": n_thr,
                  "note": "per_rank_GBps: pure cudaMemcpyAsync from page-locked memory, all ranks at once -- the ceiling of any host-fed "
-                         "number on this box; host_staging: numpy frames -> page-locked staging by the API's copy threads, all ranks at "
-                         "once -- the ceiling of the host-fed number when the caller's frames are ordinary (pageable) arrays"}
+                         "number on this box; pageable_upload: egl_upload_frames alone on ordinary (pageable) numpy frames, all ranks at "
+                         "once -- the ceiling of the host-fed number when the caller's frames are what the reference passes"}
 
     # ---- e2e through the public API: host frames -> CoordinateModel.get_coordinates -> reference-format dict
     from eagle_b200.coordinate_model import CoordinateModel, upload_threads
@@ -437,8 +437,8 @@ def main():
         state["h"] = s + n
         return hm[s:s + n]
 
-    model = CoordinateModel(keypoint_model=network, detect_objects=detector, device=dev, chunk=75)
-    model.network_batch = 75
+    model = CoordinateModel(keypoint_model=network, detect_objects=detector, device=dev, chunk=150)
+    model.network_batch = 150
     model.copy_threads = upload_threads(len(my_cores))
 
     def api_once():

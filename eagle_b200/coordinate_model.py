@@ -205,7 +205,7 @@ class CoordinateModel:
     eagle/models/coordinate_model.py:49,188,480,557)."""
 
     def __init__(self, keypoint_conf: float = 0.3, detector_conf: float = 0.35, *, keypoint_model: Callable | None = None,
-                 detect_objects: Callable | None = None, device="cuda:0", chunk: int = 64):
+                 detect_objects: Callable | None = None, device="cuda:0", chunk: int = 128):
         self.device = torch.device(device)
         self.keypoint_conf = keypoint_conf
         self.detector_conf = detector_conf
