@@ -206,6 +206,81 @@ def cascade_fixture(want=((-1, 120), (0, 40), (1, 100), (2, 100))):
     print("cascade_cv2", T, "by leg (-1 none, 0 RANSAC, 1 RHO, 2 LMEDS):", {int(k): int((leg_a == k).sum()) for k in np.unique(leg_a)})
 
 
+def find_hard_frames(width, height, want, seed=77):
+    """Heatmap peak sets (channel -> heatmap pixel) whose decoded + synthesised keypoints make the RANSAC leg of
+    coordinate_model.py:354-357 return None while RHO (leg 1) or LMEDS (leg 2) answers: `want` = {leg: how many}."""
+    from oracle import decode as _decode, homography as _hom, synthesis as _syn
+    from tools.cascade_census import _world
+    world, on = _world()
+    lines = {}
+    for i in on:
+        lines.setdefault(("x", round(float(world[i, 0]), 3)), []).append(i)
+        lines.setdefault(("y", round(float(world[i, 1]), 3)), []).append(i)
+    lines = [v for v in lines.values() if len(v) >= 3]
+    rng = np.random.default_rng(seed)
+    want = dict(want)
+    found = []
+    hh, ww = 135, 240
+    while any(v > 0 for v in want.values()):
+        fam = lines[int(rng.integers(len(lines)))]
+        m = int(rng.integers(3, min(len(fam), 6) + 1))
+        on_line = rng.choice(fam, m, replace=False)
+        rest = [i for i in on if i not in fam]
+        strays = rng.choice(rest, int(rng.integers(1, 4)), replace=False)
+        a, b = rng.uniform([10, 10], [ww - 10, hh - 10]), rng.uniform([10, 10], [ww - 10, hh - 10])
+        peaks = np.zeros((57, 3), np.int32)
+        for c, t in zip(on_line, np.sort(rng.uniform(0, 1, m))):
+            p = a + t * (b - a) + rng.normal(0, 0.4, 2)
+            peaks[c] = (1, int(np.clip(round(p[1]), 0, hh - 1)), int(np.clip(round(p[0]), 0, ww - 1)))
+        for c in strays:
+            peaks[c] = (1, int(rng.integers(0, hh)), int(rng.integers(0, ww)))
+        hm = np.zeros((57, hh, ww), np.float32)
+        for c in range(57):
+            if peaks[c, 0]:
+                hm[c, peaks[c, 1], peaks[c, 2]] = 0.9
+        kps = _decode.decode_frame(hm, width, height)
+        if len(kps) >= 2:
+            kps = _syn.synthesize(kps)
+        img, wor, _ = _hom.gather_correspondences(kps)
+        if len(img) < 5:
+            continue
+        leg = -1
+        for k, (method, thr) in enumerate(((cv2.RANSAC, 5.0), (cv2.RHO, None), (cv2.LMEDS, None))):
+            if cv2.findHomography(img, wor, method, thr)[0] is not None:
+                leg = k
+                break
+        if want.get(leg, 0) > 0:
+            want[leg] -= 1
+            found.append((leg, peaks))
+    return found
+
+
+def apply_hard_frames(heatmaps, frames, peaks):
+    for f, pk in zip(frames, peaks):
+        heatmaps[f] = 0.0
+        for c in range(57):
+            if pk[c, 0]:
+                heatmaps[f, c, pk[c, 1], pk[c, 2]] = 0.9
+
+
+def cascade_clip_fixture(name="ref_cascade_clip_720p.npz", n_frames=14, width=1280, height=720, seed=21):
+    """A clip on which the UNMODIFIED reference itself falls through to cv2.RHO and cv2.LMEDS (:354-357): four of its
+    frames carry keypoint sets the RANSAC leg gives up on (two answered by RHO, two by LMEDS), every frame a keypoint
+    and homography frame.  The dict it returns is what the CUDA path has to reproduce, rescued frames included."""
+    hard = find_hard_frames(width, height, {1: 2, 2: 2})
+    frames_idx = [2, 5, 8, 11]
+    clip = synthetic.make_clip(n_frames, width, height, seed=seed, with_frames=True, ghost_prob=0.05)
+    peaks = np.stack([pk for _, pk in hard])
+    apply_hard_frames(clip["heatmaps"], frames_idx, peaks)
+    res, rec = ref_harness.run_reference(clip["frames"], clip["heatmaps"], clip["objects"])
+    methods = [f.get("method") for f in rec.fits]
+    np.savez_compressed(os.path.join(GOLDEN, name), n_frames=n_frames, width=width, height=height, seed=seed,
+                        hard_frames=np.array(frames_idx, np.int32), hard_peaks=peaks, hard_legs=np.array([l for l, _ in hard], np.int32),
+                        cv2_version=cv2.__version__, heatmaps_sha256=sha(clip["heatmaps"]),
+                        result_json=json.dumps(res, default=float, sort_keys=True), n_fit_calls=len(rec.fits))
+    print(name, "frames", n_frames, "findHomography calls", len(rec.fits), "legs of the hard frames", [l for l, _ in hard], methods[:0])
+
+
 def resize_fixture():
     """Checksums of the live cv2.resize(..., (960,540), INTER_LINEAR) output on seeded frames."""
     out = {}
@@ -249,6 +324,7 @@ def main():
     decode_fixture()
     find_homography_fixture()
     cascade_fixture()
+    cascade_clip_fixture()
     resize_fixture()
 
 

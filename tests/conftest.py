@@ -45,3 +45,19 @@ def cadence_clip(golden_path, with_frames=False):
                                ghost_prob=0.05)
     synthetic.blank_heatmaps(clip["heatmaps"], [int(b) for b in g["blank"]])
     return g, clip
+
+
+def cascade_clip(golden_path, with_frames=False):
+    """The clip of tests/golden/ref_cascade_clip_720p.npz (oracle/make_golden.py::cascade_clip_fixture): a seeded synthetic
+    clip in which the stored heatmap peaks replace four frames, so that their homography comes from cv2.RHO / cv2.LMEDS."""
+    import numpy as np
+    from eagle_b200 import synthetic
+    g = np.load(golden_path)
+    clip = synthetic.make_clip(int(g["n_frames"]), int(g["width"]), int(g["height"]), seed=int(g["seed"]), with_frames=with_frames,
+                               ghost_prob=0.05)
+    for f, pk in zip(g["hard_frames"], g["hard_peaks"]):
+        clip["heatmaps"][f] = 0.0
+        for c in range(57):
+            if pk[c, 0]:
+                clip["heatmaps"][f, c, pk[c, 1], pk[c, 2]] = 0.9
+    return g, clip

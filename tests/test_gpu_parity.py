@@ -263,6 +263,38 @@ def test_cascade_rho_lmeds_match_cv2(engine, golden_dir):
     assert worst[0] < H_REL_TOL and worst[1] < 1e-6 and worst[2] < H_REL_TOL and carved <= 2 and bit_equal >= 95
 
 
+def test_clip_with_rho_and_lmeds_frames_equals_reference_dict(engine, golden_dir):
+    """End to end against the dict the UNMODIFIED reference produced for a clip on which it falls through to cv2.RHO (two
+    frames) and cv2.LMEDS (two frames) -- tests/golden/ref_cascade_clip_720p.npz: the rescued frames' "Keypoints" (inliers of
+    the answering leg), projections and boundaries included; through GeometryPath and through the drop-in front end."""
+    from conftest import cascade_clip
+    from eagle_b200.coordinate_model import CoordinateModel, GeometryPath
+    g, clip = cascade_clip(os.path.join(golden_dir, "ref_cascade_clip_720p.npz"), with_frames=True)
+    assert sha(clip["heatmaps"]) == str(g["heatmaps_sha256"]) and str(g["cv2_version"]) == cv2.__version__
+    hm = torch.from_numpy(clip["heatmaps"]).cuda()
+    got = GeometryPath("cuda:0").run(hm, clip["objects"], clip["width"], clip["height"], fps=1)
+    assert json.dumps(got, default=float, sort_keys=True) == str(g["result_json"])
+    # which leg answered, as the kernel reports it
+    kp = engine.synthesize(engine.decode(hm, clip["width"], clip["height"]))
+    fit = engine.fit(kp)
+    info = fit.info.cpu().numpy(); status = fit.status.cpu().numpy()
+    assert (status == 0).all()
+    for f, leg in zip(g["hard_frames"], g["hard_legs"]):
+        assert info[int(f), 2] == {1: -2, 2: -3}[int(leg)], (f, info[int(f)].tolist())
+    assert (np.delete(info[:, 2], g["hard_frames"]) >= 0).all()
+    state = {"i": 0}
+
+    def keypoint_model(x):
+        out = hm[state["i"]:state["i"] + x.shape[0]]
+        state["i"] += x.shape[0]
+        return out
+
+    objs = iter(clip["objects"])
+    model = CoordinateModel(keypoint_model=keypoint_model, detect_objects=lambda frame: next(objs), chunk=4)
+    got = model.get_coordinates(list(clip["frames"]), fps=1, num_homography=1, num_keypoint_detection=1, verbose=False)
+    assert json.dumps(got, default=float, sort_keys=True) == str(g["result_json"])
+
+
 def test_cascade_does_not_disturb_ordinary_frames(engine):
     """Frames the RANSAC leg solves are untouched by the cascade kernel: info[2] stays a hypothesis index >= 0."""
     from eagle_b200 import synthetic

@@ -172,6 +172,23 @@ def test_homography_cadence_matches_reference(golden_dir, name):
         assert res[0]["Boundaries"] == [None] * 4 and [i for i, t in enumerate(trace) if t["H"] is not None] == [1, 7, 10, 15]
 
 
+def test_clip_with_rho_and_lmeds_frames_matches_reference(golden_dir):
+    """tests/golden/ref_cascade_clip_720p.npz: the unmodified reference falls through to cv2.RHO on two frames and to
+    cv2.LMEDS on two more (:354-357); the oracle pipeline returns the same dict and takes the same legs."""
+    from conftest import cascade_clip
+    g, clip = cascade_clip(os.path.join(golden_dir, "ref_cascade_clip_720p.npz"))
+    assert sha(clip["heatmaps"]) == str(g["heatmaps_sha256"]) and str(g["cv2_version"]) == cv2.__version__
+    trace = []
+    res = pipeline.get_coordinates(clip["heatmaps"], clip["objects"], clip["width"], clip["height"], trace=trace)
+    assert json.dumps(res, default=float, sort_keys=True) == str(g["result_json"])
+    for f, leg in zip(g["hard_frames"], g["hard_legs"]):
+        t = trace[int(f)]
+        assert t["H"] is not None
+        Hr, _ = cv2.findHomography(t["img_pts"], t["world_pts"], cv2.RANSAC, 5.0)
+        Hrho, _ = cv2.findHomography(t["img_pts"], t["world_pts"], cv2.RHO, None)
+        assert Hr is None and (Hrho is not None) == (int(leg) == 1)
+
+
 def test_rho_lmeds_fallbacks_do_not_rescue_fully_degenerate_sets():
     """coordinate_model.py:354-357 falls through to cv2.RHO / cv2.LMEDS when RANSAC returns None.  On fully
     degenerate inputs (collinear, coincident, one-off-a-line) the cascade returns None exactly when RANSAC alone
