@@ -638,6 +638,7 @@ struct RefitShared {
     double aug[10 * 11];
     double vec[12];
     double xs[9], rs[9], ds[9];  // parameter vector / right-hand side / LM scaling staged for lane-indexed access
+    double sums[32];             // the 32 warp totals of warp_sum32 (24 block sums + 8 riders)
 };
 
 // Gauss-Jordan elimination with partial pivoting of an n x n system, rows in REGISTERS: lane r < n holds row r of
@@ -706,12 +707,32 @@ __device__ __forceinline__ void accumulate_point(PointSums& s, const double* b, 
         }
 }
 
-__device__ __forceinline__ void reduce_and_store_matrix(PointSums& s, double* A) {
+// 32 warp sums at once: lane l ends up with the total over all lanes of v[l].  Same additions in the same order as 32
+// butterflies `v += shfl_xor(v, m)`, m = 16 ... 1 (so the totals are bit-identical to warp_sum_f64's), but at offset m each
+// lane only keeps the half of the values whose index bit matches its own lane bit and trades the other half: 31 exchanges
+// instead of 160.  The per-frame refit spent half of its instructions in those butterflies.
+__device__ __forceinline__ double warp_sum32(double (&v)[32], int lane) {
 #pragma unroll
-    for (int e = 0; e < 6; ++e) {
-        s.bb[e] = warp_sum_f64(s.bb[e]); s.bx[e] = warp_sum_f64(s.bx[e]);
-        s.by[e] = warp_sum_f64(s.by[e]); s.bq[e] = warp_sum_f64(s.bq[e]);
+    for (int m = 16; m > 0; m >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+            const double lo = v[i], hi = v[i + m];
+            const double keep = up ? hi : lo, send = up ? lo : hi;
+            v[i] = keep + shfl_xor_f64(send, m);
+        }
     }
+    return v[0];
+}
+
+// slots of the 32 totals: 0-5 bb, 6-11 bx, 12-17 by, 18-23 bq, 24-31 riders of the caller
+__device__ __forceinline__ void pack_point_sums(const PointSums& s, double (&v)[32]) {
+#pragma unroll
+    for (int e = 0; e < 6; ++e) { v[e] = s.bb[e]; v[6 + e] = s.bx[e]; v[12 + e] = s.by[e]; v[18 + e] = s.bq[e]; }
+}
+
+// totals (shared memory, written by every lane for its own slot) -> the 9x9 matrix
+__device__ __forceinline__ void store_matrix_from_sums(const double* sums, double* A) {
     const int lane = threadIdx.x & 31;
     for (int t = lane; t < 81; t += 32) {
         const int r = t / 9, c = t % 9;
@@ -719,9 +740,9 @@ __device__ __forceinline__ void reduce_and_store_matrix(PointSums& s, double* A)
         const int lo = a < cc ? a : cc, hi = a < cc ? cc : a;
         const int e = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);
         double v;
-        if (br == bc) v = (br == 2) ? s.bq[e] : s.bb[e];
+        if (br == bc) v = (br == 2) ? sums[18 + e] : sums[e];
         else if (br + bc == 1) v = 0.0;
-        else v = -((br == 0 || bc == 0) ? s.bx[e] : s.by[e]);
+        else v = -((br == 0 || bc == 0) ? sums[6 + e] : sums[12 + e]);
         A[t] = v;
     }
     __syncwarp();
@@ -794,7 +815,15 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
                     const double b[3] = {(Mx[h] - cMx) * sMx, (My[h] - cMy) * sMy, 1.0};
                     accumulate_point(ps, b, x, y, x * x + y * y);
                 }
-            reduce_and_store_matrix(ps, sh.A);
+            {
+                double t32[32];
+                pack_point_sums(ps, t32);
+#pragma unroll
+                for (int i = 24; i < 32; ++i) t32[i] = 0.0;
+                sh.sums[lane] = warp_sum32(t32, lane);
+                __syncwarp();
+                store_matrix_from_sums(sh.sums, sh.A);
+            }
             // inverse iteration (same as smallest_eigvec9)
             double tr = 0;
             for (int i = 0; i < 9; ++i) tr += sh.A[i * 9 + i];
@@ -868,13 +897,21 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
 #pragma unroll
                     for (int q = 0; q < 3; ++q) { vx[q] += b[q] * rx; vy[q] += b[q] * ry; vq[q] += b[q] * g; }
                 }
-            reduce_and_store_matrix(ps, sh.A);
+            double t32[32];
+            pack_point_sums(ps, t32);
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                v[q] = warp_sum_f64(vx[q]); v[3 + q] = warp_sum_f64(vy[q]); v[6 + q] = -warp_sum_f64(vq[q]);
-            }
+            for (int q = 0; q < 3; ++q) { t32[24 + q] = vx[q]; t32[27 + q] = vy[q]; }
+            t32[30] = vq[0]; t32[31] = vq[1];
+            __syncwarp();                       // the previous readers of sh.sums are done
+            sh.sums[lane] = warp_sum32(t32, lane);
+            const double vq2 = warp_sum_f64(vq[2]);
             S = warp_sum_f64(s);
             rmax = warp_max_f64(rm);
+            __syncwarp();
+            store_matrix_from_sums(sh.sums, sh.A);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { v[q] = sh.sums[24 + q]; v[3 + q] = sh.sums[27 + q]; }
+            v[6] = -sh.sums[30]; v[7] = -sh.sums[31]; v[8] = -vq2;
         };
         auto cost = [&](const double* hh) {
             double s = 0;
