@@ -637,7 +637,6 @@ struct RefitShared {
     double A[81];
     double aug[10 * 11];
     double vec[12];
-    double xs[9], rs[9], ds[9];  // parameter vector / right-hand side / LM scaling staged for lane-indexed access
     double sums[32];             // the 32 warp totals of warp_sum32 (24 block sums + 8 riders)
 };
 
@@ -926,12 +925,14 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
                 }
             return warp_sum_f64(s);
         };
-        // stage a 9-vector held (replicated) in registers into shared memory; static register indices only
-        auto stage = [&](double* dst, const double* src) {
-#pragma unroll
-            for (int i = 0; i < 9; ++i)
-                if (lane == i) dst[i] = src[i];
-            __syncwarp();
+        // element `lane` of a 9-vector every lane holds in registers: a select tree on the lane bits (static register
+        // indices; staging the vector through shared memory cost a store -> barrier -> load round trip per use)
+        auto pick9 = [&](const double* q) -> double {
+            const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
+            const double t0 = b0 ? q[1] : q[0], t1 = b0 ? q[3] : q[2], t2 = b0 ? q[5] : q[4], t3 = b0 ? q[7] : q[6];
+            const double u0 = b1 ? t1 : t0, u1 = b1 ? t3 : t2;
+            const double w = b2 ? u1 : u0;
+            return b3 ? q[8] : w;
         };
         // gauge-fixed solve A d = rhs (A singular along x): bordered system [[A, s x],[s x^T, 0]] [d; mu] = [rhs; 0]
         // (solve_gauge_fixed9 of geometry_core.cuh, parallelised), result in sh.vec[0..9)
@@ -941,30 +942,26 @@ __global__ void __launch_bounds__(kRefitWarps * 32, 4) refit_warp_kernel(FitArgs
             for (int i = 0; i < 9; ++i) { xn += x[i] * x[i]; dmx = fmax(dmx, fabs(sh.A[i * 9 + i])); }
             if (!(xn > 0.0) || !(dmx > 0.0)) return false;
             const double sc = dmx / sqrt(xn);
-            stage(sh.xs, x);
-            stage(sh.rs, rhs);
             double row[11];
 #pragma unroll
-            for (int c = 0; c < 9; ++c) row[c] = lane < 9 ? sh.A[lane * 9 + c] : (lane == 9 ? sc * sh.xs[c] : 0.0);
-            row[9] = lane < 9 ? sc * sh.xs[lane] : 0.0;
-            row[10] = lane < 9 ? sh.rs[lane] : 0.0;
+            for (int c = 0; c < 9; ++c) row[c] = lane < 9 ? sh.A[lane * 9 + c] : (lane == 9 ? sc * x[c] : 0.0);
+            row[9] = lane < 9 ? sc * pick9(x) : 0.0;
+            row[10] = lane < 9 ? pick9(rhs) : 0.0;
             return warp_row_solve<10>(row, sh.vec, lane);
         };
         linearise(x);
 #pragma unroll
         for (int i = 0; i < 9; ++i) D[i] = sh.A[i * 9 + i];
-        stage(sh.ds, D);
         const double Rlo = 0.25, Rhi = 0.75;
         double lambda = 1, lc = 0.75;
         int iter = 0;
         for (;;) {
             bool ok;
             if (lambda > 0) {
-                stage(sh.rs, v);
                 double row[10];
 #pragma unroll
-                for (int c = 0; c < 9; ++c) row[c] = lane < 9 ? sh.A[lane * 9 + c] + (lane == c ? lambda * sh.ds[c] : 0.0) : 0.0;
-                row[9] = lane < 9 ? sh.rs[lane] : 0.0;
+                for (int c = 0; c < 9; ++c) row[c] = lane < 9 ? sh.A[lane * 9 + c] + (lane == c ? lambda * D[c] : 0.0) : 0.0;
+                row[9] = lane < 9 ? pick9(v) : 0.0;
                 ok = warp_row_solve<9>(row, sh.vec, lane);
             } else {
                 ok = solve_gauge(v);
