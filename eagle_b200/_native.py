@@ -44,6 +44,7 @@ lib.egl_project_points.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp,
 lib.egl_pyramid_bytes.argtypes = [_i, _i, _i]
 lib.egl_pyramid_bytes.restype = C.c_int64
 lib.egl_gray_pyramid.argtypes = [_vp, _i, _i, _i, _sz, _sz, _i, _vp, _vp]
+lib.egl_gray_pyramid_strided.argtypes = [_vp, _i, _i, _i, _sz, _sz, _i, _vp, _sz, _vp]
 lib.egl_track_keypoints.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp]
 lib.egl_filter_flow.argtypes = [_vp, _i, _i, _sz, _sz, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]
 lib.egl_merge_keypoints.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]
@@ -63,7 +64,7 @@ EXPORTS = ("egl_version", "egl_last_error", "egl_sm_count", "egl_build_flags", "
            "egl_synthesize_keypoints", "egl_fit_homography", "egl_select_homography", "egl_project_points", "egl_pyramid_bytes",
            "egl_gray_pyramid", "egl_track_keypoints", "egl_filter_flow", "egl_merge_keypoints", "egl_calibrate_keypoints",
            "egl_fit_homography_masked", "egl_commit_fit", "egl_refine_keypoints", "egl_fit_homography_subpixel",
-           "egl_select_homography_chunk", "egl_upload_frames")
+           "egl_select_homography_chunk", "egl_upload_frames", "egl_gray_pyramid_strided")
 
 if lib.egl_version() != ABI_VERSION:
     raise NativeError(f"libeagle_b200.so has ABI {lib.egl_version()}, this package expects {ABI_VERSION}; rebuild")

@@ -733,11 +733,18 @@ extern "C" int64_t egl_pyramid_bytes(int H, int W, int max_level) {
 
 extern "C" int egl_gray_pyramid(const uint8_t* frames, int F, int H, int W, size_t row_stride, size_t frame_stride, int max_level,
                                 uint8_t* pyr, void* stream) {
+    return egl_gray_pyramid_strided(frames, F, H, W, row_stride, frame_stride, max_level, pyr, 0, stream);
+}
+
+extern "C" int egl_gray_pyramid_strided(const uint8_t* frames, int F, int H, int W, size_t row_stride, size_t frame_stride,
+                                        int max_level, uint8_t* pyr, size_t pyr_stride, void* stream) {
     if (F == 0) return 0;
     EGL_REQUIRE(frames && pyr, EGL_ERR_NULL, "egl_gray_pyramid: null pointer");
     EGL_REQUIRE(F > 0 && H > 0 && W > 0 && row_stride >= (size_t)3 * W && max_level >= 0 && max_level < kMaxLevels, EGL_ERR_SHAPE,
                 "egl_gray_pyramid: bad shape (F=%d H=%d W=%d max_level=%d)", F, H, W, max_level);
-    const PyrLayout L = pyramid_layout(H, W, max_level);
+    PyrLayout L = pyramid_layout(H, W, max_level);
+    EGL_REQUIRE(pyr_stride == 0 || pyr_stride >= (size_t)L.bytes, EGL_ERR_SHAPE, "egl_gray_pyramid_strided: pyr_stride smaller than one pyramid");
+    if (pyr_stride) L.bytes = (long long)pyr_stride;  // the kernels only use it as the distance between two frames' pyramids
     cudaStream_t s = (cudaStream_t)stream;
     bool general_only = false, unfused = false;
 #ifdef EGL_BENCH_VARIANTS
@@ -746,7 +753,7 @@ extern "C" int egl_gray_pyramid(const uint8_t* frames, int F, int H, int W, size
     unfused = env && atoi(env) == 2;
 #endif
     const bool fast_gray = !general_only && W % 16 == 0 && row_stride % 16 == 0 && frame_stride % 16 == 0 &&
-                           ((uintptr_t)frames & 15) == 0 && ((uintptr_t)pyr & 15) == 0;
+                           ((uintptr_t)frames & 15) == 0 && ((uintptr_t)pyr & 15) == 0 && L.bytes % 16 == 0;
     // One pass over all frames per level: splitting the clip into L2-sized groups (so that pyrDown would find
     // the gray level still cached) was measured slower at every group size -- 4.8 ms whole, 5.6 ms in groups of
     // 32, 8.6 ms in groups of 8 for 2250 frames at 1080p -- the launch tails cost more than the re-read.

@@ -200,6 +200,25 @@ class GeometryEngine:
                                            max_level, _ptr(out), _stream()), "egl_gray_pyramid")
         return out
 
+    def alloc_pyramid(self, n_frames: int, height: int, width: int, max_level: int = 2, device=None) -> torch.Tensor:
+        nbytes = int(N.lib.egl_pyramid_bytes(height, width, max_level))
+        _require(nbytes > 0, "alloc_pyramid: bad frame size / max_level")
+        return torch.empty((n_frames, nbytes), dtype=torch.uint8, device=device or self.device)
+
+    def gray_pyramid_step(self, frames: torch.Tensor, pyr: torch.Tensor, first: int, step: int, max_level: int = 2) -> None:
+        """Pyramids of frames first, first + step, first + 2 step, ... of a contiguous (F, H, W, 3) clip into the same rows
+        of pyr (F, egl_pyramid_bytes): one step of every chain at a time (egl_gray_pyramid_strided)."""
+        _require(frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3 and frames.is_cuda and frames.is_contiguous(),
+                 "gray_pyramid_step: frames must be a contiguous CUDA uint8 tensor of shape (F, H, W, 3)")
+        F, H, W, _ = frames.shape
+        _require(pyr.dtype == torch.uint8 and pyr.is_contiguous() and pyr.shape[0] == F, "gray_pyramid_step: pyr must be (F, bytes) uint8")
+        n = (F - first + step - 1) // step if first < F else 0
+        if n <= 0:
+            return
+        with torch.cuda.device(frames.device):
+            N.check(N.lib.egl_gray_pyramid_strided(_ptr(frames[first]), n, H, W, frames.stride(1), step * frames.stride(0), max_level,
+                                                   _ptr(pyr[first]), step * pyr.stride(0), _stream()), "egl_gray_pyramid_strided")
+
     def track(self, pyr: torch.Tensor, height: int, width: int, prev: KeypointSet, prev0: int, next0: int, frame_step: int,
               max_level: int = 2, max_count: int = 10, eps: float = 0.03, out=None):
         """cv2.calcOpticalFlowPyrLK for n = prev.n_frames frame pairs (prev0 + p*step -> next0 + p*step).

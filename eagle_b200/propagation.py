@@ -84,6 +84,8 @@ class PropagatedPath:
                  thr: float = 5.0):
         self.e = engine
         self._side = None
+        self._pyr_stream = None
+        self._rounds = None
         self.keypoint_conf = keypoint_conf
         self.fit_mode, self.max_iters, self.thr = fit_mode, max_iters, thr
         self.stats = {}
@@ -112,6 +114,22 @@ class PropagatedPath:
         """The parallel pass of one piece (everything that does not need the previous piece's final state).
         Pieces after the first (first_frame > 0) carry one extra leading frame.  ``repair`` must follow.
         clip_continues: more frames follow this piece (only matters for the first-frame rescue, see FirstPieceTooShort)."""
+        # The rounds run on high-priority streams of this object, the pyramid pass on a normal one: their short launches
+        # are then scheduled into the machine as thread-block slots free up instead of queueing behind the pyramid's grid.
+        dev = frames.device
+        caller = torch.cuda.current_stream(dev)
+        if self._rounds is None:
+            self._rounds = torch.cuda.Stream(dev, priority=-1)
+            self._side = torch.cuda.Stream(dev, priority=-1)
+            self._pyr_stream = torch.cuda.Stream(dev)
+        self._rounds.wait_stream(caller)
+        with torch.cuda.stream(self._rounds):
+            self._start(frames, head_heatmaps, detect, keypoint_interval, homography_interval, calibration, first_frame, clip_continues)
+        caller.wait_stream(self._rounds)
+        for t in (frames, head_heatmaps):
+            t.record_stream(self._rounds)
+
+    def _start(self, frames, head_heatmaps, detect, keypoint_interval, homography_interval, calibration, first_frame, clip_continues) -> None:
         self.clip_continues = clip_continues
         e = self.e
         k = int(keypoint_interval)
@@ -126,7 +144,21 @@ class PropagatedPath:
         self.calibration = calibration
         self.detect = detect
         self.carry = None
-        self.pyr = e.gray_pyramid(frames, LK_MAX_LEVEL)
+        # Pyramids one step of every chain at a time, on a stream of their own: the tracker of round s only needs steps s
+        # and s + 1, so the rounds (latency-bound launches that leave the machine nearly idle) run underneath the
+        # HBM-bound pyramid pass instead of after it.
+        main = torch.cuda.current_stream(dev)
+        self.pyr = e.alloc_pyramid(frames.shape[0], Himg, Wimg, LK_MAX_LEVEL, device=dev)
+        pyr_ready = []
+        self._pyr_stream.wait_stream(main)
+        with torch.cuda.stream(self._pyr_stream):
+            for s_ in range(min(k, F)):
+                if s_ == 0 and self.base:
+                    e.gray_pyramid_step(frames, self.pyr, 0, frames.shape[0], LK_MAX_LEVEL)    # the carried leading frame
+                e.gray_pyramid_step(frames, self.pyr, self.base + s_, k, LK_MAX_LEVEL)
+                pyr_ready.append(self._pyr_stream.record_event())
+        self.pyr.record_stream(self._pyr_stream)
+        frames.record_stream(self._pyr_stream)
         st = self.st = _Sets(k, nc, dev)
         idx = np.arange(k)[:, None] + np.arange(nc)[None, :] * k
         self.sched_h = (((idx + self.g0) % homography_interval) == 0) & (idx < F)
@@ -153,9 +185,6 @@ class PropagatedPath:
         flow_cnt = torch.full((k, nc), 1 << 20, dtype=torch.int32, device=dev)
         pts = torch.empty((k, nc, N.ORDER_STRIDE, 2), dtype=torch.float32, device=dev)
         pst = torch.empty((k, nc, N.ORDER_STRIDE), dtype=torch.uint8, device=dev)
-        main = torch.cuda.current_stream(dev)
-        if self._side is None:
-            self._side = torch.cuda.Stream(dev)
         side = self._side
         tracked = None
         for s in range(k):
@@ -174,12 +203,14 @@ class PropagatedPath:
                 ready = main.record_event()
                 with torch.cuda.stream(side):
                     side.wait_event(ready)
+                    side.wait_event(pyr_ready[s]); side.wait_event(pyr_ready[s + 1])
                     e.track(self.pyr, Himg, Wimg, snap, self.base + s, self.base + s + 1, k, LK_MAX_LEVEL, LK_MAX_COUNT, LK_EPS,
                             out=(pts[s + 1, :n_next], pst[s + 1, :n_next]))
                     tracked = side.record_event()
                 snap.order.record_stream(side); snap.count.record_stream(side)
             self._fit_commit(s, 0, n_s)
 
+        main.wait_stream(self._pyr_stream)   # repairs and single-frame flows may touch any pyramid row
         self._flow_cnt = flow_cnt
 
     def repair(self, carry: dict | None) -> None:

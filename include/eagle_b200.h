@@ -224,6 +224,13 @@ int64_t egl_pyramid_bytes(int H, int W, int max_level);
 int egl_gray_pyramid(const uint8_t *frames, int F, int H, int W, size_t row_stride, size_t frame_stride, int max_level,
                      uint8_t *pyr, void *stream);
 
+/* The same for a strided subset of a clip: frame p is read at frames + p * frame_stride and its pyramid written at
+ * pyr + p * pyr_stride (0 = egl_pyramid_bytes, i.e. dense).  With frame_stride = k frames and pyr_stride = k pyramids the
+ * call builds the pyramids of one step of every chain (frames s, s + k, s + 2k, ...), which is the order the chain-parallel
+ * propagation needs them in: the tracker of round s only waits for steps s and s + 1. */
+int egl_gray_pyramid_strided(const uint8_t *frames, int F, int H, int W, size_t row_stride, size_t frame_stride, int max_level,
+                             uint8_t *pyr, size_t pyr_stride, void *stream);
+
 /*
  * cv2.calcOpticalFlowPyrLK(prev_gray, curr_gray, prev_points, None, winSize=(15,15), maxLevel,
  * criteria=(EPS|COUNT, max_count, eps)) (coordinate_model.py:431-435, lk_params :65), bit-exact with

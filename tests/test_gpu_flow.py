@@ -56,6 +56,24 @@ def _keypoint_set(points_per_frame, dev="cuda"):
     return KeypointSet(None, None, t(xy), t(order), t(count), torch.zeros((n, 64), dtype=torch.uint8, device=dev))
 
 
+
+def test_strided_pyramid_equals_dense(engine):
+    """egl_gray_pyramid_strided: the pyramids of one step of every chain at a time (frames s, s + k, ...) fill the same
+    buffer, byte for byte, as one dense pass -- at an interval that does not divide the clip and with a leading frame."""
+    rng = np.random.default_rng(4)
+    F, H, W, k = 23, 96, 160, 4
+    frames = torch.from_numpy(rng.integers(0, 256, (F, H, W, 3), dtype=np.uint8)).cuda()
+    dense = engine.gray_pyramid(frames, 2)
+    for base in (0, 1):
+        pyr = engine.alloc_pyramid(F, H, W, 2)
+        pyr.fill_(0xAB)
+        if base:
+            engine.gray_pyramid_step(frames, pyr, 0, F, 2)
+        for s in range(k):
+            engine.gray_pyramid_step(frames, pyr, base + s, k, 2)
+        torch.cuda.synchronize()
+        assert torch.equal(pyr, dense), base
+
 @pytest.mark.parametrize("shape", [(77, 101), (360, 640), (1080, 1920), (33, 18), (90, 160), (101, 256), (37, 48), (64, 1280), (720, 1280)])
 def test_gray_pyramid_matches_oracle(engine, shape):
     H, W = shape
