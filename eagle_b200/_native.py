@@ -33,6 +33,8 @@ lib.egl_last_error.restype = C.c_char_p
 lib.egl_sm_count.restype = _i
 lib.egl_build_flags.restype = _i
 lib.egl_preprocess_u8.argtypes = [_vp, _i, _i, _i, _sz, _sz, _vp, _vp]
+lib.egl_preprocess_u8_letterbox.argtypes = [_vp, _i, _i, _i, _sz, _sz, _vp, _vp, _i, _i, _vp]
+lib.egl_preprocess_u8_letterbox.restype = _i
 lib.egl_upload_frames.argtypes = [_vp, _i, _sz, _vp, _i]
 lib.egl_decode_heatmaps.argtypes = [_vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]
 lib.egl_decode_logits.argtypes = [_vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]
@@ -64,7 +66,7 @@ EXPORTS = ("egl_version", "egl_last_error", "egl_sm_count", "egl_build_flags", "
            "egl_synthesize_keypoints", "egl_fit_homography", "egl_select_homography", "egl_project_points", "egl_pyramid_bytes",
            "egl_gray_pyramid", "egl_track_keypoints", "egl_filter_flow", "egl_merge_keypoints", "egl_calibrate_keypoints",
            "egl_fit_homography_masked", "egl_commit_fit", "egl_refine_keypoints", "egl_fit_homography_subpixel",
-           "egl_select_homography_chunk", "egl_upload_frames", "egl_gray_pyramid_strided")
+           "egl_select_homography_chunk", "egl_upload_frames", "egl_gray_pyramid_strided", "egl_preprocess_u8_letterbox")
 
 if lib.egl_version() != ABI_VERSION:
     raise NativeError(f"libeagle_b200.so has ABI {lib.egl_version()}, this package expects {ABI_VERSION}; rebuild")

@@ -51,22 +51,33 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_native(force: bool = False, verbose: bool = False) -> str:
+VARIANTS_LIB = os.path.join(os.path.dirname(PKG), "tools", "_variants", "libeagle_b200_variants.so")
+
+
+def build_variants(verbose: bool = False) -> str:
+    """The measurement build (-DEGL_BENCH_VARIANTS: A/B kernels and EGL_*_VARIANT / EGL_UPLOAD_* switches) as a SEPARATE
+    library under tools/_variants/, next to the shipped one: probes load it by path, the package never does."""
+    os.makedirs(os.path.dirname(VARIANTS_LIB), exist_ok=True)
+    return build_native(True, verbose, lib=VARIANTS_LIB, objdir=os.path.join(PKG, "build", "variants"), variants=True)
+
+
+def build_native(force: bool = False, verbose: bool = False, *, lib: str = LIB, objdir: str | None = None, variants: bool = False) -> str:
     """Compile every .cu under csrc/ into one shared object; returns its path."""
     build_assemble(force)
     if not force and not _stale():
         return LIB
     nvcc = nvcc_path()
     objs = []
-    os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
+    objdir = objdir or os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
     common = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + ARCH
-    if os.environ.get("EGL_BENCH_VARIANTS") == "1":   # A/B kernels + EGL_*_VARIANT switches (tools/sweep.py, tools/sanitize.sh)
+    if variants or os.environ.get("EGL_BENCH_VARIANTS") == "1":   # A/B kernels + EGL_*_VARIANT switches (tools/sweep.py, tools/sanitize.sh)
         common += ["-DEGL_BENCH_VARIANTS"]
     if verbose:
         common += ["-Xptxas", "-v"]
     procs = []
     for src in SOURCES:
-        obj = os.path.join(PKG, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
         cmd = [nvcc, "-c", os.path.join(CSRC, src), "-o", obj] + common
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
@@ -80,9 +91,12 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(f"--- nvcc {src} ---\n{out}\n")
     if failed:
         raise RuntimeError("nvcc failed; see output above")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ARCH + ["-Xcompiler", "-fPIC", "-lcudart", "-lpthread"])
-    return LIB
+    subprocess.check_call([nvcc, "-shared", "-o", lib] + objs + ARCH + ["-Xcompiler", "-fPIC", "-lcudart", "-lpthread"])
+    return lib
 
 
 if __name__ == "__main__":
-    print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variants" in sys.argv:
+        print(build_variants(verbose="-v" in sys.argv))
+    else:
+        print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))

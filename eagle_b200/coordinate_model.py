@@ -219,6 +219,7 @@ class CoordinateModel:
         # measured on a 16-core box: 4 threads 38 GB/s, 6 -> 48, 8 -> 50, 16 -> 44 (they crowd out the assembler and the
         # thread that enqueues the kernels), so: the cores this process may run on minus one, at most 8
         self.copy_threads = upload_threads(len(os.sched_getaffinity(0)))
+        self.uploads_in_flight = 1     # 2: chunk c+1's upload starts before chunk c's has been waited for (see DenseStream)
         self.profile = False           # time H2D / kernels / D2H of every chunk with CUDA events (last_stats)
         self.always_propagate = False  # route every clip through PropagatedPath (tests)
         self.piece_frames = 2048       # sparse cadence: frames resident in HBM at a time (12.7 GB of 1080p frames + 5.6 GB of pyramids)
@@ -288,7 +289,8 @@ class CoordinateModel:
             if self._stream is not None:
                 self._stream.close()
             from .streaming import DenseStream
-            self._stream, self._stream_key = DenseStream(self.path.engine, height, width, chunk, copy_threads=self.copy_threads), key
+            self._stream, self._stream_key = DenseStream(self.path.engine, height, width, chunk, copy_threads=self.copy_threads,
+                                                         uploads_in_flight=self.uploads_in_flight), key
 
         def assemble(objs, first, a, out):
             assemble_frames(objs, fps, first, a["xy"], a["order"], a["count"], None, a["inlier_mask"], a["status"], a["attempted"],

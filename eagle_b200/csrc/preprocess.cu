@@ -51,10 +51,24 @@ __device__ __forceinline__ void axis_tap(int d, double scale, int* ofs, int* c0,
 // pixels, (S[y0][x0] + S[y0][x0+1] + S[y0+1][x0] + S[y0+1][x0+1] + 2) >> 2 with x0 = (s/2)(2dx+1) - 1 (the same
 // value, bit for bit -- it is also OpenCV's own INTER_AREA shortcut at s = 2), at a third of the
 // integer instructions; `half_scale` = s/2 is passed in scale_x's place.
-template <int R, bool kMean4>
+//
+// kDual: the same resized uint8 image also leaves as the detector's letterboxed input (ultralytics LetterBox + predictor
+// preprocess for imgsz = 960 on a 16:9 frame: INTER_LINEAR resize to 960x540, rows of 114 above and below up to a
+// stride-32 multiple, BGR -> RGB, HWC -> CHW, float32, / 255): out2[f][plane][pad_top + dy][dx] = v / 255, the pad rows
+// written by the first and the last band of a frame.  One read of the frame feeds both networks.
+//
+// kPair (exact 2x decimation, 1080p -> 540x960: the headline case): the byte-wise reads of the general code make the
+// kernel shared-memory bound -- four LDS.U8 per output value, two wavefronts each because 32 lanes x 6 bytes span 192
+// bytes: 8 wavefronts of the SM's one-per-cycle LSU data path per 32 outputs, 98.7 % of its peak in the ncu capture, and
+// the limit instead of HBM as soon as the SM clock sags under the power cap.  Here a thread takes two ADJACENT output
+// pixels, i.e. 12 contiguous source bytes per row = three aligned 32-bit words (lane stride 3 words: conflict-free, one
+// wavefront per load), sorts the bytes with two PRMT per row and forms every four-byte sum with two dp4a: one wavefront
+// and about 8 instructions per output value instead of 8 and 15.  The two floats of a plane leave as one 64-bit store.
+template <int R, bool kMean4, bool kDual = false, bool kPair = false>
 __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* __restrict__ frames, int H, int W,
                                                                  size_t row_stride, size_t frame_stride, double scale_x,
-                                                                 double scale_y, int use_bulk, float* __restrict__ out) {
+                                                                 double scale_y, int use_bulk, float* __restrict__ out,
+                                                                 float* __restrict__ out2 = nullptr, int out2_h = 0, int pad_top = 0) {
     extern __shared__ __align__(128) unsigned char s_rows[];  // 2R row slots, each padded to a multiple of 16 B
     __shared__ uint64_t s_bar;
     constexpr int kBands = kOutH / R;
@@ -129,6 +143,40 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* 
 
     __syncthreads();  // barrier init (bulk) / staged rows (fallback) visible
     if (use_bulk) mbar_wait(&s_bar, 0);
+    if constexpr (kPair) {
+        static_assert(kMean4, "kPair is the 2x2-mean case");
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t* r0 = reinterpret_cast<const uint32_t*>(s_rows + (size_t)slot[2 * r] * row_pad);
+            const uint32_t* r1 = reinterpret_cast<const uint32_t*>(s_rows + (size_t)slot[2 * r + 1] * row_pad);
+            float* dst = out + ((size_t)f * 3 * kOutH + dy0 + r) * kOutW;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int j = tid + kPreThreads * k;   // output pixels 2j, 2j+1 <- source pixels 4j .. 4j+3 = bytes [12j, 12j+12)
+                const uint32_t a0 = r0[3 * j], a1 = r0[3 * j + 1], a2 = r0[3 * j + 2];   // [B0 G0 R0 B1] [G1 R1 B2 G2] [R2 B3 G3 R3]
+                const uint32_t c0 = r1[3 * j], c1 = r1[3 * j + 1], c2 = r1[3 * j + 2];
+                const uint32_t xa = __byte_perm(a0, a1, 0x5241), xc = __byte_perm(c0, c1, 0x5241);   // [G0 G1 R0 R1]
+                const uint32_t ya = __byte_perm(a1, a2, 0x6352), yc = __byte_perm(c1, c2, 0x6352);   // [B2 B3 G2 G3]
+                // sums of four bytes + 2 (dp4a with a 0/1 selector), then >> 2: the rounded 2x2 mean
+                const int bA = (int)(__dp4a(a0, 0x01000001u, __dp4a(c0, 0x01000001u, 2u)) >> 2);
+                const int gA = (int)(__dp4a(xa, 0x00000101u, __dp4a(xc, 0x00000101u, 2u)) >> 2);
+                const int rA = (int)(__dp4a(xa, 0x01010000u, __dp4a(xc, 0x01010000u, 2u)) >> 2);
+                const int bB = (int)(__dp4a(ya, 0x00000101u, __dp4a(yc, 0x00000101u, 2u)) >> 2);
+                const int gB = (int)(__dp4a(ya, 0x01010000u, __dp4a(yc, 0x01010000u, 2u)) >> 2);
+                const int rB = (int)(__dp4a(a2, 0x01000001u, __dp4a(c2, 0x01000001u, 2u)) >> 2);
+                const int vA[3] = {rA, gA, bA}, vB[3] = {rB, gB, bB};   // planes are R, G, B
+#pragma unroll
+                for (int plane = 0; plane < 3; ++plane) {
+                    __stcs(reinterpret_cast<float2*>(dst + (size_t)plane * kOutH * kOutW + 2 * j),
+                           make_float2(__fmul_rn(__fsub_rn((float)vA[plane], mean[plane]), den[plane]),
+                                       __fmul_rn(__fsub_rn((float)vB[plane], mean[plane]), den[plane])));
+                    if (kDual)
+                        __stcs(reinterpret_cast<float2*>(out2 + (((size_t)f * 3 + plane) * out2_h + pad_top + dy0 + r) * kOutW + 2 * j),
+                               make_float2(__fdiv_rn((float)vA[plane], 255.f), __fdiv_rn((float)vB[plane], 255.f)));
+                }
+            }
+        }
+    } else {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const uint8_t* r0 = s_rows + (size_t)slot[2 * r] * row_pad;
@@ -149,7 +197,24 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* 
                 }
                 const int plane = 2 - c;
                 __stcs(dst + (size_t)plane * kOutH * kOutW + kPreThreads * k, __fmul_rn(__fsub_rn((float)v, mean[plane]), den[plane]));
+                if (kDual)
+                    __stcs(out2 + (((size_t)f * 3 + plane) * out2_h + pad_top + dy0 + r) * kOutW + tid + kPreThreads * k,
+                           __fdiv_rn((float)v, 255.f));
             }
+        }
+    }
+    }
+    if (kDual) {
+        // letterbox border: rows [0, pad_top) by the first band of the frame, rows [pad_top + 540, out2_h) by the last
+        const float border = __fdiv_rn(114.f, 255.f);
+        const bool first = dy0 == 0, last = dy0 + R == kOutH;
+        if (first || last) {
+            const int y_lo = first ? 0 : pad_top + kOutH, y_hi = first ? pad_top : out2_h;
+            for (int plane = 0; plane < 3; ++plane)
+                for (int y = y_lo; y < y_hi; ++y)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        __stcs(out2 + (((size_t)f * 3 + plane) * out2_h + y) * kOutW + tid + kPreThreads * k, border);
         }
     }
 }
@@ -158,8 +223,8 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* 
 
 using namespace egl;
 
-extern "C" int egl_preprocess_u8(const uint8_t* frames, int F, int H, int W, size_t row_stride, size_t frame_stride,
-                                 float* out, void* stream) {
+static int preprocess_impl(const uint8_t* frames, int F, int H, int W, size_t row_stride, size_t frame_stride, float* out, float* out2,
+                           int out2_h, int pad_top, void* stream) {
     if (F == 0) return 0;  // empty batch: nothing to enqueue, pointers may be null
     EGL_REQUIRE(frames && out, EGL_ERR_NULL, "egl_preprocess_u8: null pointer");
     EGL_REQUIRE(F >= 0 && H >= 2 && W >= 2, EGL_ERR_SHAPE, "egl_preprocess_u8: bad shape %dx%d", H, W);
@@ -202,11 +267,47 @@ extern "C" int egl_preprocess_u8(const uint8_t* frames, int F, int H, int W, siz
             if (rc) return rc;
         }
         kernel<<<(unsigned)(F * (kOutH / rows)), kPreThreads, smem, st>>>(frames, H, W, row_stride, frame_stride, arg_x, arg_y,
-                                                                         use_bulk, out);
+                                                                         use_bulk, out, out2, out2_h, pad_top);
         return 0;
     };
+    // exact 2x decimation (1080p): word loads + dp4a (kPair); EGL_PREPROCESS_PAIR=0 in measurement builds selects the byte-wise code
+    bool pair = mean4 && W == 2 * kOutW;
+#ifdef EGL_BENCH_VARIANTS
+    static const char* pair_env = getenv("EGL_PREPROCESS_PAIR");
+    if (pair_env && atoi(pair_env) == 0) pair = false;
+#endif
     int rc;
-    if (mean4) {
+    if (pair) {
+        if (R == 3 || R == 6) R = 4;
+        if (out2) {
+            switch (R) {
+                case 1: rc = launch(preprocess_kernel<1, true, true, true>, 1); break;
+                case 2: rc = launch(preprocess_kernel<2, true, true, true>, 2); break;
+                default: rc = launch(preprocess_kernel<4, true, true, true>, 4); break;
+            }
+        } else {
+            switch (R) {
+                case 1: rc = launch(preprocess_kernel<1, true, false, true>, 1); break;
+                case 2: rc = launch(preprocess_kernel<2, true, false, true>, 2); break;
+                default: rc = launch(preprocess_kernel<4, true, false, true>, 4); break;
+            }
+        }
+    } else if (out2) {
+        if (R == 3 || R == 6) R = 4;
+        if (mean4) {
+            switch (R) {
+                case 1: rc = launch(preprocess_kernel<1, true, true>, 1); break;
+                case 2: rc = launch(preprocess_kernel<2, true, true>, 2); break;
+                default: rc = launch(preprocess_kernel<4, true, true>, 4); break;
+            }
+        } else {
+            switch (R) {
+                case 1: rc = launch(preprocess_kernel<1, false, true>, 1); break;
+                case 2: rc = launch(preprocess_kernel<2, false, true>, 2); break;
+                default: rc = launch(preprocess_kernel<4, false, true>, 4); break;
+            }
+        }
+    } else if (mean4) {
         switch (R) {
             case 1: rc = launch(preprocess_kernel<1, true>, 1); break;
             case 2: rc = launch(preprocess_kernel<2, true>, 2); break;
@@ -228,4 +329,24 @@ extern "C" int egl_preprocess_u8(const uint8_t* frames, int F, int H, int W, siz
     }
     if (rc) return rc;
     return cuda_status(cudaGetLastError(), "egl_preprocess_u8: kernel launch");
+}
+
+extern "C" int egl_preprocess_u8(const uint8_t* frames, int F, int H, int W, size_t row_stride, size_t frame_stride,
+                                 float* out, void* stream) {
+    return preprocess_impl(frames, F, H, W, row_stride, frame_stride, out, nullptr, 0, 0, stream);
+}
+
+extern "C" int egl_preprocess_u8_letterbox(const uint8_t* frames, int F, int H, int W, size_t row_stride, size_t frame_stride,
+                                           float* out, float* out_detector, int detector_h, int pad_top, void* stream) {
+    if (F == 0) return 0;
+    EGL_REQUIRE(out_detector, EGL_ERR_NULL, "egl_preprocess_u8_letterbox: out_detector is null");
+    EGL_REQUIRE((reinterpret_cast<uintptr_t>(out_detector) & 15) == 0, EGL_ERR_ALIGN, "egl_preprocess_u8_letterbox: out_detector must be 16-byte aligned");
+    EGL_REQUIRE(pad_top >= 0 && detector_h >= pad_top + kOutH && detector_h <= kOutH + 64, EGL_ERR_SHAPE,
+                "egl_preprocess_u8_letterbox: need 0 <= pad_top and pad_top + 540 <= detector_h <= 604 (got pad_top %d, detector_h %d)", pad_top, detector_h);
+    // The detector image shares the keypoint network's resized frame only when LetterBox's own resize is W x H -> 960 x 540,
+    // i.e. round(W r) == 960 and round(H r) == 540 for r = min(960 / H, 960 / W): 16:9 frames at imgsz 960.
+    const double r = fmin(960.0 / H, 960.0 / W);
+    EGL_REQUIRE((int)nearbyint(W * r) == kOutW && (int)nearbyint(H * r) == kOutH, EGL_ERR_SHAPE,
+                "egl_preprocess_u8_letterbox: a %dx%d frame does not letterbox to 960x540 at imgsz 960", W, H);
+    return preprocess_impl(frames, F, H, W, row_stride, frame_stride, out, out_detector, detector_h, pad_top, stream);
 }

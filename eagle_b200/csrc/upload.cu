@@ -15,6 +15,10 @@
 
 #include "common.cuh"
 
+#ifdef EGL_BENCH_VARIANTS
+#include <immintrin.h>
+#endif
+
 namespace egl {
 
 constexpr int kUpMaxThreads = 32;
@@ -40,8 +44,37 @@ struct UploadJob {
     cudaError_t err;
 };
 
-static UploadWorker g_up[kUpMaxThreads];
-static pthread_mutex_t g_up_lock = PTHREAD_MUTEX_INITIALIZER;
+#ifdef EGL_BENCH_VARIANTS
+// A/B of the staging copy (tools/upload_variants_probe.py): 0 memcpy (the shipped choice), 1 AVX2 loads + non-temporal
+// stores (no read-for-ownership of the ring, nothing of it left in the caches), 2 `rep movsb`
+static int g_up_copy_mode = 0;
+static unsigned g_up_alloc_flags = cudaHostAllocDefault;
+__attribute__((target("avx2"))) static void copy_nontemporal(unsigned char* d, const unsigned char* s, size_t n) {
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        const __m256i a = _mm256_loadu_si256((const __m256i*)(s + i)), b = _mm256_loadu_si256((const __m256i*)(s + i + 32));
+        const __m256i c = _mm256_loadu_si256((const __m256i*)(s + i + 64)), e = _mm256_loadu_si256((const __m256i*)(s + i + 96));
+        _mm256_stream_si256((__m256i*)(d + i), a); _mm256_stream_si256((__m256i*)(d + i + 32), b);
+        _mm256_stream_si256((__m256i*)(d + i + 64), c); _mm256_stream_si256((__m256i*)(d + i + 96), e);
+    }
+    if (i < n) memcpy(d + i, s + i, n - i);
+    _mm_sfence();   // the DMA engine must see the data: non-temporal stores are weakly ordered
+}
+static void stage_copy(unsigned char* d, const unsigned char* s, size_t n) {
+    if (g_up_copy_mode == 1) copy_nontemporal(d, s, n);
+    else if (g_up_copy_mode == 2) { __asm__ volatile("rep movsb" : "+D"(d), "+S"(s), "+c"(n) : : "memory"); }
+    else memcpy(d, s, n);
+}
+#else
+static inline void stage_copy(unsigned char* d, const unsigned char* s, size_t n) { memcpy(d, s, n); }
+constexpr unsigned g_up_alloc_flags = cudaHostAllocDefault;
+#endif
+
+// Two independent sets of workers (rings, streams): a second call may run while the first one drains its last DMAs,
+// which is how the streaming layer keeps the link busy across chunk boundaries.  A third concurrent call waits.
+constexpr int kUpSets = 2;
+static UploadWorker g_up_sets[kUpSets][kUpMaxThreads];
+static pthread_mutex_t g_up_lock[kUpSets] = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER};
 
 static cudaError_t upload_worker_init(UploadWorker& w, int device) {
     if (w.device == device) return cudaSuccess;
@@ -53,7 +86,7 @@ static cudaError_t upload_worker_init(UploadWorker& w, int device) {
     cudaError_t e = cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking);
     for (int s = 0; s < kUpSlots && e == cudaSuccess; ++s) {
         e = cudaEventCreateWithFlags(&w.ev[s], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaHostAlloc((void**)&w.slot[s], kUpSlice, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&w.slot[s], kUpSlice, g_up_alloc_flags);
     }
     if (e == cudaSuccess) w.device = device;
     return e;
@@ -76,7 +109,7 @@ static void* upload_thread(void* arg) {
         unsigned char* dst = j.dst + (size_t)f * j.bytes + o;
         if (used[q]) j.err = cudaEventSynchronize(w.ev[q]);  // the DMA that last read this slot has finished
         if (j.err != cudaSuccess) break;
-        memcpy(w.slot[q], src, n);
+        stage_copy(w.slot[q], src, n);
         j.err = cudaMemcpyAsync(dst, w.slot[q], n, cudaMemcpyHostToDevice, w.stream);
         if (j.err == cudaSuccess) j.err = cudaEventRecord(w.ev[q], w.stream);
         used[q] = true;
@@ -98,7 +131,11 @@ extern "C" int egl_upload_frames(const void* const* frames, int n_frames, size_t
     for (int i = 0; i < n_frames; ++i) EGL_REQUIRE(frames[i], EGL_ERR_NULL, "egl_upload_frames: frame %d is null", i);
 #ifdef EGL_BENCH_VARIANTS
     static const char* slice_env = getenv("EGL_UPLOAD_SLICE_KB");
-    if (slice_env && g_up[0].device < 0) kUpSlice = (size_t)atoi(slice_env) << 10;
+    if (slice_env && g_up_sets[0][0].device < 0 && g_up_sets[1][0].device < 0) kUpSlice = (size_t)atoi(slice_env) << 10;
+    static const char* copy_env = getenv("EGL_UPLOAD_COPY");
+    if (copy_env) g_up_copy_mode = atoi(copy_env);
+    static const char* wc_env = getenv("EGL_UPLOAD_WC");
+    if (wc_env && atoi(wc_env) && g_up_sets[0][0].device < 0 && g_up_sets[1][0].device < 0) g_up_alloc_flags = cudaHostAllocWriteCombined;
 #endif
     int nt = n_threads < 1 ? 1 : (n_threads > kUpMaxThreads ? kUpMaxThreads : n_threads);
     const int per_frame = (int)((bytes_per_frame + kUpSlice - 1) / kUpSlice);
@@ -108,7 +145,12 @@ extern "C" int egl_upload_frames(const void* const* frames, int n_frames, size_t
     int device = 0;
     int rc = cuda_status(cudaGetDevice(&device), "egl_upload_frames: cudaGetDevice");
     if (rc) return rc;
-    pthread_mutex_lock(&g_up_lock);  // one upload at a time per process: the ring and its streams are shared state
+    int set = 0;  // a set of workers serves one call at a time: its rings and streams are shared state
+    if (pthread_mutex_trylock(&g_up_lock[0]) != 0) {
+        set = 1;
+        pthread_mutex_lock(&g_up_lock[1]);
+    }
+    UploadWorker* g_up = g_up_sets[set];
     UploadJob jobs[kUpMaxThreads];
     pthread_t th[kUpMaxThreads];
     cudaError_t err = cudaSuccess;
@@ -125,6 +167,6 @@ extern "C" int egl_upload_frames(const void* const* frames, int n_frames, size_t
             if (jobs[k].err != cudaSuccess) err = jobs[k].err;
         if (started == 0 && err == cudaSuccess) err = cudaErrorLaunchFailure;  // no worker thread could be created (fewer than asked for is fine: the slices are shared out dynamically)
     }
-    pthread_mutex_unlock(&g_up_lock);
+    pthread_mutex_unlock(&g_up_lock[set]);
     return cuda_status(err, "egl_upload_frames");
 }

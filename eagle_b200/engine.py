@@ -60,6 +60,19 @@ class Projection:
     bounds: torch.Tensor    # (F, 4) float64 [bottom_left, top_left, top_right, bottom_right] x; NaN = None
 
 
+def letterbox_geometry(h: int, w: int, imgsz: int = 960, stride: int = 32):
+    """ultralytics 8.3.184 LetterBox(new_shape=(imgsz, imgsz), auto=True, scaleup=True, center=True, stride=stride) for an
+    h x w frame: (new_w, new_h, pad_left, pad_top, out_w, out_h) -- the size cv2.resize is asked for, the border
+    cv2.copyMakeBorder adds on the left / top, and the shape of the detector's input."""
+    r = min(imgsz / h, imgsz / w)
+    new_w, new_h = int(round(w * r)), int(round(h * r))
+    dw, dh = (imgsz - new_w) % stride, (imgsz - new_h) % stride   # auto=True: pad only to a multiple of the stride
+    dw, dh = dw / 2, dh / 2
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    return new_w, new_h, left, top, new_w + left + right, new_h + top + bottom
+
+
 class GeometryEngine:
     """Thin, stateless-per-call wrapper; ``device`` must be a CUDA device."""
 
@@ -101,6 +114,30 @@ class GeometryEngine:
             N.check(N.lib.egl_preprocess_u8(_ptr(frames), F, H, W, frames.stride(1), frames.stride(0) if F > 1 else H * frames.stride(1),
                                             _ptr(out), _stream()), "egl_preprocess_u8")
         return out
+
+    def preprocess_with_detector_input(self, frames: torch.Tensor, out: torch.Tensor | None = None, out_detector: torch.Tensor | None = None,
+                                       imgsz: int = 960, stride: int = 32):
+        """K1 with its second output: (F, 3, 540, 960) for the keypoint network AND the detector's letterboxed input
+        (F, 3, detector_h, 960) float32 RGB in [0, 1] -- what ultralytics' LetterBox + predictor preprocess make of the frame
+        before `self.detector_model(frame, ...)` (coordinate_model.py:568) runs -- from ONE read of the uint8 frames.
+        Frames whose letterbox resize is not 960x540 (see letterbox_geometry) are rejected."""
+        _require(frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3 and frames.is_cuda,
+                 "preprocess: frames must be a CUDA uint8 tensor of shape (F, H, W, 3)")
+        _require(frames.stride(3) == 1 and frames.stride(2) == 3, "preprocess: pixels must be packed B,G,R bytes (strides 3, 1)")
+        F, H, W, _ = frames.shape
+        new_w, new_h, left, top, det_w, det_h = letterbox_geometry(H, W, imgsz, stride)
+        _require((new_w, new_h) == (N.MODEL_W, N.MODEL_H) and left == 0 and det_w == N.MODEL_W,
+                 f"preprocess_with_detector_input: a {W}x{H} frame letterboxes to {new_w}x{new_h} at imgsz {imgsz}, not to 960x540")
+        if out is None:
+            out = torch.empty((F, 3, N.MODEL_H, N.MODEL_W), dtype=torch.float32, device=frames.device)
+        if out_detector is None:
+            out_detector = torch.empty((F, 3, det_h, det_w), dtype=torch.float32, device=frames.device)
+        _require(tuple(out_detector.shape) == (F, 3, det_h, det_w) and out_detector.is_contiguous() and out_detector.dtype == torch.float32,
+                 f"preprocess_with_detector_input: out_detector must be a contiguous float32 tensor of shape {(F, 3, det_h, det_w)}")
+        with torch.cuda.device(frames.device):
+            N.check(N.lib.egl_preprocess_u8_letterbox(_ptr(frames), F, H, W, frames.stride(1), frames.stride(0) if F > 1 else H * frames.stride(1),
+                                                      _ptr(out), _ptr(out_detector), det_h, top, _stream()), "egl_preprocess_u8_letterbox")
+        return out, out_detector
 
     # -- K2 ---------------------------------------------------------------------------------
     def alloc_keypoints(self, F: int) -> KeypointSet:

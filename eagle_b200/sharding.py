@@ -103,6 +103,17 @@ def gather_to_rank0(records: torch.Tensor, counts: Sequence[int], group=None) ->
     return None
 
 
+_SIDE: dict = {}
+
+
+def _side_stream(device):
+    """One high-priority stream per device for the small kernels that run under the bandwidth-bound ones."""
+    key = (device.type, device.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device, priority=-1)
+    return _SIDE[key]
+
+
 class FewLandmarksError(RuntimeError):
     """A frame decoded fewer than four landmarks: the reference rescues it by optical flow from its neighbours
     (coordinate_model.py:287-311), which the per-frame sharded path cannot do.  Use run_sharded_propagated with
@@ -153,6 +164,11 @@ def run_sharded(path, heatmaps_local, objects_local: Sequence[dict], width: int,
     kps, fits = [], []
     x = None
     fit_iter = iter(fchunks) if fchunks is not None else None
+    # Streamed chunks: synthesis + fit of chunk c (a few hundred microseconds of small, latency-bound kernels) run on a
+    # high-priority side stream under the HBM-bound K1 / decode of chunk c+1.
+    overlap = e.device.type == "cuda" and not torch.is_tensor(heatmaps_local)
+    main = torch.cuda.current_stream(e.device) if overlap else None
+    side = _side_stream(e.device) if overlap else None
     for hm in chunks:
         if fit_iter is not None:
             fr = next(fit_iter)
@@ -160,10 +176,22 @@ def run_sharded(path, heatmaps_local, objects_local: Sequence[dict], width: int,
                 x = torch.empty((fr.shape[0], 3, 540, 960), dtype=torch.float32, device=e.device)
             e.preprocess(fr, out=x[:fr.shape[0]])
         kp = e.decode(hm, width, height, path.keypoint_conf)
-        if path.synthesis:
-            e.synthesize(kp)
         kps.append(kp)
-        fits.append(e.fit(kp, mode=path.fit_mode, K=path.max_iters, thr=path.thr))
+        if overlap:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                if path.synthesis:
+                    e.synthesize(kp)
+                fits.append(e.fit(kp, mode=path.fit_mode, K=path.max_iters, thr=path.thr))
+        else:
+            if path.synthesis:
+                e.synthesize(kp)
+            fits.append(e.fit(kp, mode=path.fit_mode, K=path.max_iters, thr=path.thr))
+    if overlap:
+        main.wait_stream(side)
+        for f in fits:   # allocated on the side stream, read on the main stream from here on
+            for t in (f.H, f.used_mask, f.inlier_mask, f.status):
+                t.record_stream(main)
     cat = lambda xs: torch.cat(xs) if len(xs) > 1 else xs[0]
     kp = KeypointSet(None, None, cat([k.xy for k in kps]), cat([k.order for k in kps]), cat([k.count for k in kps]))
     fit = FitResult(cat([f.H for f in fits]), cat([f.used_mask for f in fits]), cat([f.inlier_mask for f in fits]),

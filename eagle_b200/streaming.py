@@ -54,7 +54,8 @@ def unpack_record(buf: np.ndarray, n: int, P: int) -> dict:
 class DenseStream:
     """Reusable buffers + streams of the per-frame cadence for one frame size."""
 
-    def __init__(self, engine: GeometryEngine, height: int, width: int, chunk: int, copy_threads: int = 8, out_slots: int = 4):
+    def __init__(self, engine: GeometryEngine, height: int, width: int, chunk: int, copy_threads: int = 8, out_slots: int = 4,
+                 uploads_in_flight: int = 1):
         self.e = engine
         dev = engine.device
         self.H, self.W, self.CH = height, width, chunk
@@ -62,7 +63,10 @@ class DenseStream:
         self.compute = torch.cuda.Stream(dev)
         self.copy_out = torch.cuda.Stream(dev)
         self.copy_threads = max(1, copy_threads)
-        self.pool = ThreadPoolExecutor(max_workers=1)   # runs the (GIL-free) upload call next to detect_objects
+        # 2: the upload of chunk c+1 is started before the one of chunk c has been waited for (the library serves two calls
+        # at once from separate rings), so the link stays busy while a call drains its last DMAs
+        self.uploads_in_flight = 2 if uploads_in_flight >= 2 else 1
+        self.pool = ThreadPoolExecutor(max_workers=2)   # runs the (GIL-free) upload calls next to detect_objects
         self.P_cap = 0
         self.slots = []
         for _ in range(2):
@@ -167,29 +171,38 @@ class DenseStream:
             part = [fr if fr.flags["C_CONTIGUOUS"] else np.ascontiguousarray(fr) for fr in frames[first:first + CH]]
             return self.pool.submit(self._upload, part, s["d_frames"])
 
-        fut_next = None
+        futs: dict = {}
+
+        def ensure_upload(c):
+            if c not in futs and c * CH < F:
+                futs[c] = start_upload(c)
+
         try:
             for c, first in enumerate(range(0, F, CH)):
                 n = min(CH, F - first)
                 s = self.slots[c & 1]
                 # ---- host: the upload runs in the library's worker threads while the detector works on the same frames
                 t0 = time.perf_counter()
-                fut = start_upload(c) if c == 0 else fut_next
+                ensure_upload(c)
                 objs = [detect_objects(frames_np[first + j]) for j in range(n)]
                 t1 = time.perf_counter()
                 all_obj.extend(objs)
+                if self.uploads_in_flight == 2:
+                    ensure_upload(c + 1)     # its slot was last read by the kernels of chunk c-1 (start_upload waits for them)
                 P = max(1, max_objects(objs))
                 if P > self.P_cap:
-                    if fut is not None:
-                        fut.result()
+                    for f_ in list(futs.values()):
+                        if f_ is not None:
+                            f_.result()
                     self._grow_points(P)
                 if s["uploaded"] is not None:
                     s["uploaded"].synchronize()          # the H2D that last read this slot's foot-point staging has finished
                 objects_to_arrays(objs, self.P_cap, out=(s["h_foot"].numpy()[:n], s["h_cnt"].numpy()[:n]))
+                fut = futs.pop(c)
                 if fut is not None:
                     t_host["upload"] += fut.result()
                 # the next chunk's upload starts before this chunk's kernels are enqueued (about a millisecond of launches)
-                fut_next = start_upload(c + 1) if first + CH < F else None
+                ensure_upload(c + 1)
                 t2 = time.perf_counter()
                 t_host["detect"] += t1 - t0
                 t_host["stage"] += t2 - t1
@@ -238,11 +251,12 @@ class DenseStream:
                     marks.append((m0, m1, m2, m3, m4, m5))
                 work.put((first, n, P, objs, oslot, done))
         finally:
-            if fut_next is not None and not fut_next.done():
-                try:
-                    fut_next.result()    # an upload still in flight writes into this object's buffers
-                except Exception:  # noqa: BLE001
-                    pass
+            for f_ in futs.values():
+                if f_ is not None and not f_.done():
+                    try:
+                        f_.result()    # an upload still in flight writes into this object's buffers
+                    except Exception:  # noqa: BLE001
+                        pass
             work.put(None)
             worker.join()
         torch.cuda.current_stream(dev).wait_stream(self.compute)

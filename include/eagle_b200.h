@@ -80,6 +80,24 @@ int egl_preprocess_u8(const uint8_t *frames, int F, int H, int W, size_t row_str
                       float *out, void *stream);
 
 /*
+ * F3 (second output of K1)  the same pass also writes the DETECTOR's input tensor, so that one read of the uint8 frame
+ * feeds both networks.  Replaces what `self.detector_model(frame, ...)` (coordinate_model.py:568) does to the frame before
+ * the network sees it -- ultralytics 8.3.184 (uv.lock:1814-1815; third-party, not vendored in the reference):
+ * LetterBox(new_shape = imgsz, auto = True, stride = 32) = cv2.resize(INTER_LINEAR) to (round(W r), round(H r)),
+ * r = min(imgsz / H, imgsz / W), cv2.copyMakeBorder with 114 up to a stride-32 multiple, then BGR -> RGB, HWC -> CHW,
+ * .float(), /= 255 (BasePredictor.preprocess).  Supported where LetterBox's resize is the keypoint network's own, W x H ->
+ * 960 x 540 (imgsz 960 on 16:9 frames: 1080p, 720p, 4K ...); anything else returns EGL_ERR_SHAPE.  A maintainer passes
+ * the tensor to the model instead of the frame (ultralytics skips its own preprocessing for BCHW float tensors).
+ *   out           as egl_preprocess_u8
+ *   out_detector  [F][3][detector_h][960] float32, RGB planes, resized uint8 / 255 in rows [pad_top, pad_top + 540),
+ *                 114 / 255 elsewhere (for 16:9 at imgsz 960: detector_h = 544, pad_top = 2)
+ * Parity: against the same cv2 calls + numpy (oracle/preprocess.py::letterbox_reference_calls); ultralytics itself is
+ * absent offline, so the restatement of ITS arithmetic is unpinned.
+ */
+int egl_preprocess_u8_letterbox(const uint8_t *frames, int F, int H, int W, size_t row_stride, size_t frame_stride,
+                                float *out, float *out_detector, int detector_h, int pad_top, void *stream);
+
+/*
  * K2  heatmaps -> landmark pixel positions.
  * Replaces KeypointModel.get_keypoints (keypoint_hrnet.py:583-594: per channel flat argmax, first
  * maximum in row-major order, score = max) and the keypoint post-processing block

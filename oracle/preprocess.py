@@ -86,3 +86,34 @@ def preprocess_restated(frame_bgr: np.ndarray) -> np.ndarray:
     mean, denom = normalise_constants()
     out = (small.astype(np.float32) - mean) * denom
     return np.ascontiguousarray(out.transpose(2, 0, 1))
+
+
+def letterbox_geometry(h: int, w: int, imgsz: int = 960, stride: int = 32):
+    """ultralytics 8.3.184 (uv.lock:1814-1815; third-party, absent here) ``LetterBox.__call__`` with the predictor's
+    arguments (new_shape = imgsz, auto = True, scaleFill = False, scaleup = True, center = True), restated from its
+    published source: (new_w, new_h, left, top, right, bottom).  PARITY UNPINNED against ultralytics itself."""
+    r = min(imgsz / h, imgsz / w)
+    new_unpad = int(round(w * r)), int(round(h * r))
+    dw, dh = imgsz - new_unpad[0], imgsz - new_unpad[1]
+    dw, dh = np.mod(dw, stride), np.mod(dh, stride)
+    dw /= 2
+    dh /= 2
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    return new_unpad[0], new_unpad[1], left, top, right, bottom
+
+
+def letterbox_reference_calls(frame_bgr: np.ndarray, imgsz: int = 960, stride: int = 32) -> np.ndarray:
+    """What ``self.detector_model(frame, ...)`` (eagle/models/coordinate_model.py:568) does to a BGR uint8 frame before the
+    network runs: LetterBox (cv2.resize INTER_LINEAR if the size changes, cv2.copyMakeBorder with 114) and
+    BasePredictor.preprocess (BGR -> RGB, HWC -> CHW, float32, / 255).  The cv2 calls are live; the sequence is the restated
+    part.  Returns float32 (3, out_h, out_w)."""
+    new_w, new_h, left, top, right, bottom = letterbox_geometry(frame_bgr.shape[0], frame_bgr.shape[1], imgsz, stride)
+    img = frame_bgr
+    if (img.shape[1], img.shape[0]) != (new_w, new_h):
+        img = cv2.resize(img, (new_w, new_h), interpolation=cv2.INTER_LINEAR)
+    img = cv2.copyMakeBorder(img, top, bottom, left, right, cv2.BORDER_CONSTANT, value=(114, 114, 114))
+    chw = np.ascontiguousarray(img[..., ::-1].transpose(2, 0, 1))
+    out = chw.astype(np.float32)
+    out /= np.float32(255)
+    return out

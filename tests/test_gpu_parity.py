@@ -373,6 +373,35 @@ def test_preprocess_golden_checksums(engine, golden_dir):
         assert sha(back) == c["resized_rgb_sha256"], key
 
 
+@pytest.mark.parametrize("w,h", [(1920, 1080), (1280, 720), (3840, 2160), (2880, 1620)])
+def test_detector_letterbox_is_the_second_output_of_k1(engine, w, h):
+    """egl_preprocess_u8_letterbox: the keypoint network's tensor is unchanged and the detector's tensor equals
+    LetterBox + predictor preprocess restated with live cv2 calls (oracle.preprocess.letterbox_reference_calls), bit for bit
+    -- uint8 resize, border value 114, RGB planes, float32 division by 255."""
+    from oracle import preprocess
+    fr = np.random.default_rng(h).integers(0, 256, (3, h, w, 3), dtype=np.uint8)
+    d = torch.from_numpy(fr).cuda()
+    x, y = engine.preprocess_with_detector_input(d)
+    assert torch.equal(x, engine.preprocess(d))
+    assert tuple(y.shape) == (3, 3, 544, 960)
+    y = y.cpu().numpy()
+    for i in range(3):
+        want = preprocess.letterbox_reference_calls(fr[i])
+        assert want.shape == y[i].shape and np.array_equal(y[i], want), (w, h, i)
+    # a buffer handed in is filled completely (borders included) and nothing else is touched
+    buf = torch.full((4, 3, 544, 960), -7.0, device="cuda")
+    engine.preprocess_with_detector_input(d, out_detector=buf[:3])
+    assert np.array_equal(buf[:3].cpu().numpy(), y) and bool((buf[3] == -7.0).all())
+
+
+def test_detector_letterbox_rejects_other_geometries(engine):
+    d = torch.zeros((1, 1000, 1920, 3), dtype=torch.uint8, device="cuda")
+    with pytest.raises(Exception):
+        engine.preprocess_with_detector_input(d)                 # letterboxes to 960x500
+    with pytest.raises(Exception):
+        engine.preprocess_with_detector_input(torch.zeros((1, 1080, 1920, 3), dtype=torch.uint8, device="cuda"), imgsz=640)
+
+
 # ------------------------------------------------------------------------------------------------
 # fixed-K mode (north-star stress shape): same seeded hypothesis set on both sides
 # ------------------------------------------------------------------------------------------------
@@ -610,6 +639,24 @@ def test_sharded_clip_equals_reference_dict(golden_dir, world, name):
         p.join(300)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_streamed_run_sharded_equals_the_whole_clip(golden_dir):
+    """run_sharded fed chunk by chunk (the fit of a chunk runs on a side stream under the next chunk's K1 / decode) returns
+    the dict it returns for the whole tensor, which is the unmodified reference's."""
+    from conftest import cadence_clip
+    from eagle_b200 import synthetic
+    from eagle_b200.coordinate_model import GeometryPath
+    from eagle_b200.sharding import run_sharded
+    g, clip = cadence_clip(os.path.join(golden_dir, "ref_cadence_retry_720p.npz"))
+    n, w, h = int(g["n_frames"]), int(g["width"]), int(g["height"])
+    path = GeometryPath("cuda:0")
+    hm = torch.from_numpy(clip["heatmaps"]).cuda()
+    frames = torch.randint(0, 255, (n, h, w, 3), dtype=torch.uint8, device="cuda")
+    for step in (1, 4, 7):
+        res = run_sharded(path, (hm[s:s + step] for s in range(0, n, step)), clip["objects"], w, h, fps=int(g["fps"]), homography_interval=5,
+                          frames_local=(frames[s:s + step] for s in range(0, n, step)))
+        assert json.dumps(res, default=float, sort_keys=True) == str(g["result_json"]), step
 
 
 def test_decode_from_logits_equals_sigmoid_then_decode(engine):

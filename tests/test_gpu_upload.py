@@ -47,3 +47,48 @@ def test_repeated_uploads_reuse_the_rings(engine):
         frames = [rng.integers(0, 256, (270, 480, 3), dtype=np.uint8) for _ in range(16)]
         engine.upload_frames(frames, dev, threads=2 + rep)
         assert np.array_equal(dev.cpu().numpy(), np.stack(frames))
+
+
+def test_two_concurrent_uploads_are_byte_exact(engine):
+    """Two calls at once are served from separate rings (the streaming layer starts chunk c+1's upload while chunk c's
+    drains); a third one queues behind them."""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(3)
+    sets = [[rng.integers(0, 256, (540, 960, 3), dtype=np.uint8) for _ in range(24)] for _ in range(3)]
+    devs = [torch.zeros((24, 540, 960, 3), dtype=torch.uint8, device="cuda") for _ in range(3)]
+    for rep in range(3):
+        with ThreadPoolExecutor(3) as pool:
+            list(pool.map(lambda k: engine.upload_frames(sets[k], devs[k], threads=3), range(3)))
+        for k in range(3):
+            assert np.array_equal(devs[k].cpu().numpy(), np.stack(sets[k])), (rep, k)
+            devs[k].zero_()
+
+
+def test_api_with_two_uploads_in_flight_returns_the_same_dict():
+    """DenseStream.uploads_in_flight = 2 changes when the uploads are started, not what is computed."""
+    import json
+    from eagle_b200 import synthetic
+    from eagle_b200.coordinate_model import CoordinateModel
+    clip = synthetic.make_clip(23, 640, 360, seed=9, with_frames=True, ghost_prob=0.05)
+    hm = torch.from_numpy(clip["heatmaps"]).cuda()
+    out = []
+    for inflight in (1, 2):
+        st = {"i": 0, "h": 0}
+
+        def detector(_f):
+            st["i"] += 1
+            return clip["objects"][st["i"] - 1]
+
+        def network(x):
+            s = st["h"]
+            st["h"] += x.shape[0]
+            return hm[s:s + x.shape[0]]
+
+        model = CoordinateModel(keypoint_model=network, detect_objects=detector, chunk=5)
+        model.network_batch = 5
+        model.uploads_in_flight = inflight
+        res = model.get_coordinates(list(clip["frames"]), fps=5, num_homography=5, num_keypoint_detection=5, verbose=False)
+        assert len(res) == 23
+        out.append(json.dumps(res, default=float))
+        model._stream.close()
+    assert out[0] == out[1]

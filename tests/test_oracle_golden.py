@@ -235,3 +235,22 @@ def test_goldens_belong_to_this_opencv(golden_dir):
             stamped += 1
             assert v == cv2.__version__, (path, v)
     assert stamped >= 4
+
+
+def test_letterbox_geometry_restatement_and_host_mirror_agree():
+    """The detector-input geometry (ultralytics LetterBox, restated: oracle/preprocess.py) against the product's host helper,
+    and the restated tensor's basic facts: 16:9 frames at imgsz 960 give 544x960 with the resized image in rows 2..541."""
+    import cv2
+    from eagle_b200.engine import letterbox_geometry as product
+    from oracle import preprocess
+    for h, w, imgsz in [(1080, 1920, 960), (720, 1280, 960), (2160, 3840, 960), (1080, 1920, 640), (1000, 1920, 960), (480, 854, 960),
+                        (1080, 1920, 1280), (600, 800, 960), (1920, 1080, 960)]:
+        nw, nh, left, top, right, bottom = preprocess.letterbox_geometry(h, w, imgsz)
+        assert product(h, w, imgsz) == (nw, nh, left, top, nw + left + right, nh + top + bottom), (h, w, imgsz)
+        assert (nw + left + right) % 32 == 0 or nw + left + right == imgsz
+    fr = np.random.default_rng(5).integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+    t = preprocess.letterbox_reference_calls(fr)
+    assert t.shape == (3, 544, 960) and t.dtype == np.float32
+    assert np.all(t[:, :2] == np.float32(114) / np.float32(255)) and np.all(t[:, 542:] == np.float32(114) / np.float32(255))
+    small = cv2.resize(fr, (960, 540), interpolation=cv2.INTER_LINEAR)
+    assert np.array_equal(t[:, 2:542], (small[..., ::-1].transpose(2, 0, 1).astype(np.float32) / np.float32(255)))
