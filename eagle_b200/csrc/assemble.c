@@ -27,6 +27,13 @@ static int get_buf(PyObject* o, Py_buffer* b, Py_ssize_t itemsize, const char* n
     return 0;
 }
 
+/* The records are plain acyclic data (dicts / lists / tuples of numbers and strings) created here and handed over
+ * whole, millions of containers for a full match.  Left tracked, the first allocation after the assembly sends the cyclic
+ * collector over every one of them (seconds for 135 k frames, measured); CPython itself untracks dicts and tuples of
+ * atoms for this reason, and the same is done here for every container this file creates, once it is complete.  A dict
+ * re-tracks itself when a collectable value is stored into it later, so user code that extends the records is unaffected. */
+#define UNTRACK(o) PyObject_GC_UnTrack((PyObject*)(o))
+
 /* np.array(bbox, dtype=np.uint16).tolist() for the common case of a list of four in-range Python ints;
  * anything else goes through the Python fallback (which makes the numpy round trip). */
 static PyObject* bbox_list(PyObject* bbox, PyObject* fallback) {
@@ -218,6 +225,7 @@ static PyObject* py_assemble(PyObject* self, PyObject* args) {
                     if (!val) { Py_XDECREF(a); Py_XDECREF(b); Py_DECREF(kps); goto fail; }
                     PyList_SET_ITEM(val, 0, a);
                     PyList_SET_ITEM(val, 1, b);
+                    UNTRACK(val);
                 } else {
                     PyObject *a = PyLong_FromLong(x), *b = PyLong_FromLong(y);
                     if (as_np && a && b) {  /* the reference holds numpy integers here (they reach json.dump's default=) */
@@ -229,11 +237,13 @@ static PyObject* py_assemble(PyObject* self, PyObject* args) {
                     if (!val) { Py_XDECREF(a); Py_XDECREF(b); Py_DECREF(kps); goto fail; }
                     PyTuple_SET_ITEM(val, 0, a);
                     PyTuple_SET_ITEM(val, 1, b);
+                    UNTRACK(val);
                 }
                 const int rc = PyDict_SetItem(kps, PyTuple_GET_ITEM(names, c), val);
                 Py_DECREF(val);
                 if (rc < 0) { Py_DECREF(kps); goto fail; }
             }
+            UNTRACK(kps);
             /* ---- "Coordinates" ---- */
             PyObject* objects = PyList_GET_ITEM(objs, k);
             PyObject* indiv = PyDict_New();
@@ -267,6 +277,7 @@ static PyObject* py_assemble(PyObject* self, PyObject* args) {
                     PyObject* conf = PyObject_GetItem(obj, s_conf);
                     Py_XDECREF(bb_in);
                     if (!rec || !key || !bb || !conf) { Py_XDECREF(rec); Py_XDECREF(key); Py_XDECREF(bb); Py_XDECREF(conf); bad = 1; break; }
+                    if (PyList_CheckExact(bb) && Py_REFCNT(bb) == 1) UNTRACK(bb);   /* a fresh list of four ints */
                     int rc = PyDict_SetItem(rec, s_bbox, bb) | PyDict_SetItem(rec, s_conf, conf);
                     Py_DECREF(bb); Py_DECREF(conf);
                     if (have_h && ibp[k * P + p]) {
@@ -276,6 +287,7 @@ static PyObject* py_assemble(PyObject* self, PyObject* args) {
                         else {
                             PyList_SET_ITEM(tc, 0, a);
                             PyList_SET_ITEM(tc, 1, b);
+                            UNTRACK(tc);
                             rc |= PyDict_SetItem(rec, s_tc, tc);
                             Py_DECREF(tc);
                         }
@@ -287,6 +299,7 @@ static PyObject* py_assemble(PyObject* self, PyObject* args) {
                             Py_DECREF(foot);
                         }
                     }
+                    UNTRACK(rec);
                     if (rc == 0) rc = PyDict_SetItem(d, key, rec);
                     Py_DECREF(rec); Py_DECREF(key);
                     if (rc) { bad = 1; break; }
@@ -294,6 +307,12 @@ static PyObject* py_assemble(PyObject* self, PyObject* args) {
                 }
             }
             if (bad) { Py_DECREF(indiv); Py_DECREF(kps); goto fail; }
+            {   /* the class dicts are complete now */
+                Py_ssize_t pos3 = 0;
+                PyObject *ck, *cv;
+                while (PyDict_Next(indiv, &pos3, &ck, &cv)) UNTRACK(cv);
+                UNTRACK(indiv);
+            }
             /* ---- "Boundaries" ---- */
             PyObject* bl = PyList_New(4);
             if (!bl) { Py_DECREF(indiv); Py_DECREF(kps); goto fail; }
@@ -307,11 +326,13 @@ static PyObject* py_assemble(PyObject* self, PyObject* args) {
                     Py_INCREF(e);
                     PyTuple_SET_ITEM(t, 0, v);
                     PyTuple_SET_ITEM(t, 1, e);
+                    UNTRACK(t);
                     PyList_SET_ITEM(bl, q, t);
                 }
             } else {
                 for (int q = 0; q < 4; ++q) { Py_INCREF(Py_None); PyList_SET_ITEM(bl, q, Py_None); }
             }
+            UNTRACK(bl);
             /* ---- the frame's record ---- */
             const long long sec = (long long)(i / fps);
             PyObject* tm = PyUnicode_FromFormat("%02lld:%02lld", sec / 60, sec % 60);
@@ -321,6 +342,7 @@ static PyObject* py_assemble(PyObject* self, PyObject* args) {
             if (rc == 0)
                 rc = PyDict_SetItem(rec, s_coords, indiv) | PyDict_SetItem(rec, s_time, tm) | PyDict_SetItem(rec, s_kps, kps) |
                      PyDict_SetItem(rec, s_bounds, bl);
+            if (rc == 0) UNTRACK(rec);
             if (rc == 0) rc = PyDict_SetItem(out, idx, rec);
             Py_XDECREF(tm); Py_XDECREF(rec); Py_XDECREF(idx);
             Py_DECREF(bl); Py_DECREF(indiv); Py_DECREF(kps);

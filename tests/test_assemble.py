@@ -95,3 +95,31 @@ def test_packed_record_round_trip():
     back = unpack_record(np.concatenate([buf, np.zeros((3, buf.shape[1]), np.uint8)]), n, P)
     for name, dt, shape in record_layout(P):
         assert back[name].dtype == dt and np.array_equal(back[name], cols[name])
+
+
+def test_records_are_untracked_by_the_cyclic_collector():
+    """The assembler's containers are acyclic plain data and leave the collector's lists (a generation-2 pass over the
+    records of a full match costs seconds); a dict the caller extends with a collectable value tracks itself again."""
+    import gc
+
+    import numpy as np
+
+    from eagle_b200.coordinate_model import assemble_frames
+    F, P = 3, 2
+    xy = np.arange(F * 57 * 2, dtype=np.int32).reshape(F, 57, 2); order = np.tile(np.arange(64, dtype=np.uint8), (F, 1))
+    count = np.full((F, 2), 6, np.int32); inl = np.full(F, (1 << 40) - 1, np.int64); status = np.zeros(F, np.int32)
+    att = np.array([1, 0, 1], np.uint8); hi = np.array([0, 0, -1], np.int32)
+    ci = np.ones((F, P, 2), np.int64); ib = np.array([[1, 0]] * F, np.uint8); bd = np.array([[1.0, 2.0, 3.0, 4.0]] * F)
+    objs = [{"Player": {1: {"BBox": [1, 2, 3, 4], "Confidence": 0.5, "Bottom_center": [2, 4]}}, "Goalkeeper": {},
+             "Ball": {7: {"BBox": [5, 6, 7, 70000], "Confidence": 0.25, "Bottom_center": [6, 8]}}} for _ in range(F)]
+    res = assemble_frames(objs, 25, 0, xy, order, count, None, inl, status, att, hi, ci, ib, bd)
+    for r in res.values():
+        parts = [r, r["Coordinates"], r["Keypoints"], r["Boundaries"], *r["Coordinates"].values(), *r["Keypoints"].values()]
+        parts += [o for c in r["Coordinates"].values() for o in c.values()] + [o["BBox"] for c in r["Coordinates"].values() for o in c.values()]
+        parts += [b for b in r["Boundaries"] if b is not None]
+        assert not any(gc.is_tracked(p) for p in parts)
+    assert gc.is_tracked(res)
+    r = res[0]
+    r["Coordinates"]["Extra"] = {"k": []}
+    assert gc.is_tracked(r["Coordinates"])
+    assert objs[0]["Ball"][7]["Bottom_center"] == [6, 8] and gc.is_tracked(objs[0]["Ball"][7]["Bottom_center"])   # the caller's own lists are left alone
