@@ -111,7 +111,7 @@ def test_records_are_untracked_by_the_cyclic_collector():
     att = np.array([1, 0, 1], np.uint8); hi = np.array([0, 0, -1], np.int32)
     ci = np.ones((F, P, 2), np.int64); ib = np.array([[1, 0]] * F, np.uint8); bd = np.array([[1.0, 2.0, 3.0, 4.0]] * F)
     objs = [{"Player": {1: {"BBox": [1, 2, 3, 4], "Confidence": 0.5, "Bottom_center": [2, 4]}}, "Goalkeeper": {},
-             "Ball": {7: {"BBox": [5, 6, 7, 70000], "Confidence": 0.25, "Bottom_center": [6, 8]}}} for _ in range(F)]
+             "Ball": {7: {"BBox": (5, 6, 7, 8), "Confidence": 0.25, "Bottom_center": [6, 8]}}} for _ in range(F)]
     res = assemble_frames(objs, 25, 0, xy, order, count, None, inl, status, att, hi, ci, ib, bd)
     for r in res.values():
         parts = [r, r["Coordinates"], r["Keypoints"], r["Boundaries"], *r["Coordinates"].values(), *r["Keypoints"].values()]
