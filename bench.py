@@ -364,14 +364,33 @@ def main():
     del evs
     peak, peak_src = peaks()
 
-    def hbm_roofline(kernel, bytes_per_frame, ms, profile_file):
+    def captured_traffic(summary_file):
+        """DRAM bytes per launch from the kept ncu --set full capture of this kernel -- only if the kernel source is still
+        the file the capture was taken from (sha-256 recorded with it) and the launch is the captured shape; else None."""
+        import hashlib
+        d = profile_json(summary_file)
+        if not d or F != FRAMES_PER_GPU:
+            return None
+        for rel, sha in d.get("source_sha256", {}).items():
+            try:
+                if hashlib.sha256(open(os.path.join(ROOT, rel), "rb").read()).hexdigest() != sha:
+                    return None
+            except OSError:
+                return None
+        return d.get("traffic_bytes_per_launch")
+
+    def hbm_roofline(kernel, bytes_per_frame, ms, profile_file, summary_file=None):
         a = F * bytes_per_frame / (ms * 1e-3) / 1e9
+        traffic = captured_traffic(summary_file) if summary_file else None
+        note = (f"dram__bytes_read.sum + dram__bytes_write.sum of one launch of this shape in the kept ncu --set full capture (profiles/{summary_file}, "
+                f"raw page profiles/{profile_file}; the kernel source is unchanged since: sha-256 checked); algorithmic bytes per launch {F * bytes_per_frame}"
+                if traffic is not None else f"not measured in this run; the ncu capture of this kernel is kept in profiles/{profile_file}")
         return {"kernel": kernel, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_frame": bytes_per_frame, "launch_ms": ms, "share_of_step": ms / sus_ms,
-                "traffic": None, "traffic_note": f"not measured in this run; the ncu capture of this kernel is kept in profiles/{profile_file}"}
+                "traffic": traffic, "traffic_note": note}
 
-    roofline = hbm_roofline("egl::preprocess_kernel<4,true> (K1: uint8 BGR frames -> float32 network input)", K1_BYTES, k1_ms,
-                            "r1_prof_preprocess_raw.csv")
+    roofline = hbm_roofline("egl::preprocess_kernel<4,true,false,true> (K1: uint8 BGR frames -> float32 network input; the synthesis/fit/"
+                            "cadence/projection kernels run next to it on a side stream)", K1_BYTES, k1_ms, "r2_prof_preprocess_pair_raw.csv", "r2_k1_ncu.json")
     roofline_decode = hbm_roofline("egl::argmax_ldg_kernel (K2 heatmap decode; interval also holds postprocess_kernel, <1%)", HM_BYTES, k2_ms,
                                    "r1_prof_argmax_ldg_raw.csv")
     sustained = {"value": F * world / (sus_ms * 1e-3), "unit": "frames/s", "steps": n_sus, "ms_per_step": sus_ms,
