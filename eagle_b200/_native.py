@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libeagle_b200.so")
+# EAGLE_B200_LIBRARY: another build of the same library (the measurement build under tools/_variants/, a debug build)
+LIB_PATH = os.environ.get("EAGLE_B200_LIBRARY") or os.path.join(_PKG, "libeagle_b200.so")
 
 ABI_VERSION = 1
 FIT_OK, FIT_FEW_POINTS, FIT_NO_MODEL, FIT_SKIPPED = 0, 1, 2, 3

@@ -332,6 +332,7 @@ struct FixedKPrep {
     uint8_t ch[kMaxPts];
     FixedKNorm nm;
     int N, ok;
+    unsigned cmax_bits;   // bit pattern of the largest |normalised coordinate| of the frame
     unsigned long long used;
 };
 
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(kPrepWarps * 32) fixedk_prepare_kernel(FitArgs
         o.ok = n >= 4 && aX > 0.f && aY > 0.f;
         o.nm = nm;
     }
+    unsigned cmax = 0;
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
         const int i = pass * 32 + lane;
@@ -376,24 +378,40 @@ __global__ void __launch_bounds__(kPrepWarps * 32) fixedk_prepare_kernel(FitArgs
         o.ps[i] = make_float4(q[0], q[2], q[1], q[3]);
         o.sx[i] = pl.sx[i]; o.sy[i] = pl.sy[i]; o.dx[i] = pl.dx[i]; o.dy[i] = pl.dy[i];
         o.ch[i] = pl.ch[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cmax = max(cmax, __float_as_uint(q[k]) & 0x7fffffffu);
     }
+    cmax = __reduce_max_sync(kFull, cmax);
+    if (lane == 0) o.cmax_bits = cmax;
 }
 
-__global__ void __launch_bounds__(kFixedThreads, 6) ransac_fixedk_kernel(FitArgs a, float inv_thr, double thr, const FixedKPrep* prep) {
+// Template parameters (the shipped build instantiates one combination; -DEGL_BENCH_VARIANTS builds hold the others for
+// tools/fixedk_variants.py): CTAs per SM asked of the register allocator, unroll of the scoring loop, and whether the warps
+// take their batches of 32 hypotheses from a shared counter instead of a fixed stride (the result does not depend on which
+// warp scores which hypothesis: most inliers, ties to the lowest hypothesis index).
+// kSignCount: where no NaN can arise (every |H entry| < 1e15 and every normalised coordinate < 1e3, checked per batch) the
+// inlier test  t = e - w^2 <= 0  is evaluated as the SIGN BIT of  -t = fma(w, w, -e)  (the exact negation: round-to-nearest
+// is symmetric; an exact zero is +0 on both sides) and accumulated with one shift-add (LEA.HI) per hypothesis and point
+// instead of a compare and a predicated add; padding rows (x' = +inf) and overflowed residuals give -inf = outlier on
+// both paths.  Batches that fail the range check take the compare-and-add loop, so the counts are the specification's
+// in every case (oracle/ransac_f32.c).
+template <int kMinBlocks, int kUnroll, bool kDynamic, bool kSignCount = true>
+__global__ void __launch_bounds__(kFixedThreads, kMinBlocks) ransac_fixedk_kernel(FitArgs a, float inv_thr, double thr, const FixedKPrep* prep) {
+    static_assert(kUnroll == 2 || kUnroll == 4 || kUnroll == 8, "scoring loop unroll");
     __shared__ PointList s_pl;
     // normalised points as (X', x', Y', y') -- image/pitch pairs for the sample test -- replicated into the eight
     // 16-byte columns of a 128-byte row: lane l gathers from column l & 7, so the eight lanes of a quarter warp never
     // share a bank whatever indices they drew (a random LDS.128 gather from an unreplicated table averages 3
     // wavefronts per quarter warp)
     __shared__ float4 s_ps[kMaxPts][8];
-    __shared__ float4 s_bc[kMaxPts + 4][2];  // for the scoring loop: (X',X',Y',Y') (-x',-x',-y',-y'), padded to a multiple of 4
+    __shared__ float4 s_bc[kMaxPts + 8][2];  // for the scoring loop: (X',X',Y',Y') (-x',-x',-y',-y'), padded to a multiple of the unroll
     __shared__ int s_cnt[kFixedWarps], s_hyp[kFixedWarps];
     __shared__ uint32_t s_qi[kFixedWarps][kFixedQueue];  // accepted samples: four packed indices ...
     __shared__ int s_qh[kFixedWarps][kFixedQueue];       // ... and the hypothesis number
     __shared__ uint32_t s_pi[kFixedWarps * 64];          // what the warps had left over, pooled
     __shared__ int s_ph[kFixedWarps * 64];
     __shared__ FixedKNorm s_nm;
-    __shared__ int s_N, s_pool;
+    __shared__ int s_N, s_pool, s_next;
     __shared__ unsigned long long s_used;
     const int f = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -403,6 +421,7 @@ __global__ void __launch_bounds__(kFixedThreads, 6) ransac_fixedk_kernel(FitArgs
     }
     const FixedKPrep& in = prep[f];
     const int N = in.N;
+    const bool coords_small = in.cmax_bits < 0x447a0000u;  // every normalised coordinate of the frame below 1000 (NaN / inf order above)
     if (N < 4 || !in.ok) {
         if (tid == 0) park(a, f, N < 4 ? EGL_FIT_FEW_POINTS : EGL_FIT_NO_MODEL, N, 0, -1, 0, nullptr, 0, in.used);
         return;
@@ -412,8 +431,9 @@ __global__ void __launch_bounds__(kFixedThreads, 6) ransac_fixedk_kernel(FitArgs
         s_used = in.used;
         s_nm = in.nm;
         s_pool = 0;
+        s_next = 0;
     }
-    const int N4 = (N + 3) & ~3;
+    const int N4 = (N + kUnroll - 1) & ~(kUnroll - 1);
     for (int i = tid; i < N4; i += kFixedThreads) {
         if (i < N) {
             const float4 q = in.ps[i];  // (X', x', Y', y')
@@ -422,8 +442,8 @@ __global__ void __launch_bounds__(kFixedThreads, 6) ransac_fixedk_kernel(FitArgs
             s_bc[i][0] = make_float4(q.x, q.x, q.z, q.z);
             s_bc[i][1] = make_float4(-q.y, -q.y, -q.w, -q.w);
             s_pl.sx[i] = in.sx[i]; s_pl.sy[i] = in.sy[i]; s_pl.dx[i] = in.dx[i]; s_pl.dy[i] = in.dy[i];
-        } else {  // padding rows: NaN residuals are never counted
-            const float q = __int_as_float(0x7fffffff);
+        } else {  // padding rows: w = 1 and an infinite residual, never an inlier (and never a NaN)
+            const float q = __int_as_float(0x7f800000);
             s_bc[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
             s_bc[i][1] = make_float4(q, q, q, q);
         }
@@ -462,12 +482,33 @@ __global__ void __launch_bounds__(kFixedThreads, 6) ransac_fixedk_kernel(FitArgs
         S[1] = det3_v<float2>(X[1], Y[1], X[2], Y[2], X[3], Y[3]);
         S[2] = det3_v<float2>(X[0], Y[0], X[2], Y[2], X[3], Y[3]);
         S[3] = det3_v<float2>(X[0], Y[0], X[1], Y[1], X[3], Y[3]);
-        const bool2 fin = fixedk_solve_v<float2>(X, Y, x, y, S, H);
+        float2 hs;
+        const bool2 fin = fixedk_solve_v<float2>(X, Y, x, y, S, H, &hs);
         const float2 one = make_float2(1.f, 1.f);
         int c0 = 0, c1 = 0;
-        for (int i = 0; i < N4; i += 4) {
+        const bool in_range = hs.x < 1e15f && hs.y < 1e15f;
+        if (kSignCount && coords_small && __all_sync(kFull, in_range)) {
+            unsigned o0 = 0, o1 = 0;   // outliers (padding rows included)
+            for (int i = 0; i < N4; i += kUnroll) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < kUnroll; ++j) {
+                    const float4 u = lds128(bc_addr + 32u * (i + j)), m = lds128(bc_addr + 32u * (i + j) + 16u);
+                    const float2 PX = make_float2(u.x, u.y), PY = make_float2(u.z, u.w), nx = make_float2(m.x, m.y), ny = make_float2(m.z, m.w);
+                    const float2 w = L::fma(H[6], PX, L::fma(H[7], PY, one));
+                    const float2 ex = L::fma(nx, w, L::fma(H[0], PX, L::fma(H[1], PY, H[2])));
+                    const float2 ey = L::fma(ny, w, L::fma(H[3], PX, L::fma(H[4], PY, H[5])));
+                    const float2 e = L::fma(ex, ex, L::mul(ey, ey));
+                    const float2 tn = L::fma(w, w, L::neg(e));
+                    o0 += __float_as_uint(tn.x) >> 31;
+                    o1 += __float_as_uint(tn.y) >> 31;
+                }
+            }
+            c0 = N4 - (int)o0;
+            c1 = N4 - (int)o1;
+        } else {
+        for (int i = 0; i < N4; i += kUnroll) {
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) {
                 const float4 u = lds128(bc_addr + 32u * (i + j)), m = lds128(bc_addr + 32u * (i + j) + 16u);
                 const float2 PX = make_float2(u.x, u.y), PY = make_float2(u.z, u.w), nx = make_float2(m.x, m.y), ny = make_float2(m.z, m.w);
                 const float2 w = L::fma(H[6], PX, L::fma(H[7], PY, one));
@@ -479,10 +520,16 @@ __global__ void __launch_bounds__(kFixedThreads, 6) ransac_fixedk_kernel(FitArgs
                 count_if_le0(c1, t.y);
             }
         }
+        }
         if (v0 && fin.x && (c0 > best_cnt || (c0 == best_cnt && ha < best_h))) { best_cnt = c0; best_h = ha; }
         if (v1 && fin.y && (c1 > best_cnt || (c1 == best_cnt && hb < best_h))) { best_cnt = c1; best_h = hb; }
     };
-    for (int base = warp * 32; base < a.K; base += kFixedThreads) {
+    for (int base = warp * 32;; base += kFixedThreads) {
+        if (kDynamic) {
+            if (lane == 0) base = atomicAdd(&s_next, 32);
+            base = __shfl_sync(kFull, base, 0);
+        }
+        if (base >= a.K) break;
         const int h = base + lane;
         int idx[4];
         bool ok = fixedk_sample(a, f, key, h, N, idx);
@@ -1174,7 +1221,28 @@ static int fit_impl(const char* who, const int32_t* kp_xy, const uint8_t* kp_ord
                               "egl_fit_homography: scratch allocation");
         if (rc0) return rc0;
         fixedk_prepare_kernel<<<(F + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, 0, s>>>(a, (float)(1.0 / thr), prep);
-        ransac_fixedk_kernel<<<F, kFixedThreads, 0, s>>>(a, (float)(1.0 / thr), thr, prep);
+        int fk_variant = 0;
+#ifdef EGL_BENCH_VARIANTS
+        static const char* fk_env = getenv("EGL_FIXEDK_VARIANT");
+        fk_variant = fk_env ? atoi(fk_env) : 0;
+#endif
+        const float it = (float)(1.0 / thr);
+        switch (fk_variant) {
+#ifdef EGL_BENCH_VARIANTS
+            case 1: ransac_fixedk_kernel<6, 4, true><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
+            case 2: ransac_fixedk_kernel<6, 8, false><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
+            case 3: ransac_fixedk_kernel<6, 8, true><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
+            case 4: ransac_fixedk_kernel<7, 4, false><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
+            case 5: ransac_fixedk_kernel<7, 2, false><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
+            case 6: ransac_fixedk_kernel<7, 2, true><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
+            case 7: ransac_fixedk_kernel<8, 2, true><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
+            case 8: ransac_fixedk_kernel<6, 2, true><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
+            case 9: ransac_fixedk_kernel<5, 8, true><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
+            case 10: ransac_fixedk_kernel<6, 4, false, false><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
+            case 11: ransac_fixedk_kernel<6, 8, false, true><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
+#endif
+            default: ransac_fixedk_kernel<6, 4, false, true><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
+        }
         cudaFreeAsync(prep, s);
     }
     int rc = cuda_status(cudaGetLastError(), "egl_fit_homography: hypothesis kernel launch");

@@ -1021,7 +1021,7 @@ EGL_HD typename lane_ops<V>::M fixedk_check_v(const V* X, const V* Y, const V* x
 // Minimal solve of an accepted sample: H[8] (h33 = 1) and the largest-|entry| guard; returns "all entries finite".
 // X, Y, x, y are permuted in place by the pivoting.
 template <class V>
-EGL_HD typename lane_ops<V>::M fixedk_solve_v(V* X, V* Y, V* x, V* y, const V* S, V* H /*8*/) {
+EGL_HD typename lane_ops<V>::M fixedk_solve_v(V* X, V* Y, V* x, V* y, const V* S, V* H /*8*/, V* abs_sum = nullptr) {
     typedef lane_ops<V> L;
     // left null vector of [X Y 1]: n0 = S123, n1 = -S023, n2 = S013, n3 = -S012
     V n[4] = {S[1], L::neg(S[2]), S[3], L::neg(S[0])};
@@ -1073,6 +1073,7 @@ EGL_UNROLL
     V acc = L::set(0.f);
 EGL_UNROLL
     for (int k = 0; k < 8; ++k) acc = L::add(acc, L::abs(H[k]));
+    if (abs_sum) *abs_sum = acc;          // sum of |entries|: an upper bound of every entry, for the caller's range checks
     return L::lt(acc, L::set(INFINITY));  // false for inf / NaN entries
 }
 

@@ -360,6 +360,29 @@ def test_preprocess_matches_reference_calls(engine, w, h):
         assert np.array_equal(back, cv2.resize(fr[i][:, :, ::-1], (960, 540), interpolation=cv2.INTER_LINEAR))
 
 
+def test_preprocess_1080p_views_and_strides(engine):
+    """The exact-2x code (word loads + dp4a) on frames that are not one dense block: rows with padding (16-byte multiple:
+    bulk copies; 4-byte multiple and an odd number: staged loads), a frame range starting inside a larger tensor, a single
+    frame -- always the uint8 image cv2.resize makes, and the same floats as the dense call."""
+    import cv2
+    from oracle import preprocess
+    rng = np.random.default_rng(11)
+    fr = rng.integers(0, 256, (3, 1080, 1920, 3), dtype=np.uint8)
+    dense = engine.preprocess(torch.from_numpy(fr).cuda())
+    mean, denom = preprocess.normalise_constants()
+    back = np.rint(dense[1].cpu().numpy().transpose(1, 2, 0) / denom + mean).astype(np.uint8)
+    assert np.array_equal(back, cv2.resize(fr[1][:, :, ::-1], (960, 540), interpolation=cv2.INTER_LINEAR))
+    for pad_px in (16, 4, 1):     # row stride 3 * (1920 + pad_px) bytes
+        wide = torch.zeros((4, 1080, 1920 + pad_px, 3), dtype=torch.uint8, device="cuda")
+        wide[1:, :, :1920] = torch.from_numpy(fr).cuda()
+        view = wide[1:, :, :1920]
+        assert not view.is_contiguous()
+        assert torch.equal(engine.preprocess(view), dense), pad_px
+        x, y = engine.preprocess_with_detector_input(view)
+        assert torch.equal(x, dense) and torch.equal(y[:, :, 2:542], engine.preprocess_with_detector_input(torch.from_numpy(fr).cuda())[1][:, :, 2:542])
+    assert torch.equal(engine.preprocess(torch.from_numpy(fr[2:3]).cuda()), dense[2:3])
+
+
 def test_preprocess_golden_checksums(engine, golden_dir):
     from oracle import preprocess
     cases = json.load(open(os.path.join(golden_dir, "resize_cv2.json")))["cases"]
