@@ -394,8 +394,11 @@ __global__ void __launch_bounds__(kPrepWarps * 32) fixedk_prepare_kernel(FitArgs
 // is symmetric; an exact zero is +0 on both sides) and accumulated with one shift-add (LEA.HI) per hypothesis and point
 // instead of a compare and a predicated add; padding rows (x' = +inf) and overflowed residuals give -inf = outlier on
 // both paths.  Batches that fail the range check take the compare-and-add loop, so the counts are the specification's
-// in every case (oracle/ransac_f32.c).
-template <int kMinBlocks, int kUnroll, bool kDynamic, bool kSignCount = true>
+// in every case (oracle/ransac_f32.c).  MEASURED AND NOT SHIPPED: 8 of the 73 instructions of a four-point loop body go
+// away, issue activity falls from 66.8 to 64.6 % and the kernel takes exactly as long (1.276 against 1.275 ms for 20 k
+// frames, outputs bit-identical; profiles/r2_fixedk_variants.txt) -- the loop waits on the FMA pipe
+// (stall_math_pipe_throttle 2.1 per issue), not on issue slots.  Kept as a variant of the measurement build.
+template <int kMinBlocks, int kUnroll, bool kDynamic, bool kSignCount = false>
 __global__ void __launch_bounds__(kFixedThreads, kMinBlocks) ransac_fixedk_kernel(FitArgs a, float inv_thr, double thr, const FixedKPrep* prep) {
     static_assert(kUnroll == 2 || kUnroll == 4 || kUnroll == 8, "scoring loop unroll");
     __shared__ PointList s_pl;
@@ -1238,10 +1241,11 @@ static int fit_impl(const char* who, const int32_t* kp_xy, const uint8_t* kp_ord
             case 7: ransac_fixedk_kernel<8, 2, true><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
             case 8: ransac_fixedk_kernel<6, 2, true><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
             case 9: ransac_fixedk_kernel<5, 8, true><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
-            case 10: ransac_fixedk_kernel<6, 4, false, false><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
+            case 10: ransac_fixedk_kernel<6, 4, false, true><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
             case 11: ransac_fixedk_kernel<6, 8, false, true><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
+            case 12: ransac_fixedk_kernel<6, 4, true, true><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
 #endif
-            default: ransac_fixedk_kernel<6, 4, false, true><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
+            default: ransac_fixedk_kernel<6, 4, false, false><<<F, kFixedThreads, 0, s>>>(a, it, thr, prep); break;
         }
         cudaFreeAsync(prep, s);
     }

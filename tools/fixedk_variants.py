@@ -12,8 +12,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-VARIANTS = {0: "6 CTAs, unroll 4, static, sign-bit count (shipped)", 10: "6, 4, static, compare + predicated add (shipped until now)",
-            11: "6, 8, static, sign-bit count", 1: "6, 4, dynamic, sign-bit count"}
+VARIANTS = {0: "6 CTAs, unroll 4, static, compare + predicated add (shipped)", 10: "6, 4, static, sign-bit count",
+            11: "6, 8, static, sign-bit count", 12: "6, 4, dynamic, sign-bit count"}
 # measured before the sign-bit count existed (profiles/r2_fixedk_variants_occupancy.txt): 7 and 8 CTAs per SM, unroll 2 / 8 and the
 # dynamic batch distribution were all 1.4 - 11.7 % slower than 6 CTAs / unroll 4 / static
 
