@@ -271,27 +271,14 @@ static int preprocess_impl(const uint8_t* frames, int F, int H, int W, size_t ro
         return 0;
     };
     // exact 2x decimation (1080p): word loads + dp4a (kPair); EGL_PREPROCESS_PAIR=0 in measurement builds selects the byte-wise code
-    bool pair = mean4 && W == 2 * kOutW;
+    bool pair = mean4 && W == 2 * kOutW && R == 4;
 #ifdef EGL_BENCH_VARIANTS
     static const char* pair_env = getenv("EGL_PREPROCESS_PAIR");
     if (pair_env && atoi(pair_env) == 0) pair = false;
 #endif
     int rc;
-    if (pair) {
-        if (R == 3 || R == 6) R = 4;
-        if (out2) {
-            switch (R) {
-                case 1: rc = launch(preprocess_kernel<1, true, true, true>, 1); break;
-                case 2: rc = launch(preprocess_kernel<2, true, true, true>, 2); break;
-                default: rc = launch(preprocess_kernel<4, true, true, true>, 4); break;
-            }
-        } else {
-            switch (R) {
-                case 1: rc = launch(preprocess_kernel<1, true, false, true>, 1); break;
-                case 2: rc = launch(preprocess_kernel<2, true, false, true>, 2); break;
-                default: rc = launch(preprocess_kernel<4, true, false, true>, 4); break;
-            }
-        }
+    if (pair) {   // 1920-pixel rows: eight row slots are 46 KB, so R is always 4 here
+        rc = out2 ? launch(preprocess_kernel<4, true, true, true>, 4) : launch(preprocess_kernel<4, true, false, true>, 4);
     } else if (out2) {
         if (R == 3 || R == 6) R = 4;
         if (mean4) {
